@@ -1,0 +1,262 @@
+"""ctypes binding of the CPU oracle (libmd_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing under motion_detection_b200/ imports this module.
+Each function names the reference code it restates (see md_oracle*.c headers for file:line).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+u8p = C.POINTER(C.c_uint8)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+i32p = C.POINTER(C.c_int32)
+i16p = C.POINTER(C.c_int16)
+
+
+def build(force=False):
+    """gcc-compile the restatement (oracle/Makefile)."""
+    so = os.path.join(_HERE, "libmd_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libmd_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.orc_glibc_rand.restype = C.c_int
+        _LIB.orc_pyr_levels.restype = C.c_int
+        _LIB.orc_lk_pyr.restype = C.c_int
+        _LIB.orc_grid_points.restype = C.c_int
+        _LIB.orc_flow_filter.restype = C.c_int
+        _LIB.orc_perspective_4pt.restype = C.c_int
+        _LIB.orc_fit_egomotion.restype = C.c_int
+        _LIB.orc_varflow.restype = C.c_int
+        _LIB.orc_fit_subspace.restype = C.c_int
+    return _LIB
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(u8p)
+
+
+def glibc_rand(seed, n):
+    """srand(seed); n x rand()  (outlier_detector.cpp:17,228)."""
+    st = (C.c_int32 * 36)()
+    lib().orc_glibc_srand(st, C.c_uint32(seed))
+    return [lib().orc_glibc_rand(st) for _ in range(n)]
+
+
+def gray(rgb):
+    rgb, p = _u8(rgb)
+    h, w, _ = rgb.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orc_gray_bgr2gray(p, w, h, w * 3, out.ctypes.data_as(u8p), w)
+    return out
+
+
+def pyr_down(img):
+    img, p = _u8(img)
+    h, w = img.shape
+    out = np.empty(((h + 1) // 2, (w + 1) // 2), np.uint8)
+    lib().orc_pyr_down(p, w, h, w, out.ctypes.data_as(u8p), out.shape[1])
+    return out
+
+
+def pyr_levels(w, h, win=40, max_level=5):
+    return lib().orc_pyr_levels(w, h, win, max_level)
+
+
+def pyramid(img, win=40, max_level=5):
+    lv = [np.ascontiguousarray(img, np.uint8)]
+    for _ in range(pyr_levels(img.shape[1], img.shape[0], win, max_level)):
+        lv.append(pyr_down(lv[-1]))
+    return lv
+
+
+def scharr(img):
+    img, p = _u8(img)
+    h, w = img.shape
+    out = np.empty((h, w, 2), np.int16)
+    lib().orc_scharr(p, w, h, w, out.ctypes.data_as(i16p))
+    return out
+
+
+def grid_points(w, h, ps):
+    n = lib().orc_grid_points(w, h, ps, None)
+    pts = np.empty((n, 2), np.float32)
+    lib().orc_grid_points(w, h, ps, pts.ctypes.data_as(f32p))
+    return pts
+
+
+def lk(prev, nxt, pts, win=40, max_level=5, max_iters=10, eps=0.03, min_eig=1e-3):
+    """cv::calcOpticalFlowPyrLK as called at optical_flow_calculator.cpp:71."""
+    prev, pp = _u8(prev)
+    nxt, np_ = _u8(nxt)
+    h, w = prev.shape
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    out = np.zeros_like(pts)
+    st = np.zeros(len(pts), np.uint8)
+    lib().orc_lk_pyr(pp, np_, w, h, w, pts.ctypes.data_as(f32p), len(pts), out.ctypes.data_as(f32p),
+                     st.ctypes.data_as(u8p), win, max_level, max_iters, C.c_double(eps), C.c_float(min_eig))
+    return out, st
+
+
+def flow_filter(p1, p2, status, min_vec):
+    p1 = np.ascontiguousarray(p1, np.float32)
+    p2 = np.ascontiguousarray(p2, np.float32)
+    status = np.ascontiguousarray(status, np.uint8)
+    n = len(status)
+    keep = np.zeros(n, np.uint8)
+    flow4 = np.zeros((n, 4), np.float64)
+    nv = lib().orc_flow_filter(p1.ctypes.data_as(f32p), p2.ctypes.data_as(f32p), status.ctypes.data_as(u8p), n,
+                               C.c_double(min_vec), keep.ctypes.data_as(u8p), flow4.ctypes.data_as(f64p))
+    return nv, keep, flow4
+
+
+def perspective_4pt(src, dst):
+    src = np.ascontiguousarray(src, np.float64)
+    dst = np.ascontiguousarray(dst, np.float64)
+    H = np.zeros(9, np.float64)
+    ok = lib().orc_perspective_4pt(src.ctypes.data_as(f64p), dst.ctypes.data_as(f64p), H.ctypes.data_as(f64p))
+    return ok, H.reshape(3, 3)
+
+
+MODE_FIRST4, MODE_RANSAC_HOMOGRAPHY, MODE_RANSAC_AFFINE = 0, 1, 2
+
+
+def fit_egomotion(p1, p2, keep, w, h, mode=MODE_RANSAC_HOMOGRAPHY, iters=50, thr=0.5, seed=1):
+    p1 = np.ascontiguousarray(p1, np.float32)
+    p2 = np.ascontiguousarray(p2, np.float32)
+    keep = np.ascontiguousarray(keep, np.uint8)
+    H = np.zeros(9, np.float64)
+    inl = np.zeros(len(keep), np.uint8)
+    n = lib().orc_fit_egomotion(p1.ctypes.data_as(f32p), p2.ctypes.data_as(f32p), keep.ctypes.data_as(u8p), len(keep),
+                                w, h, mode, iters, C.c_double(thr), C.c_uint32(seed), H.ctypes.data_as(f64p),
+                                inl.ctypes.data_as(u8p))
+    return n, H.reshape(3, 3), inl
+
+
+def warp_perspective(src, H):
+    src, p = _u8(src)
+    h, w = src.shape
+    H = np.ascontiguousarray(H, np.float64)
+    out = np.empty_like(src)
+    lib().orc_warp_perspective(p, w, h, w, H.ctypes.data_as(f64p), out.ctypes.data_as(u8p), w)
+    return out
+
+
+def absdiff_threshold(a, b, thresh=190):
+    a, pa = _u8(a)
+    b, pb = _u8(b)
+    h, w = a.shape
+    out = np.empty_like(a)
+    lib().orc_absdiff_threshold(pa, pb, w, h, w, thresh, out.ctypes.data_as(u8p), w)
+    return out
+
+
+def erode3(a):
+    a, pa = _u8(a)
+    h, w = a.shape
+    out = np.empty_like(a)
+    lib().orc_erode3(pa, w, h, w, out.ctypes.data_as(u8p), w)
+    return out
+
+
+def dilate3(a):
+    a, pa = _u8(a)
+    h, w = a.shape
+    out = np.empty_like(a)
+    lib().orc_dilate3(pa, w, h, w, out.ctypes.data_as(u8p), w)
+    return out
+
+
+def motion_mask(prev, cur, H, thresh=190, morph=True):
+    prev, pp = _u8(prev)
+    cur, pc = _u8(cur)
+    h, w = prev.shape
+    H = np.ascontiguousarray(H, np.float64)
+    out = np.empty_like(prev)
+    lib().orc_motion_mask(pp, pc, w, h, w, H.ctypes.data_as(f64p), thresh, 1 if morph else 0, out.ctypes.data_as(u8p), w)
+    return out
+
+
+def process_pair(prev, cur, pixel_step=10, min_vector_size=0.2, mode=MODE_RANSAC_HOMOGRAPHY, iters=50, thr=0.5,
+                 seed=1, thresh=190, morph=True, lk_kwargs=None):
+    """The oracle composition: grid LK -> filter -> H -> warp -> absdiff -> threshold -> erode -> dilate.
+    Follows OpticalFlowCalculator::calculateOpticalFlow (optical_flow_calculator.cpp:30-130) +
+    BackgroundSubtractor morphology (background_subtractor.cpp:31-32)."""
+    h, w = prev.shape
+    pts = grid_points(w, h, pixel_step)
+    p2, st = lk(prev, cur, pts, **(lk_kwargs or {}))
+    nv, keep, flow4 = flow_filter(pts, p2, st, min_vector_size)
+    ninl, H, inl = fit_egomotion(pts, p2, keep, w, h, mode, iters, thr, seed)
+    if ninl > 0:
+        mask = motion_mask(prev, cur, H, thresh, morph)
+    else:
+        mask = np.zeros_like(prev)
+    return dict(pts=pts, next=p2, status=st, keep=keep, flow4=flow4, num_vectors=nv, H=H, inliers=ninl,
+                inlier_mask=inl, mask=mask)
+
+
+def gaussian_blur_f32(img, sigma):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    out = np.empty_like(img)
+    lib().orc_gaussian_blur_f32(img.ctypes.data_as(f32p), w, h, out.ctypes.data_as(f32p), C.c_double(sigma))
+    return out
+
+
+def resize_linear_f32(img, dw, dh):
+    img = np.ascontiguousarray(img, np.float32)
+    h, w = img.shape
+    out = np.empty((dh, dw), np.float32)
+    lib().orc_resize_linear_f32(img.ctypes.data_as(f32p), w, h, out.ctypes.data_as(f32p), dw, dh)
+    return out
+
+
+def varflow(A, B, max_level=4, start_level=0, n1=2, n2=2, rho=2.8, alpha=1400.0, sigma=1.5, literal=True):
+    """VarFlow::CalcFlow with the parameters of OpticalFlowCalculator::varFlow (optical_flow_calculator.cpp:422-429)."""
+    A, pa = _u8(A)
+    B, pb = _u8(B)
+    h, w = A.shape
+    U = np.zeros((h, w), np.float32)
+    V = np.zeros((h, w), np.float32)
+    r = lib().orc_varflow(pa, pb, w, h, w, max_level, start_level, n1, n2, C.c_float(rho), C.c_float(alpha),
+                          C.c_float(sigma), U.ctypes.data_as(f32p), V.ctypes.data_as(f32p), 1 if literal else 0)
+    if r != 1:
+        raise RuntimeError("orc_varflow failed")
+    return U, V
+
+
+def fit_subspace(traj, num_motions=2, sigma=0.5, seed=1, forced_cols=None, iters=50):
+    """OutlierDetector::fitSubspace (outlier_detector.cpp:236-331). traj: [T][F][2] f32."""
+    traj = np.ascontiguousarray(traj, np.float32)
+    T, F, _ = traj.shape
+    d = 4 * num_motions
+    res = np.zeros(T, np.float32)
+    cols = np.zeros(d, np.int32)
+    outl = np.zeros(T, np.uint8)
+    thr = C.c_double(0)
+    fc = None
+    if forced_cols is not None:
+        fc_arr = np.ascontiguousarray(forced_cols, np.int32).reshape(-1, d)
+        iters = fc_arr.shape[0]
+        fc = fc_arr.ctypes.data_as(i32p)
+    n = lib().orc_fit_subspace(traj.ctypes.data_as(f32p), T, F, num_motions, C.c_double(sigma), C.c_uint32(seed), fc,
+                               iters, res.ctypes.data_as(f32p), cols.ctypes.data_as(i32p), outl.ctypes.data_as(u8p),
+                               C.byref(thr))
+    return n, res, cols, outl, thr.value
