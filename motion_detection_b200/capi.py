@@ -1,0 +1,289 @@
+"""ctypes binding of libmotion_b200.so (include/motion_b200.h).
+
+This is the ONLY compute path of the package: if the CUDA library is missing or no sm_100 GPU is usable the
+calls raise -- there is no CPU fallback and nothing here imports oracle/.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmotion_b200.so")
+
+MD_OK = 0
+MD_MEM_HOST, MD_MEM_DEVICE = 0, 1
+MD_EGO_FIRST4, MD_EGO_RANSAC_HOMOGRAPHY, MD_EGO_RANSAC_AFFINE = 0, 1, 2
+STATUS_NAMES = {0: "MD_OK", -1: "MD_ERR_INVALID", -2: "MD_ERR_CUDA", -3: "MD_ERR_NOMEM", -4: "MD_ERR_UNSUPPORTED",
+                -5: "MD_ERR_STATE"}
+
+# every symbol include/motion_b200.h declares (tests/test_abi.py checks the library exports all of them)
+SYMBOLS = [
+    "md_config_default", "md_create", "md_destroy", "md_set_stream", "md_sync", "md_last_error", "md_version",
+    "md_grid_size", "md_grid_points", "md_pyramid_levels", "md_pyramid_level_size", "md_gray_u8", "md_pyramid_u8",
+    "md_pyramid_read", "md_pyramid_read_deriv", "md_lk_flow", "md_fit_egomotion", "md_motion_mask",
+    "md_process_batch", "md_process_pair", "md_track_trajectories", "md_fit_subspace", "md_varflow", "md_stats_get",
+    "md_stats_reset", "md_profile", "md_profile_read",
+]
+
+
+class MdConfig(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("max_batch", C.c_int32), ("pixel_step", C.c_int32),
+        ("min_vector_size", C.c_double),
+        ("lk_win", C.c_int32), ("lk_max_level", C.c_int32), ("lk_max_iters", C.c_int32),
+        ("lk_eps", C.c_double), ("lk_min_eig", C.c_float),
+        ("diff_threshold", C.c_int32), ("morph", C.c_int32), ("ego_mode", C.c_int32), ("ransac_iters", C.c_int32),
+        ("ransac_thresh", C.c_double), ("seed", C.c_uint32),
+        ("vf_max_level", C.c_int32), ("vf_start_level", C.c_int32), ("vf_n1", C.c_int32), ("vf_n2", C.c_int32),
+        ("vf_rho", C.c_float), ("vf_alpha", C.c_float), ("vf_sigma", C.c_float), ("vf_literal", C.c_int32),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+class MdFrames(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("channels", C.c_int32), ("pitch", C.c_int32), ("frame_stride", C.c_int64),
+                ("count", C.c_int32), ("chain", C.c_int32)]
+
+
+class MdOutputs(C.Structure):
+    _fields_ = [("next_pts", C.c_void_p), ("status", C.c_void_p), ("keep", C.c_void_p), ("H", C.c_void_p),
+                ("num_vectors", C.c_void_p), ("inliers", C.c_void_p), ("mask", C.c_void_p), ("mask_pitch", C.c_int32),
+                ("mask_stride", C.c_int64)]
+
+
+class MdStats(C.Structure):
+    _fields_ = [("pairs", C.c_int64), ("mask_pixels", C.c_int64), ("tracked", C.c_int64), ("inliers", C.c_int64),
+                ("last_H", C.c_double * 9), ("kernel_launches", C.c_int64), ("device", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class MotionB200Error(RuntimeError):
+    def __init__(self, code, msg=""):
+        self.code = code
+        super().__init__("%s (%d): %s" % (STATUS_NAMES.get(code, "?"), code, msg))
+
+
+_lib = None
+
+
+def lib():
+    """Load libmotion_b200.so; raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MotionB200Error(-2, "CUDA library %s is missing: build it with __graft_entry__.build(); "
+                                  "there is no CPU fallback" % LIB_PATH)
+        _lib = C.CDLL(LIB_PATH)
+        _lib.md_last_error.restype = C.c_char_p
+        _lib.md_version.restype = C.c_char_p
+        for name in SYMBOLS:
+            getattr(_lib, name)
+    return _lib
+
+
+def default_config(**kw):
+    cfg = MdConfig()
+    lib().md_config_default(C.byref(cfg))
+    for k, v in kw.items():
+        if not hasattr(cfg, k):
+            raise AttributeError("md_config has no field %r" % k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _ptr(a):
+    """numpy array (host), torch tensor (device or host) or raw int -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(a.data_ptr())     # torch tensor
+
+
+class Context:
+    """One md_ctx = one camera stream on one GPU (not thread-safe; contexts are independent)."""
+
+    def __init__(self, cfg=None, device=0, **kw):
+        self.cfg = cfg if cfg is not None else default_config(**kw)
+        self._h = C.c_void_p()
+        rc = lib().md_create(C.byref(self.cfg), int(device), C.byref(self._h))
+        if rc != MD_OK:
+            raise MotionB200Error(rc, "md_create failed (needs a CUDA device with compute capability 10.x)")
+        self.device = device
+        self.w, self.h = self.cfg.width, self.cfg.height
+        self.P = lib().md_grid_size(self._h)
+        self.levels = lib().md_pyramid_levels(self._h)
+
+    def close(self):
+        if self._h:
+            lib().md_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != MD_OK:
+            raise MotionB200Error(rc, lib().md_last_error(self._h).decode())
+
+    # ---- plumbing -------------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_handle):
+        self._ck(lib().md_set_stream(self._h, C.c_void_p(cuda_stream_handle)))
+
+    def sync(self):
+        self._ck(lib().md_sync(self._h))
+
+    def grid_points(self):
+        pts = np.empty((self.P, 2), np.float32)
+        lib().md_grid_points(self._h, _ptr(pts))
+        return pts
+
+    def level_size(self, level):
+        w, h = C.c_int32(), C.c_int32()
+        self._ck(lib().md_pyramid_level_size(self._h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    # ---- host-memory (numpy) convenience wrappers; device pointers go through the raw_* methods --------------
+    def gray(self, rgb):
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        h, w, _ = rgb.shape
+        out = np.empty((h, w), np.uint8)
+        self._ck(lib().md_gray_u8(self._h, _ptr(rgb), w * 3, w, h, _ptr(out), w, MD_MEM_HOST))
+        return out
+
+    def pyramid(self, gray, slot):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        assert gray.shape == (self.h, self.w)
+        self._ck(lib().md_pyramid_u8(self._h, _ptr(gray), self.w, slot, MD_MEM_HOST))
+
+    def pyramid_read(self, slot, level):
+        w, h = self.level_size(level)
+        out = np.empty((h, w), np.uint8)
+        self._ck(lib().md_pyramid_read(self._h, slot, level, _ptr(out), w, MD_MEM_HOST))
+        return out
+
+    def pyramid_read_deriv(self, slot, level):
+        w, h = self.level_size(level)
+        out = np.empty((h, w, 2), np.int16)
+        self._ck(lib().md_pyramid_read_deriv(self._h, slot, level, _ptr(out), MD_MEM_HOST))
+        return out
+
+    def lk_flow(self, slot_prev, slot_next, pts=None):
+        if pts is None:
+            n = self.P
+            pin = None
+        else:
+            pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+            n = len(pts)
+            pin = _ptr(pts)
+        out = np.zeros((n, 2), np.float32)
+        st = np.zeros(n, np.uint8)
+        self._ck(lib().md_lk_flow(self._h, slot_prev, slot_next, pin, n, _ptr(out), _ptr(st), MD_MEM_HOST))
+        return out, st
+
+    def fit_egomotion(self, src, dst, status=None, keep=None, mode=MD_EGO_RANSAC_HOMOGRAPHY, seed=1):
+        src = np.ascontiguousarray(src, np.float32).reshape(-1, 2)
+        dst = np.ascontiguousarray(dst, np.float32).reshape(-1, 2)
+        n = len(src)
+        status = None if status is None else np.ascontiguousarray(status, np.uint8)
+        keep = None if keep is None else np.ascontiguousarray(keep, np.uint8)
+        H = np.zeros(9, np.float64)
+        nv, ninl = C.c_int32(), C.c_int32()
+        inl = np.zeros(n, np.uint8)
+        self._ck(lib().md_fit_egomotion(self._h, _ptr(src), _ptr(dst), _ptr(status), _ptr(keep), n, mode, C.c_uint32(seed),
+                                        _ptr(H), C.byref(nv), C.byref(ninl), _ptr(inl), MD_MEM_HOST))
+        return dict(H=H.reshape(3, 3), num_vectors=nv.value, inliers=ninl.value, inlier_mask=inl)
+
+    def motion_mask(self, prev, cur, H, thresh=None, morph=None):
+        prev = np.ascontiguousarray(prev, np.uint8)
+        cur = np.ascontiguousarray(cur, np.uint8)
+        H = np.ascontiguousarray(H, np.float64)
+        out = np.empty((self.h, self.w), np.uint8)
+        thresh = self.cfg.diff_threshold if thresh is None else thresh
+        morph = self.cfg.morph if morph is None else int(morph)
+        self._ck(lib().md_motion_mask(self._h, _ptr(prev), _ptr(cur), self.w, _ptr(H), thresh, morph, _ptr(out), self.w,
+                                      MD_MEM_HOST))
+        return out
+
+    def process_batch(self, frames, chain=False, want_mask=True):
+        """frames: numpy [n][h][w] (gray) or [n][h][w][3]; returns dict of per-pair numpy outputs."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        ch = 3 if frames.ndim == 4 else 1
+        n = frames.shape[0]
+        pairs = n if chain else n - 1
+        fr = MdFrames(_ptr(frames), ch, self.w * ch, self.w * self.h * ch, n, 1 if chain else 0)
+        res = dict(next=np.zeros((pairs, self.P, 2), np.float32), status=np.zeros((pairs, self.P), np.uint8),
+                   keep=np.zeros((pairs, self.P), np.uint8), H=np.zeros((pairs, 3, 3), np.float64),
+                   num_vectors=np.zeros(pairs, np.int32), inliers=np.zeros(pairs, np.int32),
+                   mask=np.zeros((pairs, self.h, self.w), np.uint8) if want_mask else None)
+        out = MdOutputs(_ptr(res["next"]), _ptr(res["status"]), _ptr(res["keep"]), _ptr(res["H"]), _ptr(res["num_vectors"]),
+                        _ptr(res["inliers"]), _ptr(res["mask"]), self.w, self.w * self.h)
+        self._ck(lib().md_process_batch(self._h, C.byref(fr), C.byref(out), MD_MEM_HOST))
+        return res
+
+    def raw_process_batch(self, frames_ptr, channels, pitch, frame_stride, count, chain, outputs, mem):
+        """Thin call for device (or pinned host) pointers. `outputs` is an MdOutputs."""
+        fr = MdFrames(C.c_void_p(frames_ptr), channels, pitch, frame_stride, count, 1 if chain else 0)
+        self._ck(lib().md_process_batch(self._h, C.byref(fr), C.byref(outputs), mem))
+
+    def track_trajectories(self, frames):
+        frames = np.ascontiguousarray(frames, np.uint8)
+        ch = 3 if frames.ndim == 4 else 1
+        F = frames.shape[0]
+        fr = MdFrames(_ptr(frames), ch, self.w * ch, self.w * self.h * ch, F, 0)
+        traj = np.zeros((self.P, F, 2), np.float32)
+        ln = np.zeros(self.P, np.int32)
+        lp = np.zeros((self.P, 2), np.float32)
+        lnx = np.zeros((self.P, 2), np.float32)
+        ls = np.zeros(self.P, np.uint8)
+        self._ck(lib().md_track_trajectories(self._h, C.byref(fr), _ptr(traj), _ptr(ln), _ptr(lp), _ptr(lnx), _ptr(ls),
+                                             MD_MEM_HOST))
+        return dict(traj=traj, len=ln, last_prev=lp, last_next=lnx, last_status=ls)
+
+    def fit_subspace(self, traj, num_motions=2, sigma=0.5, seed=1, forced_cols=None, iters=50):
+        traj = np.ascontiguousarray(traj, np.float32)
+        T, F, _ = traj.shape
+        d = 4 * num_motions
+        res = np.zeros(T, np.float32)
+        cols = np.zeros(d, np.int32)
+        outl = np.zeros(T, np.uint8)
+        ninl = C.c_int32()
+        fc = None
+        if forced_cols is not None:
+            fc_arr = np.ascontiguousarray(forced_cols, np.int32).reshape(-1, d)
+            iters = fc_arr.shape[0]
+            fc = _ptr(fc_arr)
+        self._ck(lib().md_fit_subspace(self._h, _ptr(traj), T, F, num_motions, C.c_double(sigma), C.c_uint32(seed), fc, iters,
+                                       _ptr(res), _ptr(cols), _ptr(outl), C.byref(ninl), MD_MEM_HOST))
+        return dict(inliers=ninl.value, residual=res, best_cols=cols, outlier=outl)
+
+    def varflow(self, A, B):
+        A = np.ascontiguousarray(A, np.uint8)
+        B = np.ascontiguousarray(B, np.uint8)
+        U = np.zeros((self.h, self.w), np.float32)
+        V = np.zeros((self.h, self.w), np.float32)
+        self._ck(lib().md_varflow(self._h, _ptr(A), _ptr(B), self.w, _ptr(U), _ptr(V), MD_MEM_HOST))
+        return U, V
+
+    def stats(self):
+        st = MdStats()
+        self._ck(lib().md_stats_get(self._h, C.byref(st)))
+        return dict(pairs=st.pairs, mask_pixels=st.mask_pixels, tracked=st.tracked, inliers=st.inliers,
+                    last_H=np.array(st.last_H[:]).reshape(3, 3), device=st.device, kernel_launches=st.kernel_launches)
+
+    def profile(self, enable=True):
+        self._ck(lib().md_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """ms of the four stages (pyramid, lk, egomotion, mask) of the last profiled md_process_batch."""
+        ms = (C.c_float * 4)()
+        self._ck(lib().md_profile_read(self._h, ms))
+        return [float(v) for v in ms]
+
+    def stats_reset(self):
+        self._ck(lib().md_stats_reset(self._h))

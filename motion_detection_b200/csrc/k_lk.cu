@@ -1,0 +1,151 @@
+// k_lk.cu -- K2: pyramidal Lucas-Kanade, one warp per tracked point, all levels in one launch.
+//
+// Replaces cv::calcOpticalFlowPyrLK(pyr, gray2, pts1, pts2, status, err, Size(40,40), 5,
+// TermCriteria(COUNT|EPS, 10, 0.03), 0, 0.001) as called at common/src/optical_flow_calculator.cpp:71,172
+// (algorithm: OpenCV LKTrackerInvoker; OpenCV is not vendored by the reference).
+//
+// Arithmetic follows the reference's fixed-point scheme exactly (W_BITS = 14 bilinear weights, window samples
+// descaled to 5 extra bits, derivative samples to 0 extra bits).  The structure-tensor sums (A11, A12, A22) and the
+// mismatch sums (b1, b2) are accumulated EXACTLY -- int32 per lane (<= 64 taps per lane keeps them below 2^31),
+// then a warp-shuffle butterfly in f64 -- and rounded once to f32, where OpenCV accumulates in f32 in
+// SIMD-lane order; the two agree to ~1e-7 relative (flow differences ~1e-5 px, tests/test_lk_gpu.py).
+// The scalar f32 expressions use explicit _rn intrinsics so that no FMA contraction changes their rounding.
+#include <float.h>
+
+#include "md_internal.h"
+
+#define W_BITS 14
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void lk_weights(float a, float b, int &w00, int &w01, int &w10, int &w11)
+{
+    float na = __fsub_rn(1.f, a), nb = __fsub_rn(1.f, b);
+    w00 = __float2int_rn(__fmul_rn(__fmul_rn(na, nb), (float)(1 << W_BITS)));
+    w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, nb), (float)(1 << W_BITS)));
+    w10 = __float2int_rn(__fmul_rn(__fmul_rn(na, b), (float)(1 << W_BITS)));
+    w11 = (1 << W_BITS) - w00 - w01 - w10;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_lk(const LkParams p)
+{
+    extern __shared__ int16_t lk_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * WARPS + warp;
+    const int b = blockIdx.y;
+    if (k >= p.P) return;
+    const int win = p.win, W2 = win * win;
+    int16_t *Iw = lk_smem + (size_t)warp * 3 * W2;
+    int16_t *Ixw = Iw + W2, *Iyw = Ixw + W2;
+
+    float2 pt;
+    if (p.pts_in) pt = p.pts_in[(size_t)b * p.P + k];
+    else pt = make_float2((float)(p.ps * (k / p.gy)), (float)(p.ps * (k % p.gy)));
+
+    const int slotI = (p.prev_slot0 + b) % p.g.nslots, slotJ = (p.next_slot0 + b) % p.g.nslots;
+    const float half = (win - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    float2 nxt = make_float2(0.f, 0.f);
+    int st = 1;
+
+    for (int level = p.g.nlev - 1; level >= 0; level--) {
+        const LevelGeom L = p.g.lv[level];
+        const float scale = 1.f / (float)(1 << level);
+        float ppx = pt.x * scale, ppy = pt.y * scale;
+        float npx, npy;
+        if (level == p.g.nlev - 1) { npx = ppx; npy = ppy; }
+        else { npx = nxt.x * 2.f; npy = nxt.y * 2.f; }
+        nxt = make_float2(npx, npy);
+
+        ppx = __fsub_rn(ppx, half); ppy = __fsub_rn(ppy, half);
+        const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
+        if (ipx < -win || ipx >= L.w || ipy < -win || ipy >= L.h) {
+            if (level == 0) st = 0;
+            continue;
+        }
+        int w00, w01, w10, w11;
+        lk_weights(__fsub_rn(ppx, (float)ipx), __fsub_rn(ppy, (float)ipy), w00, w01, w10, w11);
+
+        const uint8_t *I0 = p.img + (size_t)slotI * p.g.slot_img_bytes + L.img_off + (size_t)(p.g.pady + ipy) * L.pitch + p.g.padx + ipx;
+        const short2 *D0 = p.der + (size_t)slotI * p.g.slot_der_elems + L.der_off + (size_t)(p.g.pady + ipy) * L.pitch + p.g.padx + ipx;
+        int a11 = 0, a12 = 0, a22 = 0;
+        for (int t = lane; t < W2; t += 32) {
+            const int y = t / win, x = t - y * win;
+            const uint8_t *s = I0 + (size_t)y * L.pitch + x;
+            const short2 *d = D0 + (size_t)y * L.pitch + x;
+            const int ival = (s[0] * w00 + s[1] * w01 + s[L.pitch] * w10 + s[L.pitch + 1] * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+            const short2 d00 = __ldg(d), d01 = __ldg(d + 1), d10 = __ldg(d + L.pitch), d11 = __ldg(d + L.pitch + 1);
+            const int ix = (d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+            const int iy = (d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11 + (1 << (W_BITS - 1))) >> W_BITS;
+            Iw[t] = (int16_t)ival; Ixw[t] = (int16_t)ix; Iyw[t] = (int16_t)iy;
+            a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+        }
+        const float A11 = (float)warp_sum((double)a11) * FLT_SCALE;
+        const float A12 = (float)warp_sum((double)a12) * FLT_SCALE;
+        const float A22 = (float)warp_sum((double)a22) * FLT_SCALE;
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dA = __fsub_rn(A11, A22);
+        const float disc = __fadd_rn(__fmul_rn(dA, dA), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float min_eig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(disc)), (float)(2 * win * win));
+        if (min_eig < p.min_eig || D < FLT_EPSILON) {
+            if (level == 0) st = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        npx = __fsub_rn(npx, half); npy = __fsub_rn(npy, half);
+        float pdx = 0.f, pdy = 0.f;
+        const uint8_t *Jbase = p.img + (size_t)slotJ * p.g.slot_img_bytes + L.img_off + (size_t)p.g.pady * L.pitch + p.g.padx;
+        for (int j = 0; j < p.max_iters; j++) {
+            const int inx = __float2int_rd(npx), iny = __float2int_rd(npy);
+            if (inx < -win || inx >= L.w || iny < -win || iny >= L.h) {
+                if (level == 0) st = 0;
+                break;
+            }
+            lk_weights(__fsub_rn(npx, (float)inx), __fsub_rn(npy, (float)iny), w00, w01, w10, w11);
+            const uint8_t *J0 = Jbase + (ptrdiff_t)iny * L.pitch + inx;
+            int b1 = 0, b2 = 0;
+            for (int t = lane; t < W2; t += 32) {
+                const int y = t / win, x = t - y * win;
+                const uint8_t *s = J0 + (size_t)y * L.pitch + x;
+                const int diff = ((s[0] * w00 + s[1] * w01 + s[L.pitch] * w10 + s[L.pitch + 1] * w11 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5)) - Iw[t];
+                b1 += diff * Ixw[t];
+                b2 += diff * Iyw[t];
+            }
+            const float fb1 = (float)warp_sum((double)b1) * FLT_SCALE;
+            const float fb2 = (float)warp_sum((double)b2) * FLT_SCALE;
+            const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb2), __fmul_rn(A22, fb1)), D);
+            const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, fb1), __fmul_rn(A11, fb2)), D);
+            npx = __fadd_rn(npx, ddx); npy = __fadd_rn(npy, ddy);
+            nxt = make_float2(__fadd_rn(npx, half), __fadd_rn(npy, half));
+            if (__dadd_rn(__dmul_rn((double)ddx, (double)ddx), __dmul_rn((double)ddy, (double)ddy)) <= p.eps2) break;
+            if (j > 0 && (double)fabsf(__fadd_rn(ddx, pdx)) < 0.01 && (double)fabsf(__fadd_rn(ddy, pdy)) < 0.01) {
+                nxt.x = __fsub_rn(nxt.x, __fmul_rn(ddx, 0.5f));
+                nxt.y = __fsub_rn(nxt.y, __fmul_rn(ddy, 0.5f));
+                break;
+            }
+            pdx = ddx; pdy = ddy;
+        }
+    }
+    if (lane == 0) {
+        p.next[(size_t)b * p.P + k] = nxt;
+        p.status[(size_t)b * p.P + k] = (uint8_t)st;
+    }
+}
+
+cudaError_t launch_lk(const LkParams &p, int pairs, cudaStream_t s)
+{
+    constexpr int WARPS = 8;
+    size_t smem = (size_t)WARPS * 3 * p.win * p.win * sizeof(int16_t);
+    cudaError_t e = cudaFuncSetAttribute(k_lk<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((p.P + WARPS - 1) / WARPS, pairs);
+    k_lk<WARPS><<<grid, WARPS * 32, smem, s>>>(p);
+    MD_COUNT_LAUNCH(1);
+    return cudaGetLastError();
+}

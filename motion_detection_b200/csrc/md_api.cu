@@ -1,0 +1,659 @@
+// md_api.cu -- the C ABI of libmotion_b200.so (include/motion_b200.h): context, staging, kernel orchestration.
+// No CPU fallback anywhere: every compute entry point runs CUDA kernels on the context's stream.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "md_internal.h"
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char buf_[256];                                                                           \
+            snprintf(buf_, sizeof buf_, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            ctx->err = buf_;                                                                          \
+            return MD_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+#define FAIL(code, msg)     \
+    do {                    \
+        ctx->err = (msg);   \
+        return (code);      \
+    } while (0)
+
+long long g_md_launches = 0;
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+extern "C" const char *md_version(void) { return "motion_b200 0.1 (sm_100a)"; }
+
+extern "C" int md_config_default(md_config *c)
+{
+    if (!c) return MD_ERR_INVALID;
+    memset(c, 0, sizeof *c);
+    c->width = 640; c->height = 480; c->max_batch = 1;
+    c->pixel_step = 10;            // ros/launch/bag.launch (and camera/video/towercam/tu)
+    c->min_vector_size = 1.0;      // ros/src/motion_detection_node.cpp:44
+    c->lk_win = 40; c->lk_max_level = 5; c->lk_max_iters = 10; c->lk_eps = 0.03; c->lk_min_eig = 0.001f;   // cpp:40-44,71
+    c->diff_threshold = 190;       // cpp:127
+    c->morph = 1;                  // background_subtractor.cpp:31-32
+    c->ego_mode = MD_EGO_RANSAC_HOMOGRAPHY;
+    c->ransac_iters = 50;          // outlier_detector.cpp:250
+    c->ransac_thresh = 0.5;
+    c->seed = 1;
+    c->vf_max_level = 4; c->vf_start_level = 0; c->vf_n1 = 2; c->vf_n2 = 2;      // cpp:422-425
+    c->vf_rho = 2.8f; c->vf_alpha = 1400.f; c->vf_sigma = 1.5f;                  // cpp:427-429
+    c->vf_literal = 1;
+    return MD_OK;
+}
+
+static int pyr_levels(int w, int h, int win, int max_level)
+{
+    for (int level = 0; level <= max_level; level++) {
+        w = (w + 1) / 2; h = (h + 1) / 2;
+        if (w <= win || h <= win) return level;
+    }
+    return max_level;
+}
+
+static void free_ctx(md_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    void *ptrs[] = {ctx->d_img, ctx->d_der, ctx->d_frames, ctx->d_mask, ctx->d_pts_in, ctx->d_next, ctx->d_status, ctx->d_keep,
+                    ctx->d_inlier_mask, ctx->d_blockcnt, ctx->d_kept_idx, ctx->d_M, ctx->d_hyp_valid, ctx->d_counts,
+                    ctx->d_inliers, ctx->d_valid, ctx->d_hyp, ctx->d_partial, ctx->d_H, ctx->d_Hinv, ctx->d_stats,
+                    ctx->d_traj, ctx->d_traj_len};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
+{
+    if (!cfg || !out) return MD_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->width < 8 || cfg->height < 8 || cfg->width > 16384 || cfg->height > 16384) return MD_ERR_INVALID;
+    if (cfg->max_batch < 1 || cfg->max_batch > 4096 || cfg->pixel_step < 1) return MD_ERR_INVALID;
+    if (cfg->lk_win < 4 || cfg->lk_win > 44 || cfg->lk_max_level < 0 || cfg->lk_max_level >= MD_MAX_LEVELS) return MD_ERR_INVALID;
+    if (cfg->ransac_iters < 1 || cfg->ransac_iters > MD_MAX_HYP) return MD_ERR_INVALID;
+    if (cfg->ego_mode < 0 || cfg->ego_mode > 2) return MD_ERR_INVALID;
+    if (cfg->vf_start_level != 0) return MD_ERR_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MD_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return MD_ERR_CUDA;
+    if (prop.major != 10) return MD_ERR_CUDA;     // sm_100a code only
+    if (cudaSetDevice(device) != cudaSuccess) return MD_ERR_CUDA;
+
+    md_ctx *ctx = new (std::nothrow) md_ctx();
+    if (!ctx) return MD_ERR_NOMEM;
+    ctx->cfg = *cfg;
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MD_ERR_CUDA; }
+    ctx->stream = ctx->own_stream;
+
+    const int w = cfg->width, h = cfg->height, B = cfg->max_batch;
+    PyrGeom &g = ctx->g;
+    g.nlev = pyr_levels(w, h, cfg->lk_win, cfg->lk_max_level) + 1;
+    g.padx = align_up(cfg->lk_win, 16);
+    g.pady = cfg->lk_win;
+    g.nslots = B + 1;
+    size_t ioff = 0, doff = 0;
+    int lw = w, lh = h;
+    for (int l = 0; l < g.nlev; l++) {
+        LevelGeom &L = g.lv[l];
+        L.w = lw; L.h = lh;
+        L.pitch = align_up(lw + 2 * g.padx, 128);
+        L.rows = lh + 2 * g.pady;
+        L.img_off = ioff; L.der_off = doff;
+        ioff += (size_t)L.pitch * L.rows;
+        doff += (size_t)L.pitch * L.rows;
+        lw = (lw + 1) / 2; lh = (lh + 1) / 2;
+    }
+    g.slot_img_bytes = ioff;
+    g.slot_der_elems = doff;
+    ctx->gx = (w + cfg->pixel_step - 1) / cfg->pixel_step;
+    ctx->gy = (h + cfg->pixel_step - 1) / cfg->pixel_step;
+    ctx->P = ctx->gx * ctx->gy;
+    ctx->pts_cap = (size_t)ctx->P;
+    ctx->fpitch = align_up(w, 128);
+    ctx->nblk_scan = (ctx->P + 2047) / 2048;
+    ctx->nblk_acc = (ctx->P + 255) / 256 < 64 ? (ctx->P + 255) / 256 : 64;
+
+    const size_t P = ctx->P;
+    const int it = cfg->ransac_iters;
+    bool ok = true;
+    auto A = [&](void **p, size_t bytes) { if (ok && cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) ok = false; };
+    A((void **)&ctx->d_img, g.slot_img_bytes * g.nslots);
+    A((void **)&ctx->d_der, g.slot_der_elems * sizeof(short2) * g.nslots);
+    A((void **)&ctx->d_mask, (size_t)B * h * ctx->fpitch);
+    A((void **)&ctx->d_pts_in, sizeof(float2) * P * B);
+    A((void **)&ctx->d_next, sizeof(float2) * P * B);
+    A((void **)&ctx->d_status, P * B);
+    A((void **)&ctx->d_keep, P * B);
+    A((void **)&ctx->d_inlier_mask, P * B);
+    A((void **)&ctx->d_blockcnt, sizeof(int) * ctx->nblk_scan * B);
+    A((void **)&ctx->d_kept_idx, sizeof(int) * P * B);
+    A((void **)&ctx->d_M, sizeof(int) * B);
+    A((void **)&ctx->d_hyp_valid, sizeof(int) * it * B);
+    A((void **)&ctx->d_counts, sizeof(int) * it * B);
+    A((void **)&ctx->d_inliers, sizeof(int) * B);
+    A((void **)&ctx->d_valid, sizeof(int) * B);
+    A((void **)&ctx->d_hyp, sizeof(double) * 9 * it * B);
+    A((void **)&ctx->d_partial, sizeof(double) * 24 * ctx->nblk_acc * B);
+    A((void **)&ctx->d_H, sizeof(double) * 9 * B);
+    A((void **)&ctx->d_Hinv, sizeof(double) * 9 * B);
+    A((void **)&ctx->d_stats, sizeof(unsigned long long) * 4);
+    if (ok) {
+        // derivative planes keep a ZERO frame forever (derivBorder = BORDER_CONSTANT); image frames are rewritten per build
+        ok = cudaMemsetAsync(ctx->d_der, 0, g.slot_der_elems * sizeof(short2) * g.nslots, ctx->stream) == cudaSuccess &&
+             cudaMemsetAsync(ctx->d_stats, 0, sizeof(unsigned long long) * 4, ctx->stream) == cudaSuccess &&
+             cudaStreamSynchronize(ctx->stream) == cudaSuccess;
+    }
+    if (!ok) { free_ctx(ctx); return MD_ERR_NOMEM; }
+    ctx->stats.device = device;
+    *out = ctx;
+    return MD_OK;
+}
+
+extern "C" int md_destroy(md_ctx *ctx)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_ctx(ctx);
+    return MD_OK;
+}
+
+extern "C" int md_set_stream(md_ctx *ctx, void *s)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return MD_OK;
+}
+
+extern "C" int md_sync(md_ctx *ctx)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
+
+extern "C" const char *md_last_error(const md_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int md_grid_size(const md_ctx *ctx) { return ctx ? ctx->P : MD_ERR_INVALID; }
+
+extern "C" int md_grid_points(const md_ctx *ctx, float *pts)
+{
+    if (!ctx || !pts) return MD_ERR_INVALID;
+    int n = 0;
+    for (int i = 0; i < ctx->cfg.width; i += ctx->cfg.pixel_step)
+        for (int j = 0; j < ctx->cfg.height; j += ctx->cfg.pixel_step) { pts[2 * n] = (float)i; pts[2 * n + 1] = (float)j; n++; }
+    return n;
+}
+
+extern "C" int md_pyramid_levels(const md_ctx *ctx) { return ctx ? ctx->g.nlev : MD_ERR_INVALID; }
+
+extern "C" int md_pyramid_level_size(const md_ctx *ctx, int level, int32_t *w, int32_t *h)
+{
+    if (!ctx || level < 0 || level >= ctx->g.nlev) return MD_ERR_INVALID;
+    if (w) *w = ctx->g.lv[level].w;
+    if (h) *h = ctx->g.lv[level].h;
+    return MD_OK;
+}
+
+// ---- staging helpers -----------------------------------------------------------------------------------------------
+static int ensure_frames(md_ctx *ctx, int channels)
+{
+    if (ctx->d_frames && ctx->frames_channels >= channels) return MD_OK;
+    if (ctx->d_frames) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_frames); ctx->d_frames = nullptr; }
+    size_t bytes = (size_t)(ctx->cfg.max_batch + 1) * ctx->cfg.height * ctx->fpitch * channels;
+    CK(cudaMalloc((void **)&ctx->d_frames, bytes));
+    ctx->frames_channels = channels;
+    return MD_OK;
+}
+
+static inline uint8_t *slot_plane(md_ctx *ctx, int slot, int level)
+{
+    const LevelGeom &L = ctx->g.lv[level];
+    return ctx->d_img + (size_t)slot * ctx->g.slot_img_bytes + L.img_off + (size_t)ctx->g.pady * L.pitch + ctx->g.padx;
+}
+
+// ---- K0 ------------------------------------------------------------------------------------------------------------
+extern "C" int md_gray_u8(md_ctx *ctx, const uint8_t *src3, int32_t src_pitch, int32_t w, int32_t h, uint8_t *dst,
+                          int32_t dst_pitch, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!src3 || !dst || w < 1 || h < 1 || src_pitch < 3 * w || dst_pitch < w) FAIL(MD_ERR_INVALID, "md_gray_u8: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    if (mem == MD_MEM_DEVICE) {
+        CK(launch_gray(src3, src_pitch, w, h, dst, dst_pitch, ctx->stream));
+        return MD_OK;
+    }
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    CK(cudaMalloc((void **)&d_in, (size_t)3 * w * h));
+    if (cudaMalloc((void **)&d_out, (size_t)w * h) != cudaSuccess) { cudaFree(d_in); FAIL(MD_ERR_NOMEM, "md_gray_u8: out of memory"); }
+    cudaError_t e = cudaMemcpy2DAsync(d_in, 3 * w, src3, src_pitch, 3 * w, h, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = launch_gray(d_in, 3 * w, w, h, d_out, w, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(dst, dst_pitch, d_out, w, w, h, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_in); cudaFree(d_out);
+    CK(e);
+    return MD_OK;
+}
+
+// ---- K1 ------------------------------------------------------------------------------------------------------------
+static int stage_frames(md_ctx *ctx, const uint8_t *data, int channels, int pitch, long long fstride, int count, int mem,
+                        const uint8_t **d_frames, int *d_pitch, long long *d_stride)
+{
+    if (mem == MD_MEM_DEVICE) { *d_frames = data; *d_pitch = pitch; *d_stride = fstride; return MD_OK; }
+    int r = ensure_frames(ctx, channels);
+    if (r != MD_OK) return r;
+    const int dp = ctx->fpitch * channels;
+    const long long ds = (long long)dp * ctx->cfg.height;
+    for (int f = 0; f < count; f++)
+        CK(cudaMemcpy2DAsync(ctx->d_frames + f * ds, dp, data + f * fstride, pitch, (size_t)ctx->cfg.width * channels,
+                             ctx->cfg.height, cudaMemcpyHostToDevice, ctx->stream));
+    *d_frames = ctx->d_frames; *d_pitch = dp; *d_stride = ds;
+    return MD_OK;
+}
+
+extern "C" int md_pyramid_u8(md_ctx *ctx, const uint8_t *gray, int32_t pitch, int slot, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!gray || pitch < ctx->cfg.width || slot < 0 || slot >= ctx->g.nslots) FAIL(MD_ERR_INVALID, "md_pyramid_u8: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t *df; int dp; long long ds;
+    int r = stage_frames(ctx, gray, 1, pitch, 0, 1, mem, &df, &dp, &ds);
+    if (r != MD_OK) return r;
+    CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, slot, 1, df, 1, dp, ds, ctx->stream));
+    if (mem == MD_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    ctx->have_cached = 0;
+    return MD_OK;
+}
+
+extern "C" int md_pyramid_read(md_ctx *ctx, int slot, int level, uint8_t *dst, int32_t dst_pitch, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!dst || slot < 0 || slot >= ctx->g.nslots || level < 0 || level >= ctx->g.nlev || dst_pitch < ctx->g.lv[level].w)
+        FAIL(MD_ERR_INVALID, "md_pyramid_read: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const LevelGeom &L = ctx->g.lv[level];
+    CK(cudaMemcpy2DAsync(dst, dst_pitch, slot_plane(ctx, slot, level), L.pitch, L.w, L.h,
+                         mem == MD_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    if (mem == MD_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
+
+extern "C" int md_pyramid_read_deriv(md_ctx *ctx, int slot, int level, int16_t *dst, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!dst || slot < 0 || slot >= ctx->g.nslots || level < 0 || level >= ctx->g.nlev) FAIL(MD_ERR_INVALID, "md_pyramid_read_deriv: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const LevelGeom &L = ctx->g.lv[level];
+    const short2 *src = ctx->d_der + (size_t)slot * ctx->g.slot_der_elems + L.der_off + (size_t)ctx->g.pady * L.pitch + ctx->g.padx;
+    CK(cudaMemcpy2DAsync(dst, (size_t)L.w * 4, src, (size_t)L.pitch * 4, (size_t)L.w * 4, L.h,
+                         mem == MD_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    if (mem == MD_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
+
+// ---- K2 ------------------------------------------------------------------------------------------------------------
+static void fill_lk(md_ctx *ctx, LkParams &p, int prev_slot0, int next_slot0, const float2 *pts_in, int P, float2 *next,
+                    uint8_t *status)
+{
+    p.g = ctx->g;
+    p.img = ctx->d_img; p.der = ctx->d_der;
+    p.prev_slot0 = prev_slot0; p.next_slot0 = next_slot0;
+    p.pts_in = pts_in;
+    p.ps = ctx->cfg.pixel_step; p.gy = ctx->gy;
+    p.P = P;
+    p.next = next; p.status = status;
+    p.win = ctx->cfg.lk_win;
+    int it = ctx->cfg.lk_max_iters;
+    p.max_iters = it < 0 ? 0 : (it > 100 ? 100 : it);
+    double eps = ctx->cfg.lk_eps;
+    eps = eps < 0 ? 0 : (eps > 10 ? 10 : eps);
+    p.eps2 = eps * eps;
+    p.min_eig = ctx->cfg.lk_min_eig;
+}
+
+extern "C" int md_lk_flow(md_ctx *ctx, int slot_prev, int slot_next, const float *pts_in, int32_t npts, float *pts_out,
+                          uint8_t *status, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!pts_out || !status || npts < 1 || (size_t)npts > ctx->pts_cap || slot_prev < 0 || slot_next < 0 ||
+        slot_prev >= ctx->g.nslots || slot_next >= ctx->g.nslots || (!pts_in && npts != ctx->P))
+        FAIL(MD_ERR_INVALID, "md_lk_flow: bad arguments (npts must be <= md_grid_size)");
+    CK(cudaSetDevice(ctx->device));
+    const float2 *d_in = nullptr;
+    float2 *d_out = (float2 *)pts_out;
+    uint8_t *d_st = status;
+    if (mem == MD_MEM_HOST) {
+        if (pts_in) { CK(cudaMemcpyAsync(ctx->d_pts_in, pts_in, sizeof(float2) * npts, cudaMemcpyHostToDevice, ctx->stream)); d_in = ctx->d_pts_in; }
+        d_out = ctx->d_next; d_st = ctx->d_status;
+    } else d_in = (const float2 *)pts_in;
+    LkParams p;
+    fill_lk(ctx, p, slot_prev, slot_next, d_in, npts, d_out, d_st);
+    CK(launch_lk(p, 1, ctx->stream));
+    if (mem == MD_MEM_HOST) {
+        CK(cudaMemcpyAsync(pts_out, d_out, sizeof(float2) * npts, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(status, d_st, npts, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return MD_OK;
+}
+
+// ---- K3 ------------------------------------------------------------------------------------------------------------
+static void fill_ego(md_ctx *ctx, EgoParams &p, const float2 *pts_in, int P, const float2 *next, const uint8_t *status,
+                     uint8_t *keep, int keep_given, int mode, uint32_t seed0, double *H, int *inliers, uint8_t *inlier_mask)
+{
+    p.P = P; p.ps = ctx->cfg.pixel_step; p.gy = ctx->gy;
+    p.pts_in = pts_in; p.next = next; p.status = status; p.keep = keep; p.keep_given = keep_given;
+    p.min_vec = ctx->cfg.min_vector_size;
+    p.mode = mode; p.iters = ctx->cfg.ransac_iters; p.minimal = mode == MD_EGO_RANSAC_AFFINE ? 3 : 4;
+    p.thr2 = ctx->cfg.ransac_thresh * ctx->cfg.ransac_thresh;
+    p.seed0 = seed0;
+    p.w = ctx->cfg.width; p.h = ctx->cfg.height;
+    p.nblk_scan = (P + 2047) / 2048;
+    p.nblk_acc = (P + 255) / 256 < 64 ? (P + 255) / 256 : 64;
+    p.blockcnt = ctx->d_blockcnt; p.kept_idx = ctx->d_kept_idx; p.M = ctx->d_M;
+    p.hyp = ctx->d_hyp; p.hyp_valid = ctx->d_hyp_valid; p.counts = ctx->d_counts; p.partial = ctx->d_partial;
+    p.H = H ? H : ctx->d_H; p.Hinv = ctx->d_Hinv;
+    p.inliers = inliers ? inliers : ctx->d_inliers; p.valid = ctx->d_valid;
+    p.inlier_mask = inlier_mask;
+    p.stat_tracked = ctx->d_stats + 1; p.stat_inliers = ctx->d_stats + 2;
+}
+
+extern "C" int md_fit_egomotion(md_ctx *ctx, const float *src, const float *dst, const uint8_t *status, const uint8_t *keep,
+                                int32_t npts, int mode, uint32_t seed, double *H9, int32_t *num_vectors, int32_t *inliers,
+                                uint8_t *inlier_mask, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!src || !dst || (!status && !keep) || npts < 1 || (size_t)npts > ctx->pts_cap || mode < 0 || mode > 2)
+        FAIL(MD_ERR_INVALID, "md_fit_egomotion: bad arguments (npts must be <= md_grid_size)");
+    CK(cudaSetDevice(ctx->device));
+    const cudaMemcpyKind in = mem == MD_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const cudaMemcpyKind outk = mem == MD_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(ctx->d_pts_in, src, sizeof(float2) * npts, in, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_next, dst, sizeof(float2) * npts, in, ctx->stream));
+    if (status) CK(cudaMemcpyAsync(ctx->d_status, status, npts, in, ctx->stream));
+    else CK(cudaMemsetAsync(ctx->d_status, 1, npts, ctx->stream));
+    if (keep) CK(cudaMemcpyAsync(ctx->d_keep, keep, npts, in, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_inlier_mask, 0, npts, ctx->stream));
+    EgoParams p;
+    fill_ego(ctx, p, ctx->d_pts_in, npts, ctx->d_next, ctx->d_status, ctx->d_keep, keep ? 1 : 0, mode, seed, nullptr, nullptr,
+             ctx->d_inlier_mask);
+    p.stat_tracked = nullptr; p.stat_inliers = nullptr;
+    CK(launch_ego(p, 1, ctx->stream));
+    if (H9) CK(cudaMemcpyAsync(H9, ctx->d_H, sizeof(double) * 9, outk, ctx->stream));
+    if (num_vectors) CK(cudaMemcpyAsync(num_vectors, ctx->d_M, sizeof(int), outk, ctx->stream));
+    if (inliers) CK(cudaMemcpyAsync(inliers, ctx->d_inliers, sizeof(int), outk, ctx->stream));
+    if (inlier_mask) CK(cudaMemcpyAsync(inlier_mask, ctx->d_inlier_mask, npts, outk, ctx->stream));
+    if (mem == MD_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    return MD_OK;
+}
+
+// ---- K4 ------------------------------------------------------------------------------------------------------------
+static bool invert3_host(const double *S, double *D)
+{
+    // cv::invert 3x3 (cofactors), same operation order as k_ego.cu:invert3 and the oracle
+    double c0 = S[4] * S[8] - S[5] * S[7], c1 = S[3] * S[8] - S[5] * S[6], c2 = S[3] * S[7] - S[4] * S[6];
+    double d = S[0] * c0 - S[1] * c1 + S[2] * c2;
+    if (d == 0) { for (int i = 0; i < 9; i++) D[i] = 0; return false; }
+    d = 1. / d;
+    double t[9];
+    t[0] = c0 * d;
+    t[1] = (S[2] * S[7] - S[1] * S[8]) * d;
+    t[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+    t[3] = (S[5] * S[6] - S[3] * S[8]) * d;
+    t[4] = (S[0] * S[8] - S[2] * S[6]) * d;
+    t[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+    t[6] = c2 * d;
+    t[7] = (S[1] * S[6] - S[0] * S[7]) * d;
+    t[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+    memcpy(D, t, sizeof t);
+    return true;
+}
+
+extern "C" int md_motion_mask(md_ctx *ctx, const uint8_t *prev, const uint8_t *cur, int32_t pitch, const double *H9,
+                              int32_t thresh, int32_t morph, uint8_t *mask, int32_t mask_pitch, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    const int w = ctx->cfg.width, h = ctx->cfg.height;
+    if (!prev || !cur || !H9 || !mask || pitch < w || mask_pitch < w) FAIL(MD_ERR_INVALID, "md_motion_mask: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    double Hinv[9];
+    invert3_host(H9, Hinv);
+    // d_Hinv row `max_batch-1` is scratch for this call; copy is stream ordered (pageable source is staged before return)
+    double *d_hi = ctx->d_Hinv;
+    CK(cudaMemcpyAsync(d_hi, Hinv, sizeof Hinv, cudaMemcpyHostToDevice, ctx->stream));
+    MaskParams p;
+    memset(&p, 0, sizeof p);
+    p.w = w; p.h = h; p.Hinv = d_hi; p.valid = nullptr; p.thresh = thresh; p.morph = morph; p.nslots = 0;
+    p.stat_mask = nullptr;
+    if (mem == MD_MEM_HOST) {
+        if (ctx->cfg.max_batch < 1) FAIL(MD_ERR_STATE, "md_motion_mask: no staging");
+        int r = ensure_frames(ctx, 1);
+        if (r != MD_OK) return r;
+        const long long fs = (long long)ctx->fpitch * h;
+        CK(cudaMemcpy2DAsync(ctx->d_frames, ctx->fpitch, prev, pitch, w, h, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpy2DAsync(ctx->d_frames + fs, ctx->fpitch, cur, pitch, w, h, cudaMemcpyHostToDevice, ctx->stream));
+        p.prev = ctx->d_frames; p.cur = ctx->d_frames + fs; p.pitch = ctx->fpitch; p.stride = 0;
+        p.mask = ctx->d_mask; p.mask_pitch = ctx->fpitch; p.mask_stride = 0;
+        CK(launch_mask(p, 1, ctx->stream));
+        CK(cudaMemcpy2DAsync(mask, mask_pitch, ctx->d_mask, ctx->fpitch, w, h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    } else {
+        p.prev = prev; p.cur = cur; p.pitch = pitch; p.stride = 0;
+        p.mask = mask; p.mask_pitch = mask_pitch; p.mask_stride = 0;
+        CK(launch_mask(p, 1, ctx->stream));
+    }
+    return MD_OK;
+}
+
+// ---- the chain -------------------------------------------------------------------------------------------------------
+extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outputs *out, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!fr || !out || !fr->data || (fr->channels != 1 && fr->channels != 3) || fr->count < 1 ||
+        fr->pitch < ctx->cfg.width * fr->channels)
+        FAIL(MD_ERR_INVALID, "md_process_batch: bad frame descriptor");
+    const int pairs = fr->chain ? fr->count : fr->count - 1;
+    if (pairs < 1 || pairs > ctx->cfg.max_batch) FAIL(MD_ERR_INVALID, "md_process_batch: pairs must be in [1, max_batch]");
+    if (fr->chain && !ctx->have_cached) FAIL(MD_ERR_STATE, "md_process_batch: chain=1 without a cached previous frame");
+    if (out->mask && out->mask_pitch < ctx->cfg.width) FAIL(MD_ERR_INVALID, "md_process_batch: mask_pitch too small");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int w = ctx->cfg.width, h = ctx->cfg.height, P = ctx->P, ns = ctx->g.nslots;
+
+    const uint8_t *df; int dp; long long ds;
+    int r = stage_frames(ctx, fr->data, fr->channels, fr->pitch, fr->frame_stride, fr->count, mem, &df, &dp, &ds);
+    if (r != MD_OK) return r;
+    const int prev0 = ctx->slot_base;
+    const int new0 = fr->chain ? (prev0 + 1) % ns : prev0;
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[0], s));
+    CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, new0, fr->count, df, fr->channels, dp, ds, s));
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], s));
+
+    const bool dev = mem == MD_MEM_DEVICE;
+    float2 *d_next = dev && out->next_pts ? (float2 *)out->next_pts : ctx->d_next;
+    uint8_t *d_status = dev && out->status ? out->status : ctx->d_status;
+    uint8_t *d_keep = dev && out->keep ? out->keep : ctx->d_keep;
+    double *d_H = ctx->d_H;
+    int *d_inl = ctx->d_inliers;
+
+    LkParams lp;
+    fill_lk(ctx, lp, prev0, (prev0 + 1) % ns, nullptr, P, d_next, d_status);
+    CK(launch_lk(lp, pairs, s));
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], s));
+
+    EgoParams ep;
+    fill_ego(ctx, ep, nullptr, P, d_next, d_status, d_keep, 0, ctx->cfg.ego_mode, ctx->cfg.seed + (uint32_t)ctx->pair_counter,
+             nullptr, nullptr, nullptr);
+    CK(launch_ego(ep, pairs, s));
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[3], s));
+
+    if (out->mask) {
+        MaskParams mp;
+        memset(&mp, 0, sizeof mp);
+        mp.prev = slot_plane(ctx, 0, 0); mp.cur = mp.prev;
+        mp.pitch = ctx->g.lv[0].pitch; mp.stride = (long long)ctx->g.slot_img_bytes;
+        mp.nslots = ns; mp.prev_slot0 = prev0; mp.cur_slot0 = (prev0 + 1) % ns;
+        mp.w = w; mp.h = h; mp.Hinv = ctx->d_Hinv; mp.valid = ctx->d_valid;
+        mp.thresh = ctx->cfg.diff_threshold; mp.morph = ctx->cfg.morph;
+        if (dev) { mp.mask = out->mask; mp.mask_pitch = out->mask_pitch; mp.mask_stride = out->mask_stride; }
+        else { mp.mask = ctx->d_mask; mp.mask_pitch = ctx->fpitch; mp.mask_stride = (long long)ctx->fpitch * h; }
+        mp.stat_mask = ctx->d_stats;
+        CK(launch_mask(mp, pairs, s));
+    }
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[4], s));
+
+    if (dev) {
+        if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors, ctx->d_M, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
+        if (out->H) CK(cudaMemcpyAsync(out->H, d_H, sizeof(double) * 9 * pairs, cudaMemcpyDeviceToDevice, s));
+        if (out->inliers) CK(cudaMemcpyAsync(out->inliers, d_inl, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
+    } else {
+        if (out->next_pts) CK(cudaMemcpyAsync(out->next_pts, d_next, sizeof(float2) * P * pairs, cudaMemcpyDeviceToHost, s));
+        if (out->status) CK(cudaMemcpyAsync(out->status, d_status, (size_t)P * pairs, cudaMemcpyDeviceToHost, s));
+        if (out->keep) CK(cudaMemcpyAsync(out->keep, d_keep, (size_t)P * pairs, cudaMemcpyDeviceToHost, s));
+        if (out->H) CK(cudaMemcpyAsync(out->H, d_H, sizeof(double) * 9 * pairs, cudaMemcpyDeviceToHost, s));
+        if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors, ctx->d_M, sizeof(int) * pairs, cudaMemcpyDeviceToHost, s));
+        if (out->inliers) CK(cudaMemcpyAsync(out->inliers, d_inl, sizeof(int) * pairs, cudaMemcpyDeviceToHost, s));
+        if (out->mask) {
+            if (out->mask_stride == (long long)out->mask_pitch * h)
+                CK(cudaMemcpy2DAsync(out->mask, out->mask_pitch, ctx->d_mask, ctx->fpitch, w, (size_t)h * pairs, cudaMemcpyDeviceToHost, s));
+            else
+                for (int b = 0; b < pairs; b++)
+                    CK(cudaMemcpy2DAsync(out->mask + b * out->mask_stride, out->mask_pitch, ctx->d_mask + (size_t)b * ctx->fpitch * h,
+                                         ctx->fpitch, w, h, cudaMemcpyDeviceToHost, s));
+        }
+        CK(cudaStreamSynchronize(s));
+    }
+    ctx->slot_base = (prev0 + pairs) % ns;
+    ctx->have_cached = 1;
+    ctx->pair_counter += pairs;
+    ctx->stats.pairs += pairs;
+    return MD_OK;
+}
+
+extern "C" int md_process_pair(md_ctx *ctx, const uint8_t *prev, const uint8_t *cur, int32_t channels, int32_t pitch,
+                               const md_outputs *out, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!prev || !cur) FAIL(MD_ERR_INVALID, "md_process_pair: null frame");
+    md_frames fr;
+    memset(&fr, 0, sizeof fr);
+    fr.data = prev; fr.channels = channels; fr.pitch = pitch;
+    fr.frame_stride = (int64_t)(cur - prev);
+    fr.count = 2; fr.chain = 0;
+    return md_process_batch(ctx, &fr, out, mem);
+}
+
+// ---- trajectories ----------------------------------------------------------------------------------------------------
+extern "C" int md_track_trajectories(md_ctx *ctx, const md_frames *fr, float *traj, int32_t *traj_len, float *last_prev,
+                                     float *last_next, uint8_t *last_status, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!fr || !fr->data || !traj || !traj_len || (fr->channels != 1 && fr->channels != 3) || fr->count < 2 ||
+        fr->count > ctx->g.nslots || fr->pitch < ctx->cfg.width * fr->channels || fr->chain)
+        FAIL(MD_ERR_INVALID, "md_track_trajectories: need 2..max_batch+1 frames, chain=0");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int P = ctx->P, F = fr->count;
+    if (!ctx->d_traj || ctx->traj_F < F) {
+        CK(cudaStreamSynchronize(s));
+        if (ctx->d_traj) cudaFree(ctx->d_traj);
+        if (ctx->d_traj_len) cudaFree(ctx->d_traj_len);
+        ctx->d_traj = nullptr; ctx->d_traj_len = nullptr;
+        CK(cudaMalloc((void **)&ctx->d_traj, sizeof(float2) * P * F));
+        CK(cudaMalloc((void **)&ctx->d_traj_len, sizeof(int32_t) * P));
+        ctx->traj_F = F;
+    }
+    const uint8_t *df; int dp; long long ds;
+    int r = stage_frames(ctx, fr->data, fr->channels, fr->pitch, fr->frame_stride, F, mem, &df, &dp, &ds);
+    if (r != MD_OK) return r;
+    CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, 0, F, df, fr->channels, dp, ds, s));
+    ctx->slot_base = 0; ctx->have_cached = 0;
+    const bool dev = mem == MD_MEM_DEVICE;
+    float2 *d_traj = dev ? (float2 *)traj : ctx->d_traj;
+    int32_t *d_len = dev ? traj_len : ctx->d_traj_len;
+    float2 *cur = ctx->d_pts_in;
+    CK(launch_traj_init(cur, d_traj, d_len, P, F, ctx->cfg.pixel_step, ctx->gy, s));
+    const cudaMemcpyKind outk = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int j = 0; j < F - 1; j++) {
+        LkParams lp;
+        fill_lk(ctx, lp, j, j + 1, cur, P, ctx->d_next, ctx->d_status);
+        CK(launch_lk(lp, 1, s));
+        if (j == F - 2) {
+            if (last_prev) CK(cudaMemcpyAsync(last_prev, cur, sizeof(float2) * P, outk, s));
+            if (last_next) CK(cudaMemcpyAsync(last_next, ctx->d_next, sizeof(float2) * P, outk, s));
+            if (last_status) CK(cudaMemcpyAsync(last_status, ctx->d_status, P, outk, s));
+        }
+        CK(launch_traj_step(cur, ctx->d_next, ctx->d_status, d_traj, d_len, P, F, ctx->cfg.width, ctx->cfg.height, s));
+    }
+    if (!dev) {
+        CK(cudaMemcpyAsync(traj, d_traj, sizeof(float2) * P * F, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(traj_len, d_len, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return MD_OK;
+}
+
+// ---- statistics --------------------------------------------------------------------------------------------------------
+extern "C" int md_stats_get(md_ctx *ctx, md_stats *out)
+{
+    if (!ctx || !out) return MD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long v[4];
+    CK(cudaMemcpyAsync(v, ctx->d_stats, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->stats.last_H, ctx->d_H, sizeof(double) * 9, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.mask_pixels = (int64_t)v[0];
+    ctx->stats.tracked = (int64_t)v[1];
+    ctx->stats.inliers = (int64_t)v[2];
+    ctx->stats.kernel_launches = g_md_launches;
+    *out = ctx->stats;
+    return MD_OK;
+}
+
+extern "C" int md_stats_reset(md_ctx *ctx)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(unsigned long long) * 4, ctx->stream));
+    int dev = ctx->stats.device;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.device = dev;
+    return MD_OK;
+}
+
+// ---- measurement hook ----------------------------------------------------------------------------------------------------
+extern "C" int md_profile(md_ctx *ctx, int enable)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (enable)
+        for (int i = 0; i < 5; i++)
+            if (!ctx->ev[i]) CK(cudaEventCreate(&ctx->ev[i]));
+    ctx->profile = enable ? 1 : 0;
+    return MD_OK;
+}
+
+extern "C" int md_profile_read(md_ctx *ctx, float *ms4)
+{
+    if (!ctx || !ms4) return MD_ERR_INVALID;
+    if (!ctx->ev[4]) FAIL(MD_ERR_STATE, "md_profile_read: profiling was never enabled");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev[4]));
+    for (int i = 0; i < 4; i++) CK(cudaEventElapsedTime(&ms4[i], ctx->ev[i], ctx->ev[i + 1]));
+    return MD_OK;
+}

@@ -1,0 +1,143 @@
+// md_internal.h -- context layout and kernel launch prototypes shared by the .cu files of libmotion_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/motion_b200.h"
+
+#define MD_MAX_LEVELS 8
+#define MD_MAX_HYP 256
+
+// Pyramid planes are stored PADDED, exactly like cv::buildOpticalFlowPyramid does (winSize border):
+// image planes carry a BORDER_REFLECT_101 frame, derivative planes a zero frame, so the LK window reads
+// (which reach from -win to w+win-1) never need border logic.
+struct LevelGeom {
+    int w, h;          // interior size
+    int pitch;         // elements per padded row (u8 for images, short2 for derivatives); multiple of 128
+    int rows;          // h + 2*pady
+    size_t img_off;    // byte offset of the padded plane inside a slot's image arena
+    size_t der_off;    // short2 offset of the padded plane inside a slot's derivative arena
+};
+
+struct PyrGeom {
+    int nlev;
+    int padx, pady;
+    LevelGeom lv[MD_MAX_LEVELS];
+    size_t slot_img_bytes;   // bytes per slot (all levels)
+    size_t slot_der_elems;   // short2 per slot
+    int nslots;
+};
+
+struct LkParams {
+    PyrGeom g;
+    const uint8_t *img;      // slot 0 image arena
+    const short2 *der;       // slot 0 derivative arena
+    int prev_slot0, next_slot0;   // pair b uses slots (prev_slot0 + b) % nslots, (next_slot0 + b) % nslots
+    const float2 *pts_in;    // [pairs][P] or nullptr (grid)
+    int ps, gy;              // grid: x = ps * (k / gy), y = ps * (k % gy)
+    int P;
+    float2 *next;            // [pairs][P]
+    uint8_t *status;         // [pairs][P]
+    int win, max_iters;
+    double eps2;
+    float min_eig;
+};
+
+struct EgoParams {
+    int P, ps, gy;
+    const float2 *pts_in;    // nullptr = grid
+    const float2 *next;      // [pairs][P]
+    const uint8_t *status;   // [pairs][P]
+    uint8_t *keep;           // [pairs][P]
+    int keep_given;          // 1: keep[] is an input
+    double min_vec;
+    int mode, iters, minimal;
+    double thr2;
+    uint32_t seed0;          // pair b uses seed0 + b
+    int w, h;
+    int nblk_scan;           // blocks per pair for keep/compact (2048 items each)
+    int nblk_acc;            // blocks per pair for the normal-equation accumulation
+    int *blockcnt;           // [pairs][nblk_scan]
+    int *kept_idx;           // [pairs][P]
+    int *M;                  // [pairs]
+    double *hyp;             // [pairs][iters][9]
+    int *hyp_valid;          // [pairs][iters]
+    int *counts;             // [pairs][iters]
+    double *partial;         // [pairs][nblk_acc][48]
+    double *H, *Hinv;        // [pairs][9]
+    int *inliers;            // [pairs]
+    int *valid;              // [pairs] 1 = mask may be computed
+    uint8_t *inlier_mask;    // [pairs][P] or nullptr
+    unsigned long long *stat_tracked, *stat_inliers;
+};
+
+struct MaskParams {
+    // frame b of prev lives at prev + ((prev_slot0 + b) % nslots) * stride when nslots > 0 (pyramid ring),
+    // at prev + b * stride when nslots == 0 (plain frame arrays); same for cur.
+    const uint8_t *prev, *cur;
+    int pitch;
+    long long stride;
+    int nslots, prev_slot0, cur_slot0;
+    int w, h;
+    const double *Hinv;      // [pairs][9] device
+    const int *valid;        // [pairs] device (nullptr = always valid)
+    int thresh, morph;
+    uint8_t *mask;
+    int mask_pitch;
+    long long mask_stride;
+    unsigned long long *stat_mask;   // nullable
+};
+
+struct md_ctx {
+    md_config cfg;
+    int device;
+    cudaStream_t own_stream, stream;
+    std::string err;
+    int sm_count;
+
+    PyrGeom g;
+    uint8_t *d_img;
+    short2 *d_der;
+    int P, gx, gy;
+    int slot_base;        // slot holding frame 0 of the current batch
+    int have_cached;      // slot_base holds a valid pyramid of the last frame of the previous batch
+    uint64_t pair_counter;
+
+    // staging for host-memory calls / plain frames
+    uint8_t *d_frames;    // [(max_batch+1)][h][fpitch*channels], allocated on first host-memory call
+    int frames_channels;
+    int fpitch;
+    uint8_t *d_mask;      // [max_batch][h][fpitch]
+    float2 *d_pts_in;     // [max_batch][P]
+    float2 *d_next;
+    uint8_t *d_status, *d_keep, *d_inlier_mask;
+    size_t pts_cap;       // capacity (points per pair) of the per-point buffers
+
+    // egomotion workspace
+    int nblk_scan, nblk_acc;
+    int *d_blockcnt, *d_kept_idx, *d_M, *d_hyp_valid, *d_counts, *d_inliers, *d_valid;
+    double *d_hyp, *d_partial, *d_H, *d_Hinv;
+    unsigned long long *d_stats;   // [0] mask px, [1] tracked, [2] inliers
+    float2 *d_traj;       // [P][F] trajectory staging (host-memory calls)
+    int32_t *d_traj_len;
+    int traj_F;
+    md_stats stats;
+    int profile;
+    cudaEvent_t ev[5];
+};
+
+extern long long g_md_launches;   // kernels launched by this library (process wide)
+#define MD_COUNT_LAUNCH(n) (g_md_launches += (n))
+
+// kernel launchers (each in its own .cu)
+cudaError_t launch_gray(const uint8_t *src3, int src_pitch, int w, int h, uint8_t *dst, int dst_pitch, cudaStream_t s);
+cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot0, int nframes, const uint8_t *frames,
+                           int channels, int fpitch, long long fstride, cudaStream_t s);
+cudaError_t launch_lk(const LkParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_ego(const EgoParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_mask(const MaskParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_traj_step(float2 *pts_cur, const float2 *next, const uint8_t *status, float2 *traj, int32_t *len,
+                             int P, int F, int w, int h, cudaStream_t s);
+cudaError_t launch_traj_init(float2 *pts_cur, float2 *traj, int32_t *len, int P, int F, int ps, int gy, cudaStream_t s);

@@ -1,0 +1,78 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares,
+struct layouts agree between C and ctypes, and the product fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "motion_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(md_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(capi):
+    lib = capi.lib()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), "libmotion_b200.so does not export %s" % s
+    assert sorted(capi.SYMBOLS) == syms
+
+
+def test_struct_layouts_match_c(capi, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "motion_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(md_config),sizeof(md_frames),sizeof(md_outputs),sizeof(md_stats),offsetof(md_config,lk_eps),'
+                   'offsetof(md_config,ransac_thresh),offsetof(md_config,vf_rho));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    want = [C.sizeof(capi.MdConfig), C.sizeof(capi.MdFrames), C.sizeof(capi.MdOutputs), C.sizeof(capi.MdStats),
+            capi.MdConfig.lk_eps.offset, capi.MdConfig.ransac_thresh.offset, capi.MdConfig.vf_rho.offset]
+    assert got == want
+
+
+def test_defaults_are_the_reference_constants(capi):
+    cfg = capi.default_config()
+    # optical_flow_calculator.cpp:40-44,71,127 ; outlier_detector.cpp:250 ; cpp:422-429
+    assert (cfg.lk_win, cfg.lk_max_level, cfg.lk_max_iters) == (40, 5, 10)
+    assert abs(cfg.lk_eps - 0.03) < 1e-12 and abs(cfg.lk_min_eig - 0.001) < 1e-9
+    assert cfg.diff_threshold == 190 and cfg.morph == 1 and cfg.ransac_iters == 50
+    assert (cfg.vf_max_level, cfg.vf_start_level, cfg.vf_n1, cfg.vf_n2) == (4, 0, 2, 2)
+    assert abs(cfg.vf_rho - 2.8) < 1e-6 and cfg.vf_alpha == 1400.0 and cfg.vf_sigma == 1.5
+    assert cfg.pixel_step == 10 and cfg.min_vector_size == 1.0
+
+
+def test_no_cpu_fallback_without_gpu(capi):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.MotionB200Error) as e:
+        capi.Context(width=64, height=64)
+    assert e.value.code == -2
+
+
+def test_invalid_arguments_return_status_codes(capi):
+    lib = capi.lib()
+    assert lib.md_config_default(None) == -1
+    cfg = capi.default_config(width=4, height=4)
+    h = C.c_void_p()
+    assert lib.md_create(C.byref(cfg), 0, C.byref(h)) == -1
+    assert lib.md_destroy(None) == -1
+    assert lib.md_grid_size(None) == -1
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "motion_detection_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("no CPU fallback and nothing here imports oracle/", "") \
+                    .replace("the oracle's", "").replace("the oracle", "").replace("CPU oracle", "").replace("oracle operation order", ""), f
