@@ -151,7 +151,11 @@ def main():
 
     ctx = capi.Context(width=w, height=h, max_batch=B, pixel_step=a.pixel_step, min_vector_size=0.2, seed=1, device=local)
     P = ctx.P
-    stream = torch.cuda.current_stream()
+    # all kernels AND the timing events go on one explicit (non-default) torch stream: handle 0 would mean
+    # "the context's own stream" to md_set_stream and the events would not bracket the work
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx.set_stream(stream.cuda_stream)
 
     frames_np = make_frames(a, rank, B + 1)

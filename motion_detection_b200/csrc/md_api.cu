@@ -103,8 +103,9 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
     const int w = cfg->width, h = cfg->height, B = cfg->max_batch;
     PyrGeom &g = ctx->g;
     g.nlev = pyr_levels(w, h, cfg->lk_win, cfg->lk_max_level) + 1;
-    g.padx = align_up(cfg->lk_win, 16);
-    g.pady = cfg->lk_win;
+    // window reach (win) + the drift margin of the shared-memory J tiles staged by k_lk_tiled (k_lk.cu)
+    g.padx = align_up(cfg->lk_win + 8, 16) + 16;
+    g.pady = cfg->lk_win + 8;
     g.nslots = B + 1;
     size_t ioff = 0, doff = 0;
     int lw = w, lh = h;

@@ -126,7 +126,7 @@ def test_egomotion_first4_nondegenerate(capi, oracle):
     # strict mode (optical_flow_calculator.cpp:120) on four non-collinear leading vectors
     w, h = 160, 120
     ctx = _ctx(capi, w, h, pixel_step=50)
-    src = np.array([[0, 0], [0, 50], [0, 100], [50, 0], [50, 50], [100, 100]], np.float32)
+    src = np.array([[0, 0], [0, 50], [50, 100], [100, 0], [50, 50], [100, 100]], np.float32)
     Ht = np.array([[1.01, 0.02, 1.5], [-0.01, 0.99, -0.7], [1e-5, -2e-5, 1.0]])
     q = (Ht @ np.c_[src, np.ones(len(src))].T).T
     dst = (q[:, :2] / q[:, 2:]).astype(np.float32)
