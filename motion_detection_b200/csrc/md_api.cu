@@ -8,6 +8,7 @@
 #include <new>
 
 #include "md_internal.h"
+#include "tma.h"
 
 #define CK(call)                                                                                      \
     do {                                                                                              \
@@ -160,6 +161,22 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
              cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     }
     if (!ok) { free_ctx(ctx); return MD_ERR_NOMEM; }
+    // TMA tensor maps over the padded planes (x, y, slot) for the production LK kernel (window 40)
+    ctx->lk_maps.valid = 0;
+    if (cfg->lk_win == 40) {
+        bool mok = true;
+        for (int l = 0; l < g.nlev && mok; l++) {
+            const LevelGeom &L = g.lv[l];
+            mok = tma_encode_3d(&ctx->lk_maps.imgI[l], 1, ctx->d_img + L.img_off, L.pitch, L.rows, g.nslots, L.pitch,
+                                g.slot_img_bytes, MD_LK_I_BOX_W, 41) &&
+                  tma_encode_3d(&ctx->lk_maps.imgJ[l], 1, ctx->d_img + L.img_off, L.pitch, L.rows, g.nslots, L.pitch,
+                                g.slot_img_bytes, MD_LK_J_BOX_W, 41 + 2 * MD_LK_J_MARGIN_Y) &&
+                  tma_encode_3d(&ctx->lk_maps.der[l], 4, ctx->d_der + L.der_off, L.pitch, L.rows, g.nslots, (uint64_t)L.pitch * 4,
+                                g.slot_der_elems * 4, MD_LK_D_BOX_W, 41);
+        }
+        if (!mok) { free_ctx(ctx); return MD_ERR_CUDA; }
+        ctx->lk_maps.valid = 1;
+    }
     ctx->stats.device = device;
     *out = ctx;
     return MD_OK;
@@ -344,7 +361,7 @@ extern "C" int md_lk_flow(md_ctx *ctx, int slot_prev, int slot_next, const float
     } else d_in = (const float2 *)pts_in;
     LkParams p;
     fill_lk(ctx, p, slot_prev, slot_next, d_in, npts, d_out, d_st);
-    CK(launch_lk(p, 1, ctx->stream));
+    CK(launch_lk(p, &ctx->lk_maps, 1, ctx->stream));
     if (mem == MD_MEM_HOST) {
         CK(cudaMemcpyAsync(pts_out, d_out, sizeof(float2) * npts, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(status, d_st, npts, cudaMemcpyDeviceToHost, ctx->stream));
@@ -494,7 +511,7 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
 
     LkParams lp;
     fill_lk(ctx, lp, prev0, (prev0 + 1) % ns, nullptr, P, d_next, d_status);
-    CK(launch_lk(lp, pairs, s));
+    CK(launch_lk(lp, &ctx->lk_maps, pairs, s));
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], s));
 
     EgoParams ep;
@@ -593,7 +610,7 @@ extern "C" int md_track_trajectories(md_ctx *ctx, const md_frames *fr, float *tr
     for (int j = 0; j < F - 1; j++) {
         LkParams lp;
         fill_lk(ctx, lp, j, j + 1, cur, P, ctx->d_next, ctx->d_status);
-        CK(launch_lk(lp, 1, s));
+        CK(launch_lk(lp, &ctx->lk_maps, 1, s));
         if (j == F - 2) {
             if (last_prev) CK(cudaMemcpyAsync(last_prev, cur, sizeof(float2) * P, outk, s));
             if (last_next) CK(cudaMemcpyAsync(last_next, ctx->d_next, sizeof(float2) * P, outk, s));

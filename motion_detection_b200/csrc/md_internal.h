@@ -1,5 +1,6 @@
 // md_internal.h -- context layout and kernel launch prototypes shared by the .cu files of libmotion_b200.so.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -28,6 +29,22 @@ struct PyrGeom {
     size_t slot_img_bytes;   // bytes per slot (all levels)
     size_t slot_der_elems;   // short2 per slot
     int nslots;
+};
+
+// Shared-memory tile geometry of k_lk_tma (boxes of the per-level TMA tensor maps), window = 40.
+#define MD_LK_I_BOX_W 64        // bytes: <= 15 alignment offset + 41 window columns + the over-read word, multiple of 16
+#define MD_LK_J_BOX_W 80        // bytes: window + drift margin
+#define MD_LK_D_BOX_W 44        // short2 elements (176 bytes)
+#define MD_LK_J_MARGIN_X 8
+#define MD_LK_J_MARGIN_Y 3
+
+// Per-level tensor maps over the padded pyramid planes: dims (x, y, slot).  128 bytes each, passed as a
+// __grid_constant__ kernel parameter.
+struct alignas(64) LkTmaMaps {
+    CUtensorMap imgI[MD_MAX_LEVELS];   // u8, box 64 x 41
+    CUtensorMap imgJ[MD_MAX_LEVELS];   // u8, box 80 x 47
+    CUtensorMap der[MD_MAX_LEVELS];    // u32 (short2), box 44 x 41
+    int valid;
 };
 
 struct LkParams {
@@ -126,6 +143,7 @@ struct md_ctx {
     md_stats stats;
     int profile;
     cudaEvent_t ev[5];
+    LkTmaMaps lk_maps;
 };
 
 extern long long g_md_launches;   // kernels launched by this library (process wide)
@@ -135,7 +153,7 @@ extern long long g_md_launches;   // kernels launched by this library (process w
 cudaError_t launch_gray(const uint8_t *src3, int src_pitch, int w, int h, uint8_t *dst, int dst_pitch, cudaStream_t s);
 cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot0, int nframes, const uint8_t *frames,
                            int channels, int fpitch, long long fstride, cudaStream_t s);
-cudaError_t launch_lk(const LkParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_lk(const LkParams &p, const LkTmaMaps *maps, int pairs, cudaStream_t s);
 cudaError_t launch_ego(const EgoParams &p, int pairs, cudaStream_t s);
 cudaError_t launch_mask(const MaskParams &p, int pairs, cudaStream_t s);
 cudaError_t launch_traj_step(float2 *pts_cur, const float2 *next, const uint8_t *status, float2 *traj, int32_t *len,
