@@ -117,12 +117,12 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_lk_tma(const LkParams p, cons
 {
     using T = LkTile<WIN>;
     constexpr int TW = T::TW, TH = T::TH, NP = T::NP;
-    extern __shared__ uint8_t lk_sm_raw[];
+    extern __shared__ __align__(1024) uint8_t lk_sm_raw[];     // dynamic smem starts 1 KB aligned; keep shared-space pointers
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int k = blockIdx.x * WARPS + warp;
     const int b = blockIdx.y;
     if (k >= p.P) return;
-    uint8_t *wbase = reinterpret_cast<uint8_t *>(((uintptr_t)lk_sm_raw + 127) & ~(uintptr_t)127) + (size_t)warp * T::WARP_BYTES;
+    uint8_t *wbase = lk_sm_raw + (size_t)warp * T::WARP_BYTES;
     uint32_t *tI = reinterpret_cast<uint32_t *>(wbase + T::I_OFF);
     uint32_t *tJ = reinterpret_cast<uint32_t *>(wbase + T::J_OFF);
     uint32_t *tD = reinterpret_cast<uint32_t *>(wbase + T::D_OFF);

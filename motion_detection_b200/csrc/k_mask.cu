@@ -12,29 +12,24 @@
 // 5-bit fraction; out = ((32-ax)(32-ay) p00 + ax(32-ay) p01 + (32-ax)ay p10 + ax ay p11 + 512) >> 10, taps outside the
 // image read 0.  Threshold is strict '>'.  Erode ignores out-of-image pixels (identity 255), dilate likewise (identity 0).
 //
-// v1 layout: CTA = 256 threads, output tile 128 x 16, thresholded bits for the (tile + 2) halo kept in shared memory.
+// Layout: CTA = 256 threads, output tile 128 x 32.  A thread owns runs of 4 consecutive pixels: the thresholded
+// bytes (0x00 / 0xFF) of a run are one 32-bit word in shared memory, so the 3x3 erode / dilate are AND / OR of nine
+// funnel-shifted words (four pixels per instruction) and the mask leaves as coalesced 32-bit stores.
+// The per-pixel projective divide is the FP64 cost centre: 32/den is taken from a Newton-refined reciprocal
+// (error < 1e-15 relative), and only when the scaled coordinate lands within 1e-7 of a rounding boundary -- where the
+// last-bit difference to the correctly rounded quotient could change rint() -- is the IEEE division redone, so the
+// result stays bit-identical to the reference at a third of the FP64 work.
 #include "md_internal.h"
 
 #define TW 128
-#define TH 16
-#define RW (TW + 4)
-#define RH (TH + 4)
+#define TH 32
+#define GW (TW / 4 + 2)      // 34 groups of 4 columns: [tx0 - 4, tx0 + 132)
+#define TR (TH + 4)          // 36 rows of thresholded words
+#define ER (TH + 2)          // 34 rows of eroded words
+#define SP (GW + 1)          // shared-memory pitch in words
 
-__device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int pitch, int w, int h, const double *M,
-                                           int x, int y, int bw0)
+__device__ __forceinline__ int bilinear_fetch(const uint8_t *__restrict__ src, int pitch, int w, int h, int X, int Y)
 {
-    const int bx = x - x % bw0, x1 = x - bx;
-    const double dbx = (double)bx, dy = (double)y, dx1 = (double)x1;
-    const double X0 = __dadd_rn(__dadd_rn(__dmul_rn(M[0], dbx), __dmul_rn(M[1], dy)), M[2]);
-    const double Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M[3], dbx), __dmul_rn(M[4], dy)), M[5]);
-    const double W0 = __dadd_rn(__dadd_rn(__dmul_rn(M[6], dbx), __dmul_rn(M[7], dy)), M[8]);
-    double W = __dadd_rn(W0, __dmul_rn(M[6], dx1));
-    W = W != 0.0 ? __ddiv_rn(32.0, W) : 0.0;
-    double fX = __dmul_rn(__dadd_rn(X0, __dmul_rn(M[0], dx1)), W);
-    double fY = __dmul_rn(__dadd_rn(Y0, __dmul_rn(M[3], dx1)), W);
-    fX = fmax(-2147483648.0, fmin(2147483647.0, fX));
-    fY = fmax(-2147483648.0, fmin(2147483647.0, fY));
-    const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
     int sx = X >> 5, sy = Y >> 5;
     sx = max(-32768, min(32767, sx));
     sy = max(-32768, min(32767, sy));
@@ -55,20 +50,45 @@ __device__ __forceinline__ int warp_sample(const uint8_t *__restrict__ src, int 
     return (v + 512) >> 10;
 }
 
+// rint(num * (32 / den)) exactly as the reference computes it (W = den ? 32/den : 0; fX = num * W; saturating rint)
+__device__ __forceinline__ void project(double nx, double ny, double den, int &X, int &Y)
+{
+    if (den == 0.0) { X = 0; Y = 0; return; }
+    // Newton-refined reciprocal: two steps from the f32 seed give < 1e-15 relative error
+    double r = (double)__frcp_rn((float)den);
+    r = fma(r, fma(-den, r, 1.0), r);
+    r = fma(r, fma(-den, r, 1.0), r);
+    const double W = 32.0 * r;
+    const double fX = nx * W, fY = ny * W;
+    X = __double2int_rn(fX);
+    Y = __double2int_rn(fY);
+    // distance to the nearest rounding boundary (k + 0.5); tiny -> the last bits of W matter -> exact path
+    const double dx = 0.5 - fabs(fX - (double)X), dy = 0.5 - fabs(fY - (double)Y);
+    const double tol = 1e-7;
+    // (|fX| < 1e6 bounds the absolute error of the fast path by 1e6 * 7e-16 << tol; it also catches inf / NaN)
+    if (dx < tol || dy < tol || !(fabs(fX) < 1e6) || !(fabs(fY) < 1e6)) {
+        const double We = __ddiv_rn(32.0, den);
+        X = __double2int_rn(__dmul_rn(nx, We));     // cvt.rni.s32.f64 saturates like the reference's clamp
+        Y = __double2int_rn(__dmul_rn(ny, We));
+    }
+}
+
+template <bool ALIGNED>
 __global__ void __launch_bounds__(256) k_mask(const MaskParams p)
 {
-    __shared__ uint8_t T[RH][RW + 4];
-    __shared__ uint8_t E[RH][RW + 4];
+    __shared__ uint32_t T[TR][SP];
+    __shared__ uint32_t E[ER][SP];
     __shared__ double sM[9];
     const int b = blockIdx.z;
     const int tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     uint8_t *out = p.mask + (size_t)b * p.mask_stride;
     const bool valid = p.valid ? p.valid[b] != 0 : true;
+    const int w = p.w, h = p.h;
     if (!valid) {
         // no egomotion (fewer than the minimal number of vectors): empty mask
         for (int i = threadIdx.x; i < TW * TH; i += 256) {
             int x = tx0 + i % TW, y = ty0 + i / TW;
-            if (x < p.w && y < p.h) out[(size_t)y * p.mask_pitch + x] = 0;
+            if (x < w && y < h) out[(size_t)y * p.mask_pitch + x] = 0;
         }
         return;
     }
@@ -76,57 +96,126 @@ __global__ void __launch_bounds__(256) k_mask(const MaskParams p)
     __syncthreads();
     const uint8_t *prev = p.prev + (long long)(p.nslots ? (p.prev_slot0 + b) % p.nslots : b) * p.stride;
     const uint8_t *cur = p.cur + (long long)(p.nslots ? (p.cur_slot0 + b) % p.nslots : b) * p.stride;
-    const int bh0 = p.h < 16 ? p.h : 16;
-    const int bw0 = (1024 / bh0 < p.w) ? 1024 / bh0 : p.w;
-    for (int i = threadIdx.x; i < RW * RH; i += 256) {
-        const int rx = i % RW, ry = i / RW;
-        const int x = tx0 + rx - 2, y = ty0 + ry - 2;
-        uint8_t t = 255;   // erode identity outside the image
-        if (x >= 0 && y >= 0 && x < p.w && y < p.h) {
-            int wv = warp_sample(prev, p.pitch, p.w, p.h, sM, x, y, bw0);
-            int d = wv - (int)__ldg(cur + (size_t)y * p.pitch + x);
-            d = d < 0 ? -d : d;
-            t = d > p.thresh ? 255 : 0;
+    const int bh0 = h < 16 ? h : 16;
+    const int bw0 = (1024 / bh0 < w) ? 1024 / bh0 : w;
+    const double M0 = sM[0], M1 = sM[1], M2 = sM[2], M3 = sM[3], M4 = sM[4], M5 = sM[5], M6 = sM[6], M7 = sM[7], M8 = sM[8];
+    const bool uniform_block = (bw0 & 3) == 0;     // a run of 4 aligned columns never straddles a 64-column block
+
+    // ---- phase 1: warp + absdiff + threshold, 4 pixels per thread-iteration ---------------------------------------
+    for (int g = threadIdx.x; g < GW * TR; g += 256) {
+        const int ry = g / GW, gx = g - ry * GW;
+        const int x = tx0 - 4 + 4 * gx, y = ty0 - 2 + ry;
+        uint32_t word = 0xffffffffu;            // erode identity outside the image
+        if (y >= 0 && y < h && x + 3 >= 0 && x < w) {
+            uint32_t c4;
+            if (ALIGNED && x >= 0 && x + 3 < w) c4 = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)y * p.pitch + x));
+            else {
+                c4 = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (x + j >= 0 && x + j < w) c4 |= (uint32_t)__ldg(cur + (size_t)y * p.pitch + x + j) << (8 * j);
+            }
+            const double dy = (double)y;
+            double X0 = 0, Y0 = 0, W0 = 0;
+            int bx = 0;
+            if (uniform_block) {
+                const int xc = x < 0 ? 0 : x;
+                bx = xc - xc % bw0;
+                const double dbx = (double)bx;
+                X0 = __dadd_rn(__dadd_rn(__dmul_rn(M0, dbx), __dmul_rn(M1, dy)), M2);
+                Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M3, dbx), __dmul_rn(M4, dy)), M5);
+                W0 = __dadd_rn(__dadd_rn(__dmul_rn(M6, dbx), __dmul_rn(M7, dy)), M8);
+            }
+            word = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int xj = x + j;
+                uint32_t t = 0xffu;
+                if (xj >= 0 && xj < w) {
+                    if (!uniform_block) {
+                        bx = xj - xj % bw0;
+                        const double dbx = (double)bx;
+                        X0 = __dadd_rn(__dadd_rn(__dmul_rn(M0, dbx), __dmul_rn(M1, dy)), M2);
+                        Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M3, dbx), __dmul_rn(M4, dy)), M5);
+                        W0 = __dadd_rn(__dadd_rn(__dmul_rn(M6, dbx), __dmul_rn(M7, dy)), M8);
+                    }
+                    const double dx1 = (double)(xj - bx);
+                    const double den = __dadd_rn(W0, __dmul_rn(M6, dx1));
+                    const double nx = __dadd_rn(X0, __dmul_rn(M0, dx1)), ny = __dadd_rn(Y0, __dmul_rn(M3, dx1));
+                    int X, Y;
+                    project(nx, ny, den, X, Y);
+                    const int wv = bilinear_fetch(prev, p.pitch, w, h, X, Y);
+                    int d = wv - (int)((c4 >> (8 * j)) & 0xffu);
+                    d = d < 0 ? -d : d;
+                    t = d > p.thresh ? 0xffu : 0u;
+                }
+                word |= t << (8 * j);
+            }
         }
-        T[ry][rx] = t;
+        T[ry][gx] = word;
     }
     __syncthreads();
+
     int local = 0;
     if (p.morph) {
-        for (int i = threadIdx.x; i < (TW + 2) * (TH + 2); i += 256) {
-            const int rx = i % (TW + 2) + 1, ry = i / (TW + 2) + 1;
-            const int x = tx0 + rx - 2, y = ty0 + ry - 2;
-            uint8_t e = 0;     // dilate identity outside the image
-            if (x >= 0 && y >= 0 && x < p.w && y < p.h) {
-                e = 255;
+        // ---- phase 2: erode = AND of the nine neighbours, four pixels per word ----------------------------------
+        for (int g = threadIdx.x; g < GW * ER; g += 256) {
+            const int ry = g / GW, gx = g - ry * GW;
+            const int x = tx0 - 4 + 4 * gx, y = ty0 - 1 + ry;
+            uint32_t e = 0xffffffffu;
 #pragma unroll
-                for (int j = -1; j <= 1; j++)
-#pragma unroll
-                    for (int k = -1; k <= 1; k++) e = min(e, T[ry + j][rx + k]);
+            for (int j = 0; j < 3; j++) {
+                const uint32_t c = T[ry + j][gx];
+                const uint32_t l = gx > 0 ? T[ry + j][gx - 1] : 0xffffffffu;
+                const uint32_t r = gx < GW - 1 ? T[ry + j][gx + 1] : 0xffffffffu;
+                e &= c & __funnelshift_l(l, c, 8) & __funnelshift_r(c, r, 8);
             }
-            E[ry][rx] = e;
+            // dilate identity (0) for pixels outside the image
+            uint32_t m = 0;
+            if (y >= 0 && y < h) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (x + j >= 0 && x + j < w) m |= 0xffu << (8 * j);
+            }
+            E[ry][gx] = e & m;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < TW * TH; i += 256) {
-            const int rx = i % TW + 2, ry = i / TW + 2;
-            const int x = tx0 + rx - 2, y = ty0 + ry - 2;
-            if (x < p.w && y < p.h) {
-                uint8_t m = 0;
+        // ---- phase 3: dilate = OR of the nine neighbours, coalesced 32-bit stores -------------------------------
+        for (int g = threadIdx.x; g < (TW / 4) * TH; g += 256) {
+            const int ry = g / (TW / 4), go = g - ry * (TW / 4);
+            const int gx = go + 1;
+            const int x = tx0 + 4 * go, y = ty0 + ry;
+            if (x >= w || y >= h) continue;
+            uint32_t o = 0;
 #pragma unroll
-                for (int j = -1; j <= 1; j++)
+            for (int j = 0; j < 3; j++) {
+                const uint32_t c = E[ry + j][gx], l = E[ry + j][gx - 1], r = E[ry + j][gx + 1];
+                o |= c | __funnelshift_l(l, c, 8) | __funnelshift_r(c, r, 8);
+            }
+            uint8_t *dst = out + (size_t)y * p.mask_pitch + x;
+            if (ALIGNED && x + 3 < w) {
+                *reinterpret_cast<uint32_t *>(dst) = o;
+                local += __popc(o & 0x01010101u);
+            } else {
 #pragma unroll
-                    for (int k = -1; k <= 1; k++) m = max(m, E[ry + j][rx + k]);
-                out[(size_t)y * p.mask_pitch + x] = m;
-                local += m != 0;
+                for (int j = 0; j < 4; j++)
+                    if (x + j < w) { dst[j] = (uint8_t)(o >> (8 * j)); local += (o >> (8 * j)) & 1; }
             }
         }
     } else {
-        for (int i = threadIdx.x; i < TW * TH; i += 256) {
-            const int rx = i % TW + 2, ry = i / TW + 2;
-            const int x = tx0 + rx - 2, y = ty0 + ry - 2;
-            if (x < p.w && y < p.h) {
-                out[(size_t)y * p.mask_pitch + x] = T[ry][rx];
-                local += T[ry][rx] != 0;
+        for (int g = threadIdx.x; g < (TW / 4) * TH; g += 256) {
+            const int ry = g / (TW / 4), go = g - ry * (TW / 4);
+            const int x = tx0 + 4 * go, y = ty0 + ry;
+            if (x >= w || y >= h) continue;
+            const uint32_t o = T[ry + 2][go + 1];
+            uint8_t *dst = out + (size_t)y * p.mask_pitch + x;
+            if (ALIGNED && x + 3 < w) {
+                *reinterpret_cast<uint32_t *>(dst) = o;
+                local += __popc(o & 0x01010101u);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (x + j < w) { dst[j] = (uint8_t)(o >> (8 * j)); local += (o >> (8 * j)) & 1; }
             }
         }
     }
@@ -139,7 +228,10 @@ __global__ void __launch_bounds__(256) k_mask(const MaskParams p)
 cudaError_t launch_mask(const MaskParams &p, int pairs, cudaStream_t s)
 {
     dim3 grid((p.w + TW - 1) / TW, (p.h + TH - 1) / TH, pairs);
-    k_mask<<<grid, 256, 0, s>>>(p);
+    const bool aligned = (((uintptr_t)p.cur | (uintptr_t)p.mask | (uintptr_t)p.pitch | (uintptr_t)p.mask_pitch |
+                           (uintptr_t)p.stride | (uintptr_t)p.mask_stride) & 3) == 0;
+    if (aligned) k_mask<true><<<grid, 256, 0, s>>>(p);
+    else k_mask<false><<<grid, 256, 0, s>>>(p);
     MD_COUNT_LAUNCH(1);
     return cudaGetLastError();
 }
