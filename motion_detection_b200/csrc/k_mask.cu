@@ -31,22 +31,30 @@
 __device__ __forceinline__ int bilinear_fetch(const uint8_t *__restrict__ src, int pitch, int w, int h, int X, int Y)
 {
     int sx = X >> 5, sy = Y >> 5;
-    sx = max(-32768, min(32767, sx));
-    sy = max(-32768, min(32767, sy));
     const int ax = X & 31, ay = Y & 31;
     int p00 = 0, p01 = 0, p10 = 0, p11 = 0;
-    const bool x0in = (unsigned)sx < (unsigned)w, x1in = (unsigned)(sx + 1) < (unsigned)w;
-    if ((unsigned)sy < (unsigned)h) {
-        const uint8_t *r = src + (size_t)sy * pitch;
-        if (x0in) p00 = __ldg(r + sx);
-        if (x1in) p01 = __ldg(r + sx + 1);
+    if ((unsigned)sx < (unsigned)(w - 1) && (unsigned)sy < (unsigned)(h - 1)) {
+        // common case: the 2x2 footprint is inside the image -> four unconditional loads from one base
+        const uint8_t *r = src + (sy * pitch + sx);
+        p00 = __ldg(r); p01 = __ldg(r + 1); p10 = __ldg(r + pitch); p11 = __ldg(r + pitch + 1);
+    } else {
+        sx = max(-32768, min(32767, sx));      // saturate_cast<short> of the remap tables
+        sy = max(-32768, min(32767, sy));
+        const bool x0in = (unsigned)sx < (unsigned)w, x1in = (unsigned)(sx + 1) < (unsigned)w;
+        if ((unsigned)sy < (unsigned)h) {
+            const uint8_t *r = src + (size_t)sy * pitch;
+            if (x0in) p00 = __ldg(r + sx);
+            if (x1in) p01 = __ldg(r + sx + 1);
+        }
+        if ((unsigned)(sy + 1) < (unsigned)h) {
+            const uint8_t *r = src + (size_t)(sy + 1) * pitch;
+            if (x0in) p10 = __ldg(r + sx);
+            if (x1in) p11 = __ldg(r + sx + 1);
+        }
     }
-    if ((unsigned)(sy + 1) < (unsigned)h) {
-        const uint8_t *r = src + (size_t)(sy + 1) * pitch;
-        if (x0in) p10 = __ldg(r + sx);
-        if (x1in) p11 = __ldg(r + sx + 1);
-    }
-    const int v = (32 - ax) * (32 - ay) * p00 + ax * (32 - ay) * p01 + (32 - ax) * ay * p10 + ax * ay * p11;
+    // (32-ax)(32-ay), ax(32-ay), (32-ax)ay, ax*ay from one product
+    const int w11 = ax * ay, w01 = (ax << 5) - w11, w10 = (ay << 5) - w11, w00 = 1024 - (ax << 5) - w10;
+    const int v = w00 * p00 + w01 * p01 + w10 * p10 + w11 * p11;
     return (v + 512) >> 10;
 }
 
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(256) k_mask(const MaskParams p)
             int bx = 0;
             if (uniform_block) {
                 const int xc = x < 0 ? 0 : x;
-                bx = xc - xc % bw0;
+                bx = bw0 == 64 ? (xc & ~63) : xc - xc % bw0;
                 const double dbx = (double)bx;
                 X0 = __dadd_rn(__dadd_rn(__dmul_rn(M0, dbx), __dmul_rn(M1, dy)), M2);
                 Y0 = __dadd_rn(__dadd_rn(__dmul_rn(M3, dbx), __dmul_rn(M4, dy)), M5);

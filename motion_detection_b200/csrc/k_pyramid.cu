@@ -121,19 +121,41 @@ __global__ void __launch_bounds__(256) k_scharr(const uint8_t *__restrict__ img,
                                                 size_t slot_bytes, size_t slot_der, int slot0, int nslots, LevelGeom L,
                                                 int padx, int pady)
 {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int y = blockIdx.y;
-    int f = blockIdx.z;
+    // one thread = 4 consecutive pixels: three aligned 32-bit loads per row (x-4 .. x+7), one 16-byte store
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    const int f = blockIdx.z;
     if (x >= L.w) return;
-    int slot = (slot0 + f) % nslots;
+    const int slot = (slot0 + f) % nslots;
     const uint8_t *p = img + (size_t)slot * slot_bytes + L.img_off + (size_t)(pady + y) * L.pitch + padx + x;
-    const uint8_t *u = p - L.pitch, *d = p + L.pitch;
-    int a0 = (u[-1] + d[-1]) * 3 + p[-1] * 10, a2 = (u[1] + d[1]) * 3 + p[1] * 10;
-    int b0 = d[-1] - u[-1], b1 = d[0] - u[0], b2 = d[1] - u[1];
-    short2 o;
-    o.x = (short)(a2 - a0);
-    o.y = (short)((b0 + b2) * 3 + b1 * 10);
-    der[(size_t)slot * slot_der + L.der_off + (size_t)(pady + y) * L.pitch + padx + x] = o;
+    int t0[6], t1[6];      // column sums for x-1 .. x+4
+    {
+        const uint32_t *u = reinterpret_cast<const uint32_t *>(p - L.pitch), *m = reinterpret_cast<const uint32_t *>(p),
+                       *d = reinterpret_cast<const uint32_t *>(p + L.pitch);
+        const uint32_t ul = __ldg(u - 1), uc = __ldg(u), ur = __ldg(u + 1);
+        const uint32_t ml = __ldg(m - 1), mc = __ldg(m), mr = __ldg(m + 1);
+        const uint32_t dl = __ldg(d - 1), dc = __ldg(d), dr = __ldg(d + 1);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            // byte i-1 relative to x: i = 0 -> last byte of the left word, 1..4 -> centre word, 5 -> first byte of the right word
+            const uint32_t uw = i == 0 ? ul >> 24 : (i == 5 ? ur & 0xffu : (uc >> (8 * (i - 1))) & 0xffu);
+            const uint32_t mw = i == 0 ? ml >> 24 : (i == 5 ? mr & 0xffu : (mc >> (8 * (i - 1))) & 0xffu);
+            const uint32_t dw = i == 0 ? dl >> 24 : (i == 5 ? dr & 0xffu : (dc >> (8 * (i - 1))) & 0xffu);
+            t0[i] = (int)(uw + dw) * 3 + (int)mw * 10;
+            t1[i] = (int)dw - (int)uw;
+        }
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int ix = t0[i + 2] - t0[i];
+        const int iy = (t1[i] + t1[i + 2]) * 3 + t1[i + 1] * 10;
+        o[i] = ((uint32_t)ix & 0xffffu) | ((uint32_t)iy << 16);
+    }
+    short2 *dst = der + (size_t)slot * slot_der + L.der_off + (size_t)(pady + y) * L.pitch + padx + x;
+    if (x + 3 < L.w) *reinterpret_cast<uint4 *>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    else
+        for (int i = 0; i < 4 && x + i < L.w; i++) reinterpret_cast<uint32_t *>(dst)[i] = o[i];
 }
 
 cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot0, int nframes, const uint8_t *frames,
@@ -155,8 +177,8 @@ cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot
     MD_COUNT_LAUNCH(2 * g.nlev);
     for (int l = 0; l < g.nlev; l++) {
         const LevelGeom &L = g.lv[l];
-        dim3 grid((L.w + 255) / 256, L.h, nframes);
-        k_scharr<<<grid, 256, 0, s>>>(img, der, g.slot_img_bytes, g.slot_der_elems, slot0, g.nslots, L, g.padx, g.pady);
+        dim3 grid(((L.w + 3) / 4 + 127) / 128, L.h, nframes);
+        k_scharr<<<grid, 128, 0, s>>>(img, der, g.slot_img_bytes, g.slot_der_elems, slot0, g.nslots, L, g.padx, g.pady);
     }
     return cudaGetLastError();
 }

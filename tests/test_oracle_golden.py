@@ -1,0 +1,105 @@
+"""CPU: the plain-C oracle against the committed golden vectors (tests/golden/golden_cv2.npz, produced from the OpenCV
+routines the reference calls by tests/golden/make_golden.py).  Integer stages bit-exact; LK and VarFlow to float noise."""
+import os
+
+import numpy as np
+import pytest
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_cv2.npz"))
+
+
+def test_gray(oracle):
+    assert np.array_equal(oracle.gray(G["gray_in"]), G["gray_out"])
+
+
+def test_pyramid_and_scharr(oracle):
+    pyr = oracle.pyramid(G["pyr_in"])
+    assert len(pyr) == int(G["pyr_levels"])
+    for l, im in enumerate(pyr):
+        assert np.array_equal(im, G["pyr_l%d" % l])
+        assert np.array_equal(oracle.scharr(im), G["pyr_d%d" % l])
+
+
+def test_pyramid_level_rule(oracle):
+    # cv::buildOpticalFlowPyramid stops when the next level would be <= winSize in either dimension
+    assert oracle.pyr_levels(320, 240) == 2 and oracle.pyr_levels(640, 480) == 3
+    assert oracle.pyr_levels(1920, 1080) == 4 and oracle.pyr_levels(3840, 2160) == 5
+    assert oracle.pyr_levels(120, 100) == 1 and oracle.pyr_levels(60, 60) == 0
+
+
+def test_lk(oracle):
+    nxt, st = oracle.lk(G["lk_f0"], G["lk_f1"], G["lk_pts"])
+    assert (st != G["lk_status"]).mean() < 0.01
+    ok = (st == 1) & (G["lk_status"] == 1)
+    d = np.linalg.norm(nxt[ok] - G["lk_next"][ok], axis=1)
+    assert d.mean() < 1e-3 and np.median(d) < 1e-4      # north_star flow bar is 0.01 px mean EPE
+
+
+def test_perspective_4pt(oracle):
+    ok, H = oracle.perspective_4pt(G["p4_src"], G["p4_dst"])
+    assert ok == 1
+    assert np.linalg.norm(H - G["p4_H"]) / np.linalg.norm(G["p4_H"]) < 1e-9
+
+
+def test_degenerate_first_four_is_reported(oracle):
+    # the reference's literal first-four choice is collinear (column x = 0): no valid homography
+    src = np.array([[0, 0], [0, 10], [0, 20], [0, 30]], np.float64)
+    ok, _ = oracle.perspective_4pt(src, src + 1.5)
+    assert ok == 0
+
+
+def test_warp_and_mask_chain(oracle):
+    a, b = G["mask_a"], G["mask_b"]
+    for i, H in enumerate(G["mask_H"]):
+        assert np.array_equal(oracle.warp_perspective(a, H), G["mask_warp"][i])
+        assert np.array_equal(oracle.motion_mask(a, b, H, thresh=40), G["mask_t40"][i])
+        assert np.array_equal(oracle.motion_mask(a, b, H, thresh=40, morph=False), G["mask_t40_nomorph"][i])
+    assert (G["mask_t40"] > 0).sum() > 500
+
+
+def test_threshold_is_strict(oracle):
+    a = np.full((8, 8), 190, np.uint8)
+    z = np.zeros((8, 8), np.uint8)
+    assert oracle.absdiff_threshold(a, z, 190).sum() == 0
+    assert (oracle.absdiff_threshold(a + 1, z, 190) == 255).all()
+
+
+def test_morphology_border_identities(oracle):
+    full = np.full((5, 7), 255, np.uint8)
+    assert (oracle.erode3(full) == 255).all()            # out-of-image pixels do not erode
+    one = np.zeros((5, 7), np.uint8); one[0, 0] = 255
+    d = oracle.dilate3(one)
+    assert d[:2, :2].min() == 255 and d.sum() == 4 * 255
+
+
+def test_varflow(oracle):
+    U, V = oracle.varflow(G["vf_a"], G["vf_b"])
+    assert np.abs(U - G["vf_U"]).max() < 2e-5 and np.abs(V - G["vf_V"]).max() < 2e-5
+    # U is +x, V is y-UP (VarFlow.cpp:103-107): the field moves by (+0.75, -0.5) px in image coordinates
+    assert U.mean() > 0.3 and V.mean() > 0.2
+
+
+def test_varflow_primitives(oracle):
+    x = G["prim_in"]
+    assert np.abs(oracle.gaussian_blur_f32(x, 1.5) - G["prim_blur15"]).max() < 5e-5
+    assert np.abs(oracle.gaussian_blur_f32(x, 2.8) - G["prim_blur28"]).max() < 5e-5
+    assert np.abs(oracle.resize_linear_f32(x, 23, 16) - G["prim_resize_23_16"]).max() < 1e-3
+    assert np.abs(oracle.resize_linear_f32(x, 94, 66) - G["prim_resize_94_66"]).max() < 1e-3
+    assert np.abs(oracle.resize_linear_f32(G["prim_in2"], 24, 16) - G["prim_resize_half"]).max() < 1e-5
+
+
+def test_glibc_rand_known_answers(oracle):
+    # glibc TYPE_3 rand(): srand(1) (also the default state) starts 1804289383, 846930886, 1681692777, ...
+    assert oracle.glibc_rand(1, 5) == [1804289383, 846930886, 1681692777, 1714636915, 1957747793]
+    assert oracle.glibc_rand(42, 3) == [71876166, 708592740, 1483128881]
+
+
+def test_glibc_rand_matches_libc(oracle):
+    import ctypes
+    try:
+        libc = ctypes.CDLL("libc.so.6")
+    except OSError:
+        pytest.skip("no glibc")
+    for seed in (1, 7, 123456789):
+        libc.srand(seed)
+        assert [libc.rand() for _ in range(400)] == oracle.glibc_rand(seed, 400)
