@@ -1,9 +1,301 @@
-// k_subspace.cu -- placeholder until the fitSubspace scorer lands.
+// k_subspace.cu -- OutlierDetector::fitSubspace (common/src/outlier_detector.cpp:236-331) on the device.
+//
+//   fillMatrix :188-200      data (2F x T), rows x0,y0,x1,y1,...        -> read straight from traj[T][F][2]
+//   meanSubtract :202-221    x rows -= mean(x0), y rows = mean(y0) - y  -> k_sub_mean (f64 fixed-order reduction)
+//   fillSubset :223-234      d = 4*num_motions columns, rand() % T      -> k_sub_hyp (glibc TYPE_3 restated)
+//   JacobiSVD + Pnd :266-282 Pnd = I - sum_{k<d} u_k u_k^T              -> k_sub_hyp (one-sided Jacobi, f64, one thread
+//                                                                          per hypothesis, oracle operation order)
+//   residual / inliers :284-299   |d_i^T Pnd d_i| < (2F-d) sigma^2     -> k_sub_score (all hypotheses x all trajectories,
+//                                                                          Pnd in shared memory, ballot + popc counts)
+//   best-of + threshold :300-324  first max wins; chi-square p99 table  -> k_sub_final
+// Every f64 expression uses _rn intrinsics in the oracle's order, so projectors, residuals, inlier counts and labels
+// are bit-identical to oracle/md_oracle_subspace.c for the same column draws.
+#include <float.h>
+
 #include "md_internal.h"
-extern "C" int md_fit_subspace(md_ctx *ctx, const float *, int32_t, int32_t, int32_t, double, uint32_t, const int32_t *, int32_t,
-                               float *, int32_t *, uint8_t *, int32_t *, int)
+
+#define SUB_MAXN 32
+
+struct SubParams {
+    const float *traj;       // [T][F][2]
+    int T, F, n, d, iters;
+    double sigma;
+    uint32_t seed;
+    const int *forced_cols;  // [iters][d] or nullptr
+    double *mean;            // [2]  (x0 mean, y0 mean)
+    double *P;               // [iters][n*n]
+    int *cols;               // [iters][d]
+    int *counts;             // [iters]
+    float *residual;         // [T]
+    uint8_t *outlier;        // [T]
+    int *best_cols;          // [d]
+    int *num_inliers;        // [1]
+};
+
+__device__ __forceinline__ double sub_datum(const SubParams &p, int r, int i, float xm, float ym)
+{
+    // row r of column i after meanSubtract, as the f32 value the reference stores, widened to f64
+    const float v = p.traj[((size_t)i * p.F + (r >> 1)) * 2 + (r & 1)];
+    return (double)((r & 1) ? __fsub_rn(ym, v) : __fsub_rn(v, xm));
+}
+
+__global__ void __launch_bounds__(1024) k_sub_mean(const SubParams p)
+{
+    __shared__ double sx[1024], sy[1024];
+    double ax = 0, ay = 0;
+    for (int i = threadIdx.x; i < p.T; i += 1024) {
+        ax += (double)p.traj[(size_t)i * p.F * 2];
+        ay += (double)p.traj[(size_t)i * p.F * 2 + 1];
+    }
+    sx[threadIdx.x] = ax; sy[threadIdx.x] = ay;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sx[threadIdx.x] += sx[threadIdx.x + o]; sy[threadIdx.x] += sy[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { p.mean[0] = sx[0] / p.T; p.mean[1] = sy[0] / p.T; }
+    for (int i = threadIdx.x; i < p.iters; i += 1024) p.counts[i] = 0;
+}
+
+struct SubRand { int32_t r[34]; int f, b; };
+__device__ void sub_srand(SubRand &st, uint32_t seed)
+{
+    if (seed == 0) seed = 1;
+    st.r[0] = (int32_t)seed;
+    for (int i = 1; i < 31; i++) {
+        long long hi = st.r[i - 1] / 127773, lo = st.r[i - 1] % 127773;
+        long long word = 16807 * lo - 2836 * hi;
+        if (word < 0) word += 2147483647;
+        st.r[i] = (int32_t)word;
+    }
+    st.f = 3; st.b = 0;
+}
+__device__ int sub_rand(SubRand &st)
+{
+    uint32_t *r = reinterpret_cast<uint32_t *>(st.r);
+    r[st.f] += r[st.b];
+    uint32_t out = r[st.f] >> 1;
+    st.f = st.f + 1 == 31 ? 0 : st.f + 1;
+    st.b = st.b + 1 == 31 ? 0 : st.b + 1;
+    return (int)out;
+}
+
+// one-sided (Hestenes) Jacobi, same sweep order and formulas as the oracle's hestenes()
+__device__ void hestenes(double *A, int n, int d, double *norms)
+{
+    for (int sweep = 0; sweep < 60; sweep++) {
+        int rotated = 0;
+        for (int pc = 0; pc < d - 1; pc++)
+            for (int q = pc + 1; q < d; q++) {
+                double a = 0, b = 0, g = 0;
+                for (int i = 0; i < n; i++) {
+                    a = __dadd_rn(a, __dmul_rn(A[pc * n + i], A[pc * n + i]));
+                    b = __dadd_rn(b, __dmul_rn(A[q * n + i], A[q * n + i]));
+                    g = __dadd_rn(g, __dmul_rn(A[pc * n + i], A[q * n + i]));
+                }
+                if (g == 0 || fabs(g) <= __dmul_rn(1e-15, __dsqrt_rn(__dmul_rn(a, b)))) continue;
+                rotated = 1;
+                const double zeta = __ddiv_rn(__dsub_rn(b, a), __dmul_rn(2.0, g));
+                const double t = __ddiv_rn(zeta >= 0 ? 1.0 : -1.0,
+                                           __dadd_rn(fabs(zeta), __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(zeta, zeta)))));
+                const double c = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(t, t)))), s = __dmul_rn(c, t);
+                for (int i = 0; i < n; i++) {
+                    const double vp = A[pc * n + i], vq = A[q * n + i];
+                    A[pc * n + i] = __dsub_rn(__dmul_rn(c, vp), __dmul_rn(s, vq));
+                    A[q * n + i] = __dadd_rn(__dmul_rn(s, vp), __dmul_rn(c, vq));
+                }
+            }
+        if (!rotated) break;
+    }
+    for (int k = 0; k < d; k++) {
+        double a = 0;
+        for (int i = 0; i < n; i++) a = __dadd_rn(a, __dmul_rn(A[k * n + i], A[k * n + i]));
+        norms[k] = __dsqrt_rn(a);
+    }
+}
+
+__global__ void __launch_bounds__(64) k_sub_hyp(const SubParams p)
+{
+    extern __shared__ int s_cols[];      // [iters][d]
+    if (threadIdx.x == 0) {
+        SubRand st;
+        sub_srand(st, p.seed);
+        for (int i = 0; i < 310; i++) (void)sub_rand(st);
+        for (int i = 0; i < p.iters * p.d; i++) s_cols[i] = p.forced_cols ? p.forced_cols[i] : sub_rand(st) % p.T;
+    }
+    __syncthreads();
+    const float xm = (float)p.mean[0], ym = (float)p.mean[1];
+    const int n = p.n, d = p.d;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < p.iters; it += gridDim.x * blockDim.x) {
+        double A[SUB_MAXN * SUB_MAXN], norms[SUB_MAXN];
+        for (int k = 0; k < d; k++) {
+            int c = s_cols[it * d + k];
+            c = c < 0 ? 0 : (c >= p.T ? p.T - 1 : c);
+            p.cols[it * d + k] = c;
+            for (int i = 0; i < n; i++) A[k * n + i] = sub_datum(p, i, c, xm, ym);
+        }
+        hestenes(A, n, d, norms);
+        double smax = 0;
+        for (int k = 0; k < d; k++) if (norms[k] > smax) smax = norms[k];
+        double *P = p.P + (size_t)it * n * n;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) P[i * n + j] = i == j ? 1.0 : 0.0;
+        for (int k = 0; k < d; k++) {
+            if (!(norms[k] > __dmul_rn(1e-12, smax)) || norms[k] == 0) continue;
+            const double inv = __ddiv_rn(1.0, norms[k]);
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++)
+                    P[i * n + j] = __dsub_rn(P[i * n + j], __dmul_rn(__dmul_rn(A[k * n + i], inv), __dmul_rn(A[k * n + j], inv)));
+        }
+    }
+}
+
+__device__ __forceinline__ double sub_residual(const double *P, const double *dcol, int n)
+{
+    double acc = 0;
+    for (int r = 0; r < n; r++) {
+        double pr = 0;
+        for (int c = 0; c < n; c++) pr = __dadd_rn(pr, __dmul_rn(P[r * n + c], dcol[c]));
+        acc = __dadd_rn(acc, __dmul_rn(dcol[r], pr));
+    }
+    return fabs(acc);
+}
+
+// all hypotheses against all trajectories; HB hypotheses' projectors per shared-memory pass
+__global__ void __launch_bounds__(256) k_sub_score(const SubParams p, int hb)
+{
+    extern __shared__ double s_P[];      // [hb][n*n]
+    const int n = p.n, nn = n * n;
+    const float xm = (float)p.mean[0], ym = (float)p.mean[1];
+    const double inl_thr = __dmul_rn(__dmul_rn((double)(n - p.d), p.sigma), p.sigma);
+    const int lane = threadIdx.x & 31;
+    const int Tr = (p.T + 31) & ~31;
+    for (int h0 = 0; h0 < p.iters; h0 += hb) {
+        const int nh = min(hb, p.iters - h0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nh * nn; i += blockDim.x) s_P[i] = p.P[(size_t)h0 * nn + i];
+        __syncthreads();
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Tr; i += gridDim.x * blockDim.x) {
+            double dcol[SUB_MAXN];
+            const bool act = i < p.T;
+            if (act) for (int r = 0; r < n; r++) dcol[r] = sub_datum(p, r, i, xm, ym);
+            for (int j = 0; j < nh; j++) {
+                const bool inl = act && sub_residual(s_P + j * nn, dcol, n) < inl_thr;
+                const unsigned bal = __ballot_sync(0xffffffffu, inl);
+                if (lane == 0 && bal) atomicAdd(&p.counts[h0 + j], __popc(bal));
+            }
+        }
+    }
+}
+
+// chi_square_table p99, outlier_detector.cpp:19-30
+__constant__ double c_chi2_p99[10] = {0.0, 0.020, 0.115, 0.297, 0.554, 0.872, 1.239, 1.646, 2.088, 2.558};
+
+__global__ void __launch_bounds__(256) k_sub_final(const SubParams p)
+{
+    extern __shared__ double s_P[];
+    const int n = p.n, nn = n * n;
+    int best = -1, best_cnt = 0;
+    for (int j = 0; j < p.iters; j++)
+        if (p.counts[j] > best_cnt) { best_cnt = p.counts[j]; best = j; }      // :300 first best wins
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *p.num_inliers = best_cnt;
+        for (int k = 0; k < p.d; k++) p.best_cols[k] = best >= 0 ? p.cols[best * p.d + k] : -1;
+    }
+    if (best < 0) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.T; i += gridDim.x * blockDim.x) { p.residual[i] = 0.f; p.outlier[i] = 0; }
+        return;
+    }
+    for (int i = threadIdx.x; i < nn; i += blockDim.x) s_P[i] = p.P[(size_t)best * nn + i];
+    __syncthreads();
+    const float xm = (float)p.mean[0], ym = (float)p.mean[1];
+    double thr = 0.2;                                                           // :312-317
+    const int k = n - p.d;
+    if (k < 11 && k > 0) thr = __dmul_rn(__dmul_rn(p.sigma, p.sigma), c_chi2_p99[k >= 10 ? 9 : k]);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < p.T; i += gridDim.x * blockDim.x) {
+        double dcol[SUB_MAXN];
+        for (int r = 0; r < n; r++) dcol[r] = sub_datum(p, r, i, xm, ym);
+        const float res = (float)sub_residual(s_P, dcol, n);
+        p.residual[i] = res;
+        p.outlier[i] = (double)res > thr ? 1 : 0;                               // :318-324 (residual is stored as f32)
+    }
+}
+
+#define SCK(call)                                                                                               \
+    do {                                                                                                        \
+        cudaError_t e_ = (call);                                                                                \
+        if (e_ != cudaSuccess) {                                                                                \
+            ctx->err = std::string("md_fit_subspace: ") + #call + " -> " + cudaGetErrorString(e_);             \
+            rc = MD_ERR_CUDA;                                                                                   \
+            goto done;                                                                                          \
+        }                                                                                                       \
+    } while (0)
+
+extern "C" int md_fit_subspace(md_ctx *ctx, const float *traj, int32_t T, int32_t F, int32_t num_motions, double sigma,
+                               uint32_t seed, const int32_t *forced_cols, int32_t iters, float *residual, int32_t *best_cols,
+                               uint8_t *outlier, int32_t *num_inliers, int mem)
 {
     if (!ctx) return MD_ERR_INVALID;
-    ctx->err = "md_fit_subspace: not implemented yet";
-    return MD_ERR_UNSUPPORTED;
+    const int n = 2 * F, d = 4 * num_motions;
+    if (!traj || !residual || !best_cols || !outlier || T < 1 || F < 1 || n > SUB_MAXN || d < 1 || d > SUB_MAXN || d > n ||
+        iters < 1 || iters > 4096) {
+        ctx->err = "md_fit_subspace: bad arguments (need 2F <= 32, 4*num_motions <= 2F)";
+        return MD_ERR_INVALID;
+    }
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return MD_ERR_CUDA;
+    cudaStream_t s = ctx->stream;
+    int rc = MD_OK;
+    const bool host = mem == MD_MEM_HOST;
+    float *d_traj = nullptr, *d_res = nullptr;
+    int *d_forced = nullptr, *d_cols = nullptr, *d_counts = nullptr, *d_best = nullptr, *d_ninl = nullptr;
+    double *d_mean = nullptr, *d_P = nullptr;
+    uint8_t *d_out = nullptr;
+    SubParams p;
+    {
+        const size_t tb = sizeof(float) * 2 * (size_t)T * F;
+        if (host) { SCK(cudaMalloc((void **)&d_traj, tb)); SCK(cudaMemcpyAsync(d_traj, traj, tb, cudaMemcpyHostToDevice, s)); }
+        if (forced_cols) {
+            SCK(cudaMalloc((void **)&d_forced, sizeof(int) * iters * d));
+            SCK(cudaMemcpyAsync(d_forced, forced_cols, sizeof(int) * iters * d, cudaMemcpyHostToDevice, s));
+        }
+        SCK(cudaMalloc((void **)&d_mean, 2 * sizeof(double)));
+        SCK(cudaMalloc((void **)&d_P, sizeof(double) * (size_t)iters * n * n));
+        SCK(cudaMalloc((void **)&d_cols, sizeof(int) * iters * d));
+        SCK(cudaMalloc((void **)&d_counts, sizeof(int) * iters));
+        SCK(cudaMalloc((void **)&d_best, sizeof(int) * d));
+        SCK(cudaMalloc((void **)&d_ninl, sizeof(int)));
+        if (host) { SCK(cudaMalloc((void **)&d_res, sizeof(float) * T)); SCK(cudaMalloc((void **)&d_out, T)); }
+        p.traj = host ? d_traj : traj;
+        p.T = T; p.F = F; p.n = n; p.d = d; p.iters = iters; p.sigma = sigma; p.seed = seed;
+        p.forced_cols = d_forced; p.mean = d_mean; p.P = d_P; p.cols = d_cols; p.counts = d_counts;
+        p.residual = host ? d_res : residual; p.outlier = host ? d_out : outlier;
+        p.best_cols = d_best; p.num_inliers = d_ninl;
+        k_sub_mean<<<1, 1024, 0, s>>>(p);
+        const size_t cols_smem = sizeof(int) * iters * d;
+        SCK(cudaFuncSetAttribute(k_sub_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
+        k_sub_hyp<<<1, 64, cols_smem, s>>>(p);
+        int hb = (int)(96 * 1024 / (sizeof(double) * n * n));
+        if (hb > iters) hb = iters;
+        if (hb < 1) hb = 1;
+        const size_t psm = sizeof(double) * (size_t)hb * n * n;
+        SCK(cudaFuncSetAttribute(k_sub_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
+        int nb = (T + 255) / 256;
+        if (nb > 592) nb = 592;
+        k_sub_score<<<nb, 256, psm, s>>>(p, hb);
+        k_sub_final<<<nb, 256, sizeof(double) * n * n, s>>>(p);
+        MD_COUNT_LAUNCH(4);
+        SCK(cudaGetLastError());
+        const cudaMemcpyKind k = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+        if (host) {
+            SCK(cudaMemcpyAsync(residual, d_res, sizeof(float) * T, k, s));
+            SCK(cudaMemcpyAsync(outlier, d_out, T, k, s));
+        }
+        SCK(cudaMemcpyAsync(best_cols, d_best, sizeof(int) * d, k, s));
+        if (num_inliers) SCK(cudaMemcpyAsync(num_inliers, d_ninl, sizeof(int), k, s));
+        SCK(cudaStreamSynchronize(s));     // temporaries are freed below
+    }
+done:
+    cudaFree(d_traj); cudaFree(d_forced); cudaFree(d_mean); cudaFree(d_P); cudaFree(d_cols); cudaFree(d_counts);
+    cudaFree(d_best); cudaFree(d_ninl); cudaFree(d_res); cudaFree(d_out);
+    return rc;
 }

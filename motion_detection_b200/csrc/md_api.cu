@@ -71,6 +71,7 @@ static void free_ctx(md_ctx *ctx)
                     ctx->d_inliers, ctx->d_valid, ctx->d_hyp, ctx->d_partial, ctx->d_H, ctx->d_Hinv, ctx->d_stats,
                     ctx->d_traj, ctx->d_traj_len};
     for (void *p : ptrs) if (p) cudaFree(p);
+    vf_free_workspace(ctx->vf_ws);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;

@@ -144,7 +144,10 @@ struct md_ctx {
     int profile;
     cudaEvent_t ev[5];
     LkTmaMaps lk_maps;
+    void *vf_ws;          // VarFlow workspace (k_varflow.cu), allocated on the first md_varflow call
 };
+
+void vf_free_workspace(void *ws);
 
 extern long long g_md_launches;   // kernels launched by this library (process wide)
 #define MD_COUNT_LAUNCH(n) (g_md_launches += (n))

@@ -305,3 +305,67 @@ def test_trajectories_match_oracle_bookkeeping(capi, oracle, seq640):
     ref_full = np.array([traj[i] for i in np.nonzero(full)[0]], np.float32)
     d = np.linalg.norm(got["traj"][full] - ref_full, axis=2)
     assert d.mean() < FLOW_EPE_TOL
+
+
+# ---- fitSubspace (outlier_detector.cpp:236-331) -----------------------------------------------------------------
+@pytest.mark.parametrize("T,F,nm,sigma", [(2000, 5, 2, 0.5), (517, 5, 1, 4.0), (3000, 7, 3, 1.0)])
+def test_fit_subspace_matches_oracle(capi, oracle, T, F, nm, sigma):
+    traj, _ = synth.trajectories(T, F, num_motions=nm, seed=T, noise=0.05)
+    ctx = _ctx(capi, 640, 480)
+    for seed in (1, 99):
+        n, res, cols, outl, thr = oracle.fit_subspace(traj, num_motions=nm, sigma=sigma, seed=seed)
+        got = ctx.fit_subspace(traj, num_motions=nm, sigma=sigma, seed=seed)
+        assert got["inliers"] == n
+        assert np.array_equal(got["best_cols"], cols)
+        assert np.array_equal(got["outlier"], outl)
+        assert np.allclose(got["residual"], res, rtol=1e-6, atol=1e-9)
+    # explicit column lists instead of rand()
+    rng = np.random.default_rng(5)
+    forced = rng.integers(0, T, (20, 4 * nm)).astype(np.int32)
+    n, res, cols, outl, thr = oracle.fit_subspace(traj, num_motions=nm, sigma=sigma, forced_cols=forced)
+    got = ctx.fit_subspace(traj, num_motions=nm, sigma=sigma, forced_cols=forced)
+    assert got["inliers"] == n and np.array_equal(got["best_cols"], cols) and np.array_equal(got["outlier"], outl)
+
+
+def test_trajectories_into_fit_subspace(capi, oracle, seq640):
+    # the live path of the node: calculateOpticalFlowTrajectory -> fitSubspace (node.cpp:295,348)
+    frames, _ = seq640
+    ctx = _ctx(capi, 640, 480, max_batch=4)
+    tr = ctx.track_trajectories(frames[:5])
+    full = tr["traj"][tr["len"] == 5]
+    got = ctx.fit_subspace(full, num_motions=2, sigma=0.5, seed=3)
+    n, res, cols, outl, thr = oracle.fit_subspace(full, num_motions=2, sigma=0.5, seed=3)
+    assert got["inliers"] == n and np.array_equal(got["outlier"], outl)
+
+
+# ---- VarFlow (VarFlow.cpp:600-697) ------------------------------------------------------------------------------
+@pytest.mark.parametrize("size", [(96, 80), (320, 240), (333, 211)])
+def test_varflow_matches_oracle(capi, oracle, size):
+    w, h = size
+    fr, _ = synth.sequence(w, h, 2, seed=5, camera=False, blobs=0, whole_field=(0.75, -0.5), margin=16)
+    ctx = _ctx(capi, w, h)
+    U, V = ctx.varflow(fr[0], fr[1])
+    Uo, Vo = oracle.varflow(fr[0], fr[1])
+    epe = np.sqrt((U - Uo) ** 2 + (V - Vo) ** 2)
+    assert epe.mean() < FLOW_EPE_TOL and epe.max() < 1e-3
+    # U is +x, V is y-UP: image motion (+0.75, -0.5)
+    assert U.mean() > 0.3 and V.mean() > 0.2
+
+
+def test_varflow_640_patch_sequence(capi, oracle):
+    # C1: static camera, translating textured patch
+    fr, _ = synth.sequence(640, 480, 2, seed=1234, camera=False, blobs=0, patch=True)
+    ctx = _ctx(capi, 640, 480)
+    U, V = ctx.varflow(fr[0], fr[1])
+    Uo, Vo = oracle.varflow(fr[0], fr[1])
+    epe = np.sqrt((U - Uo) ** 2 + (V - Vo) ** 2)
+    assert epe.mean() < FLOW_EPE_TOL and epe.max() < 1e-3
+
+
+def test_varflow_fast_mode_is_within_budget(capi, oracle):
+    # eliding the (numerically inert) coarse-grid corrections, SURVEY 8a a14
+    fr, _ = synth.sequence(320, 240, 2, seed=5, camera=False, blobs=0, whole_field=(0.75, -0.5), margin=16)
+    ctx = _ctx(capi, 320, 240, vf_literal=0)
+    U, V = ctx.varflow(fr[0], fr[1])
+    Uo, Vo = oracle.varflow(fr[0], fr[1])
+    assert np.sqrt((U - Uo) ** 2 + (V - Vo) ** 2).mean() < FLOW_EPE_TOL
