@@ -1,0 +1,233 @@
+// adapter.cpp -- the reference's common/ classes re-expressed over the C ABI of libmotion_b200.so.
+// cv::Mat in / out exactly like the reference; errors of the ABI are mapped to "no vectors / empty outputs" so the
+// node keeps running (the reference has no error convention of its own).
+#include <motion_detection/optical_flow_calculator.h>
+#include <motion_detection/outlier_detector.h>
+#include <motion_detection/VarFlow.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <ctime>
+
+#include "motion_b200.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+OpticalFlowCalculator::OpticalFlowCalculator()
+    : ctx_(0), w_(0), h_(0), ps_(0), batch_(0), device_(0), ego_mode_(MD_EGO_RANSAC_HOMOGRAPHY), morph_(true), seed_(1), minvec_(0)
+{
+    for (int i = 0; i < 9; i++) last_H_[i] = (i % 4 == 0) ? 1.0 : 0.0;
+}
+
+OpticalFlowCalculator::~OpticalFlowCalculator() { release(); }
+
+void OpticalFlowCalculator::release()
+{
+    if (ctx_) md_destroy(ctx_);
+    ctx_ = 0;
+}
+
+const char *OpticalFlowCalculator::lastError() const { return md_last_error(ctx_); }
+
+bool OpticalFlowCalculator::ensure(int w, int h, int pixel_step, double min_vector_size, int max_batch)
+{
+    if (ctx_ && w == w_ && h == h_ && pixel_step == ps_ && min_vector_size == minvec_ && max_batch <= batch_) return true;
+    release();
+    md_config cfg;
+    md_config_default(&cfg);
+    cfg.width = w; cfg.height = h; cfg.pixel_step = pixel_step; cfg.min_vector_size = min_vector_size;
+    cfg.max_batch = max_batch; cfg.ego_mode = ego_mode_; cfg.morph = morph_ ? 1 : 0; cfg.seed = seed_;
+    if (md_create(&cfg, device_, &ctx_) != MD_OK) { ctx_ = 0; return false; }
+    w_ = w; h_ = h; ps_ = pixel_step; minvec_ = min_vector_size; batch_ = max_batch;
+    return true;
+}
+
+// The node allocates the flow field as CV_32FC4 but every accessor uses at<cv::Vec4d> (node.cpp:81,98 vs
+// optical_flow_calculator.cpp:88): re-create it as CV_64FC4 so those reads are in bounds.
+void OpticalFlowCalculator::ensureFlowMat(cv::Mat &m, int rows, int cols)
+{
+    if (m.rows != rows || m.cols != cols || m.type() != CV_64FC4) {
+        m.create(rows, cols, CV_64FC4);
+        std::memset(m.data, 0, m.step * (size_t)rows);
+    }
+}
+
+static void write_flow(cv::Mat &flow, const float *p1, const float *p2, const uint8_t *status, const uint8_t *keep, int n, int &num_vectors)
+{
+    for (int i = 0; i < n; i++) {
+        if (status[i]) {
+            const int x = (int)p1[2 * i], y = (int)p1[2 * i + 1];
+            if (x < 0 || y < 0 || x >= flow.cols || y >= flow.rows) continue;
+            cv::Vec4d &e = flow.at<cv::Vec4d>(y, x);
+            e[0] = p1[2 * i]; e[1] = p1[2 * i + 1];
+            if (keep[i]) { e[2] = p2[2 * i] - p1[2 * i]; e[3] = p2[2 * i + 1] - p1[2 * i + 1]; num_vectors++; }
+            else { e[2] = 0.0; e[3] = 0.0; }
+        } else {
+            const int x = (int)p1[2 * i], y = (int)p1[2 * i + 1];
+            if (x < 0 || y < 0 || x >= flow.cols || y >= flow.rows) continue;
+            cv::Vec4d &e = flow.at<cv::Vec4d>(y, x);
+            e[0] = -1.0; e[1] = -1.0; e[2] = 0.0; e[3] = 0.0;
+        }
+    }
+}
+
+int OpticalFlowCalculator::calculateOpticalFlow(const cv::Mat &image1, const cv::Mat &image2, cv::Mat &optical_flow_vectors,
+                                                int pixel_step, cv::Mat &comp, double min_vector_size)
+{
+    const int w = image1.cols, h = image1.rows, ch = image1.channels();
+    if (image1.empty() || image2.empty() || image2.cols != w || image2.rows != h || image2.channels() != ch || (ch != 1 && ch != 3)) return 0;
+    if (!ensure(w, h, pixel_step, min_vector_size, 1)) return 0;
+    const int P = md_grid_size(ctx_);
+    std::vector<float> pts(2 * (size_t)P), nxt(2 * (size_t)P);
+    std::vector<uint8_t> st(P), keep(P);
+    cv::Mat mask(h, w, CV_8UC1);
+    int nv = 0, inl = 0;
+    md_outputs out;
+    std::memset(&out, 0, sizeof out);
+    out.next_pts = nxt.data(); out.status = st.data(); out.keep = keep.data(); out.H = last_H_;
+    out.num_vectors = &nv; out.inliers = &inl; out.mask = mask.data; out.mask_pitch = (int)mask.step; out.mask_stride = 0;
+    // md_process_pair takes one pitch for both frames: re-pack the second frame when the two Mats disagree
+    std::vector<uint8_t> repack;
+    const uint8_t *cur = image2.data;
+    if (image2.step != image1.step) {
+        repack.resize(image1.step * (size_t)h);
+        for (int y = 0; y < h; y++) std::memcpy(&repack[(size_t)y * image1.step], image2.data + (size_t)y * image2.step, (size_t)w * ch);
+        cur = repack.data();
+    }
+    if (md_process_pair(ctx_, image1.data, cur, ch, (int)image1.step, &out, MD_MEM_HOST) != MD_OK) return 0;
+    md_grid_points(ctx_, pts.data());
+    ensureFlowMat(optical_flow_vectors, h, w);
+    int counted = 0;
+    write_flow(optical_flow_vectors, pts.data(), nxt.data(), st.data(), keep.data(), P, counted);
+    if (nv > 0) mask.copyTo(comp);          // the reference leaves comp untouched when there are no vectors (cpp:118)
+    return nv;
+}
+
+int OpticalFlowCalculator::calculateOpticalFlowTrajectory(const std::vector<cv::Mat> &images, cv::Mat &optical_flow_vectors,
+                                                          std::vector<std::vector<cv::Point2f> > &trajectories, int pixel_step,
+                                                          cv::Mat &comp, double min_vector_size)
+{
+    (void)comp;      // untouched by the reference as well
+    const int F = (int)images.size();
+    if (F < 2) return 0;
+    const int w = images[0].cols, h = images[0].rows, ch = images[0].channels();
+    for (int i = 0; i < F; i++)
+        if (images[i].empty() || images[i].cols != w || images[i].rows != h || images[i].channels() != ch) return 0;
+    if (!ensure(w, h, pixel_step, min_vector_size, F - 1)) return 0;
+    const int P = md_grid_size(ctx_);
+    // md_frames wants one base + stride: copy the window into one contiguous block (F small frames, host side)
+    const size_t fbytes = (size_t)w * ch * h;
+    std::vector<uint8_t> block(fbytes * F);
+    for (int i = 0; i < F; i++)
+        for (int y = 0; y < h; y++) std::memcpy(&block[i * fbytes + (size_t)y * w * ch], images[i].data + (size_t)y * images[i].step, (size_t)w * ch);
+    md_frames fr;
+    std::memset(&fr, 0, sizeof fr);
+    fr.data = block.data(); fr.channels = ch; fr.pitch = w * ch; fr.frame_stride = (int64_t)fbytes; fr.count = F; fr.chain = 0;
+    std::vector<float> traj(2 * (size_t)P * F), lp(2 * (size_t)P), ln(2 * (size_t)P);
+    std::vector<int32_t> len(P);
+    std::vector<uint8_t> ls(P), keep(P);
+    if (md_track_trajectories(ctx_, &fr, traj.data(), len.data(), lp.data(), ln.data(), ls.data(), MD_MEM_HOST) != MD_OK) return 0;
+    ensureFlowMat(optical_flow_vectors, h, w);
+    for (int i = 0; i < P; i++) {
+        const float xd = ln[2 * i] - lp[2 * i], yd = ln[2 * i + 1] - lp[2 * i + 1];
+        keep[i] = ls[i] && (std::abs(xd) > min_vector_size || std::abs(yd) > min_vector_size);      // cpp:189
+    }
+    int num_vectors = 0;
+    write_flow(optical_flow_vectors, lp.data(), ln.data(), ls.data(), keep.data(), P, num_vectors);
+    for (int i = 0; i < P; i++) {
+        if (len[i] != F) continue;                                                                   // cpp:246
+        std::vector<cv::Point2f> t(F);
+        for (int f = 0; f < F; f++) t[f] = cv::Point2f(traj[((size_t)i * F + f) * 2], traj[((size_t)i * F + f) * 2 + 1]);
+        trajectories.push_back(t);
+    }
+    return num_vectors;
+}
+
+void OpticalFlowCalculator::varFlow(const cv::Mat &image1, const cv::Mat &image2, cv::Mat &optical_flow, cv::Mat &optical_flow_vectors)
+{
+    // The reference computes U,V and only draws arrows into `optical_flow` (cpp:455-463); here the dense field itself is
+    // returned: optical_flow = 32FC1 U (+x), optical_flow_vectors = 32FC1 V (y-up, VarFlow.cpp:103-107).
+    const int w = image1.cols, h = image1.rows;
+    if (image1.empty() || image1.channels() != 1 || image2.cols != w || image2.rows != h || image2.channels() != 1) return;
+    if (!ensure(w, h, ps_ > 0 ? ps_ : 10, minvec_, batch_ > 0 ? batch_ : 1)) return;
+    optical_flow.create(h, w, CV_32FC1);
+    optical_flow_vectors.create(h, w, CV_32FC1);
+    std::vector<uint8_t> a((size_t)w * h), b((size_t)w * h);
+    for (int y = 0; y < h; y++) {
+        std::memcpy(&a[(size_t)y * w], image1.data + (size_t)y * image1.step, w);
+        std::memcpy(&b[(size_t)y * w], image2.data + (size_t)y * image2.step, w);
+    }
+    md_varflow(ctx_, a.data(), b.data(), w, reinterpret_cast<float *>(optical_flow.data), reinterpret_cast<float *>(optical_flow_vectors.data), MD_MEM_HOST);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+OutlierDetector::OutlierDetector() : ctx_(0), device_(0), seed_((unsigned)time(NULL)), last_inliers_(0) {}
+
+OutlierDetector::~OutlierDetector() { if (ctx_) md_destroy(ctx_); }
+
+std::vector<std::vector<cv::Point2f> > OutlierDetector::fitSubspace(const std::vector<std::vector<cv::Point2f> > &trajectories,
+                                                                     std::vector<cv::Point2f> &outlier_points, int num_motions, double sigma)
+{
+    std::vector<std::vector<cv::Point2f> > basis;
+    const int T = (int)trajectories.size();
+    if (T < 1) return basis;                       // the reference dereferences trajectories[0] unguarded (:239)
+    const int F = (int)trajectories[0].size();
+    if (!ctx_) {
+        md_config cfg;
+        md_config_default(&cfg);
+        cfg.width = 64; cfg.height = 64;           // geometry is irrelevant for the subspace fit
+        if (md_create(&cfg, device_, &ctx_) != MD_OK) { ctx_ = 0; return basis; }
+    }
+    std::vector<float> traj(2 * (size_t)T * F);
+    for (int i = 0; i < T; i++)
+        for (int f = 0; f < F; f++) { traj[((size_t)i * F + f) * 2] = trajectories[i][f].x; traj[((size_t)i * F + f) * 2 + 1] = trajectories[i][f].y; }
+    const int d = 4 * num_motions;
+    std::vector<float> res(T);
+    std::vector<int32_t> cols(d > 0 ? d : 1);
+    std::vector<uint8_t> outl(T);
+    int32_t ninl = 0;
+    // the reference's rand() stream continues across calls; here every call advances the seed by one
+    if (md_fit_subspace(ctx_, traj.data(), T, F, num_motions, sigma, seed_++, 0, 50, res.data(), cols.data(), outl.data(), &ninl, MD_MEM_HOST) != MD_OK)
+        return basis;
+    last_inliers_ = ninl;
+    for (int i = 0; i < T; i++)
+        if (outl[i]) outlier_points.push_back(trajectories[i][F - 2]);       // second-to-last point, :322
+    for (int k = 0; k < d; k++)
+        if (cols[k] >= 0) basis.push_back(trajectories[cols[k]]);           // :325-330
+    return basis;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+VarFlow::VarFlow(int width_in, int height_in, int max_level_in, int start_level_in, int n1_in, int n2_in, float rho_in,
+                 float alpha_in, float sigma_in)
+    : ctx_(0), width(width_in), height(height_in), initialized(0)
+{
+    md_config cfg;
+    md_config_default(&cfg);
+    cfg.width = width_in; cfg.height = height_in;
+    cfg.vf_max_level = max_level_in < start_level_in ? start_level_in : max_level_in;      // VarFlow.cpp:33-37
+    cfg.vf_start_level = start_level_in; cfg.vf_n1 = n1_in; cfg.vf_n2 = n2_in;
+    cfg.vf_rho = rho_in; cfg.vf_alpha = alpha_in; cfg.vf_sigma = sigma_in;
+    if (md_create(&cfg, 0, &ctx_) == MD_OK) initialized = 1;
+    else ctx_ = 0;
+}
+
+VarFlow::~VarFlow() { if (ctx_) md_destroy(ctx_); }
+
+int VarFlow::CalcFlow(IplImage *imgA, IplImage *imgB, IplImage *imgU, IplImage *imgV, bool saved_data)
+{
+    (void)saved_data;        // only a caching hint in the reference (VarFlow.cpp:608-616); results are the same
+    if (!initialized || !imgA || !imgB || !imgU || !imgV) return 0;
+    if (imgA->width != width || imgA->height != height || imgA->nChannels != 1 || imgB->width != width || imgB->height != height ||
+        imgA->widthStep != imgB->widthStep || imgU->width != width || imgU->height != height)
+        return 0;
+    std::vector<float> U((size_t)width * height), V((size_t)width * height);
+    if (md_varflow(ctx_, reinterpret_cast<const uint8_t *>(imgA->imageData), reinterpret_cast<const uint8_t *>(imgB->imageData),
+                   imgA->widthStep, U.data(), V.data(), MD_MEM_HOST) != MD_OK)
+        return 0;
+    for (int y = 0; y < height; y++) {
+        std::memcpy(imgU->imageData + (size_t)y * imgU->widthStep, &U[(size_t)y * width], sizeof(float) * width);
+        std::memcpy(imgV->imageData + (size_t)y * imgV->widthStep, &V[(size_t)y * width], sizeof(float) * width);
+    }
+    return 1;
+}
