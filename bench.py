@@ -32,7 +32,7 @@ UNIT = "frames/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=16, help="frame pairs per step")
@@ -71,7 +71,7 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
         except Exception:
@@ -139,7 +139,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from motion_detection_b200 import capi
+    from motion_detection_b200 import capi, streams
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
@@ -234,7 +234,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(["k_pyramid", "k_lk", "k_ego", "k_mask"][dom])
+            per_pair = json.load(open(tp)).get(["k_pyramid", "k_lk", "k_ego", "k_mask"][dom])
+            traffic = per_pair * B if per_pair is not None else None     # ncu dram bytes per pair x pairs per launch
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
@@ -283,13 +284,7 @@ def main():
 
     # ---- per-stream statistics gathered over NCCL (the only collective; off the frame path)
     st = ctx.stats()
-    mine = torch.tensor([st["pairs"], st["mask_pixels"], st["tracked"], st["inliers"]], dtype=torch.int64, device=dev)
-    if world > 1:
-        allst = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allst, mine)
-        gathered = [x.tolist() for x in allst]
-    else:
-        gathered = [mine.tolist()]
+    gathered = streams.gather_stats({k: st[k] for k in ("pairs", "mask_pixels", "tracked", "inliers")})
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the reference's OpenCV chain via cv2, all host threads
     cpu = None
