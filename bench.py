@@ -259,13 +259,21 @@ def main():
                    inl=torch.empty((B,), dtype=torch.int32).pin_memory())
         houts = capi.MdOutputs(pin["nxt"].data_ptr(), pin["st"].data_ptr(), pin["keep"].data_ptr(), pin["H"].data_ptr(),
                                pin["nv"].data_ptr(), pin["inl"].data_ptr(), pin["mask"].data_ptr(), w, w * h)
-        # prime the cached pyramid with frame 0, then every step pushes B NEW frames (chained stream)
-        ctx2.raw_process_batch(pin_frames.data_ptr(), 1, w, frame_bytes, 2, False, houts, capi.MD_MEM_HOST)
+        # Chained stream: the context keeps the pyramid of the last frame, every step pushes B NEW frames.  The clip
+        # is played forward (f1..fB) and backward (fB-1..f0) alternately so that every pair is a real consecutive pair.
+        pin_fwd = pin_frames[1:]
+        pin_bwd = torch.empty((B, h, w), dtype=torch.uint8).pin_memory()
+        pin_bwd.copy_(torch.flip(host[:B], dims=[0]))
+        ctx2.raw_process_batch(pin_frames.data_ptr(), 1, w, frame_bytes, 2, False, houts, capi.MD_MEM_HOST)   # primes f0 -> f1
+        ctx2.raw_process_batch(pin_frames.data_ptr(), 1, w, frame_bytes, 1, True, houts, capi.MD_MEM_HOST)    # back at f0
+        nstep = [0]
 
         def hstep():
-            ctx2.raw_process_batch(pin_frames[1:].data_ptr(), 1, w, frame_bytes, B, True, houts, capi.MD_MEM_HOST)
+            src = pin_fwd if nstep[0] % 2 == 0 else pin_bwd
+            nstep[0] += 1
+            ctx2.raw_process_batch(src.data_ptr(), 1, w, frame_bytes, B, True, houts, capi.MD_MEM_HOST)
 
-        for _ in range(a.warmup):
+        for _ in range(a.warmup + (a.warmup % 2)):      # an even number of warm-up steps: the timed loop starts forward
             hstep()
         barrier()
         t0 = time.perf_counter()
