@@ -73,6 +73,9 @@ static void free_ctx(md_ctx *ctx)
     for (void *p : ptrs) if (p) cudaFree(p);
     vf_free_workspace(ctx->vf_ws);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int i = 0; i < 8; i++) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]); }
+    if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
+    if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -101,6 +104,12 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return MD_ERR_CUDA; }
     ctx->stream = ctx->own_stream;
+    bool sok = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 8 && sok; i++)
+        sok = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!sok) { free_ctx(ctx); return MD_ERR_CUDA; }
 
     const int w = cfg->width, h = cfg->height, B = cfg->max_batch;
     PyrGeom &g = ctx->g;
@@ -480,6 +489,41 @@ extern "C" int md_motion_mask(md_ctx *ctx, const uint8_t *prev, const uint8_t *c
 }
 
 // ---- the chain -------------------------------------------------------------------------------------------------------
+// Runs K2 -> K3 -> K4 for pairs [p0, p1) of the current batch (pyramids of the frames involved are already built).
+static int run_pairs(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint8_t *d_status, uint8_t *d_keep, uint8_t *d_mask,
+                     int mask_pitch, long long mask_stride, bool want_mask, cudaStream_t s)
+{
+    const int P = ctx->P, ns = ctx->g.nslots, n = p1 - p0, it = ctx->cfg.ransac_iters;
+    LkParams lp;
+    fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P);
+    CK(launch_lk(lp, &ctx->lk_maps, n, s));
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], s));
+    EgoParams ep;
+    fill_ego(ctx, ep, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P, d_keep + (size_t)p0 * P, 0, ctx->cfg.ego_mode,
+             ctx->cfg.seed + (uint32_t)ctx->pair_counter + (uint32_t)p0, nullptr, nullptr, nullptr);
+    ep.blockcnt += (size_t)p0 * ep.nblk_scan; ep.kept_idx += (size_t)p0 * P; ep.M += p0;
+    ep.hyp += (size_t)p0 * it * 9; ep.hyp_valid += (size_t)p0 * it; ep.counts += (size_t)p0 * it;
+    ep.partial += (size_t)p0 * ep.nblk_acc * 24; ep.H += 9 * p0; ep.Hinv += 9 * p0; ep.inliers += p0; ep.valid += p0;
+    CK(launch_ego(ep, n, s));
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[3], s));
+    if (want_mask) {
+        MaskParams mp;
+        memset(&mp, 0, sizeof mp);
+        mp.prev = slot_plane(ctx, 0, 0); mp.cur = mp.prev;
+        mp.pitch = ctx->g.lv[0].pitch; mp.stride = (long long)ctx->g.slot_img_bytes;
+        mp.nslots = ns; mp.prev_slot0 = (prev0 + p0) % ns; mp.cur_slot0 = (prev0 + p0 + 1) % ns;
+        mp.w = ctx->cfg.width; mp.h = ctx->cfg.height; mp.Hinv = ctx->d_Hinv + 9 * p0; mp.valid = ctx->d_valid + p0;
+        mp.thresh = ctx->cfg.diff_threshold; mp.morph = ctx->cfg.morph;
+        mp.mask = d_mask + (size_t)p0 * mask_stride; mp.mask_pitch = mask_pitch; mp.mask_stride = mask_stride;
+        mp.stat_mask = ctx->d_stats;
+        CK(launch_mask(mp, n, s));
+    }
+    if (ctx->profile) CK(cudaEventRecord(ctx->ev[4], s));
+    return MD_OK;
+}
+
+#define MD_PIPE_CHUNKS 4      // measured: 4 chunks 2 032 pairs/s, 8 chunks 1 887 (per-chunk LK tails), unpipelined 1 918
+
 extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outputs *out, int mem)
 {
     if (!ctx) return MD_ERR_INVALID;
@@ -493,68 +537,81 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int w = ctx->cfg.width, h = ctx->cfg.height, P = ctx->P, ns = ctx->g.nslots;
-
-    const uint8_t *df; int dp; long long ds;
-    int r = stage_frames(ctx, fr->data, fr->channels, fr->pitch, fr->frame_stride, fr->count, mem, &df, &dp, &ds);
-    if (r != MD_OK) return r;
     const int prev0 = ctx->slot_base;
     const int new0 = fr->chain ? (prev0 + 1) % ns : prev0;
-    if (ctx->profile) CK(cudaEventRecord(ctx->ev[0], s));
-    CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, new0, fr->count, df, fr->channels, dp, ds, s));
-    if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], s));
 
-    const bool dev = mem == MD_MEM_DEVICE;
-    float2 *d_next = dev && out->next_pts ? (float2 *)out->next_pts : ctx->d_next;
-    uint8_t *d_status = dev && out->status ? out->status : ctx->d_status;
-    uint8_t *d_keep = dev && out->keep ? out->keep : ctx->d_keep;
-    double *d_H = ctx->d_H;
-    int *d_inl = ctx->d_inliers;
-
-    LkParams lp;
-    fill_lk(ctx, lp, prev0, (prev0 + 1) % ns, nullptr, P, d_next, d_status);
-    CK(launch_lk(lp, &ctx->lk_maps, pairs, s));
-    if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], s));
-
-    EgoParams ep;
-    fill_ego(ctx, ep, nullptr, P, d_next, d_status, d_keep, 0, ctx->cfg.ego_mode, ctx->cfg.seed + (uint32_t)ctx->pair_counter,
-             nullptr, nullptr, nullptr);
-    CK(launch_ego(ep, pairs, s));
-    if (ctx->profile) CK(cudaEventRecord(ctx->ev[3], s));
-
-    if (out->mask) {
-        MaskParams mp;
-        memset(&mp, 0, sizeof mp);
-        mp.prev = slot_plane(ctx, 0, 0); mp.cur = mp.prev;
-        mp.pitch = ctx->g.lv[0].pitch; mp.stride = (long long)ctx->g.slot_img_bytes;
-        mp.nslots = ns; mp.prev_slot0 = prev0; mp.cur_slot0 = (prev0 + 1) % ns;
-        mp.w = w; mp.h = h; mp.Hinv = ctx->d_Hinv; mp.valid = ctx->d_valid;
-        mp.thresh = ctx->cfg.diff_threshold; mp.morph = ctx->cfg.morph;
-        if (dev) { mp.mask = out->mask; mp.mask_pitch = out->mask_pitch; mp.mask_stride = out->mask_stride; }
-        else { mp.mask = ctx->d_mask; mp.mask_pitch = ctx->fpitch; mp.mask_stride = (long long)ctx->fpitch * h; }
-        mp.stat_mask = ctx->d_stats;
-        CK(launch_mask(mp, pairs, s));
-    }
-    if (ctx->profile) CK(cudaEventRecord(ctx->ev[4], s));
-
-    if (dev) {
+    if (mem == MD_MEM_DEVICE) {
+        // stream-ordered, no host synchronisation: everything is enqueued on the context's stream
+        float2 *d_next = out->next_pts ? (float2 *)out->next_pts : ctx->d_next;
+        uint8_t *d_status = out->status ? out->status : ctx->d_status;
+        uint8_t *d_keep = out->keep ? out->keep : ctx->d_keep;
+        if (ctx->profile) CK(cudaEventRecord(ctx->ev[0], s));
+        CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, new0, fr->count, fr->data, fr->channels, fr->pitch, fr->frame_stride, s));
+        if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], s));
+        int r = run_pairs(ctx, prev0, 0, pairs, d_next, d_status, d_keep, out->mask ? out->mask : ctx->d_mask,
+                          out->mask ? out->mask_pitch : ctx->fpitch, out->mask ? out->mask_stride : (long long)ctx->fpitch * h,
+                          out->mask != nullptr, s);
+        if (r != MD_OK) return r;
         if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors, ctx->d_M, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
-        if (out->H) CK(cudaMemcpyAsync(out->H, d_H, sizeof(double) * 9 * pairs, cudaMemcpyDeviceToDevice, s));
-        if (out->inliers) CK(cudaMemcpyAsync(out->inliers, d_inl, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
+        if (out->H) CK(cudaMemcpyAsync(out->H, ctx->d_H, sizeof(double) * 9 * pairs, cudaMemcpyDeviceToDevice, s));
+        if (out->inliers) CK(cudaMemcpyAsync(out->inliers, ctx->d_inliers, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
     } else {
-        if (out->next_pts) CK(cudaMemcpyAsync(out->next_pts, d_next, sizeof(float2) * P * pairs, cudaMemcpyDeviceToHost, s));
-        if (out->status) CK(cudaMemcpyAsync(out->status, d_status, (size_t)P * pairs, cudaMemcpyDeviceToHost, s));
-        if (out->keep) CK(cudaMemcpyAsync(out->keep, d_keep, (size_t)P * pairs, cudaMemcpyDeviceToHost, s));
-        if (out->H) CK(cudaMemcpyAsync(out->H, d_H, sizeof(double) * 9 * pairs, cudaMemcpyDeviceToHost, s));
-        if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors, ctx->d_M, sizeof(int) * pairs, cudaMemcpyDeviceToHost, s));
-        if (out->inliers) CK(cudaMemcpyAsync(out->inliers, d_inl, sizeof(int) * pairs, cudaMemcpyDeviceToHost, s));
-        if (out->mask) {
-            if (out->mask_stride == (long long)out->mask_pitch * h)
-                CK(cudaMemcpy2DAsync(out->mask, out->mask_pitch, ctx->d_mask, ctx->fpitch, w, (size_t)h * pairs, cudaMemcpyDeviceToHost, s));
-            else
-                for (int b = 0; b < pairs; b++)
-                    CK(cudaMemcpy2DAsync(out->mask + b * out->mask_stride, out->mask_pitch, ctx->d_mask + (size_t)b * ctx->fpitch * h,
-                                         ctx->fpitch, w, h, cudaMemcpyDeviceToHost, s));
+        // Host buffers: the batch is cut into chunks and software-pipelined over three streams -- H2D of chunk i+1 and
+        // D2H of chunk i-1 overlap the kernels of chunk i (PCIe is full duplex; the results are complete on return).
+        int r = ensure_frames(ctx, fr->channels);
+        if (r != MD_OK) return r;
+        const int dp = ctx->fpitch * fr->channels;
+        const long long ds = (long long)dp * h;
+        const long long mstride = (long long)ctx->fpitch * h;
+        const int nch = ctx->profile ? 1 : (pairs < MD_PIPE_CHUNKS ? pairs : MD_PIPE_CHUNKS);
+        auto d2h = [&](int p0, int p1) -> int {
+            const int n = p1 - p0;
+            cudaStream_t so = ctx->copy_out;
+            if (out->next_pts) CK(cudaMemcpyAsync(out->next_pts + (size_t)2 * p0 * P, ctx->d_next + (size_t)p0 * P, sizeof(float2) * P * n, cudaMemcpyDeviceToHost, so));
+            if (out->status) CK(cudaMemcpyAsync(out->status + (size_t)p0 * P, ctx->d_status + (size_t)p0 * P, (size_t)P * n, cudaMemcpyDeviceToHost, so));
+            if (out->keep) CK(cudaMemcpyAsync(out->keep + (size_t)p0 * P, ctx->d_keep + (size_t)p0 * P, (size_t)P * n, cudaMemcpyDeviceToHost, so));
+            if (out->H) CK(cudaMemcpyAsync(out->H + 9 * p0, ctx->d_H + 9 * p0, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, so));
+            if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors + p0, ctx->d_M + p0, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
+            if (out->inliers) CK(cudaMemcpyAsync(out->inliers + p0, ctx->d_inliers + p0, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
+            if (out->mask) {
+                if (out->mask_stride == (long long)out->mask_pitch * h)
+                    CK(cudaMemcpy2DAsync(out->mask + p0 * out->mask_stride, out->mask_pitch, ctx->d_mask + p0 * mstride, ctx->fpitch, w,
+                                         (size_t)h * n, cudaMemcpyDeviceToHost, so));
+                else
+                    for (int b = p0; b < p1; b++)
+                        CK(cudaMemcpy2DAsync(out->mask + b * out->mask_stride, out->mask_pitch, ctx->d_mask + b * mstride, ctx->fpitch, w, h,
+                                             cudaMemcpyDeviceToHost, so));
+            }
+            return MD_OK;
+        };
+        int fdone = 0, pprev0 = 0, pprev1 = 0;
+        for (int i = 0; i < nch; i++) {
+            const int p0 = (int)((long long)pairs * i / nch), p1 = (int)((long long)pairs * (i + 1) / nch);
+            const int fa = fdone, fb = fr->chain ? p1 : p1 + 1;
+            for (int f = fa; f < fb; f++)
+                CK(cudaMemcpy2DAsync(ctx->d_frames + f * ds, dp, fr->data + f * fr->frame_stride, fr->pitch, (size_t)w * fr->channels, h,
+                                     cudaMemcpyHostToDevice, ctx->copy_in));
+            CK(cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
+            CK(cudaStreamWaitEvent(s, ctx->ev_in[i], 0));
+            if (ctx->profile) CK(cudaEventRecord(ctx->ev[0], s));
+            CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, (new0 + fa) % ns, fb - fa, ctx->d_frames + fa * ds, fr->channels, dp, ds, s));
+            if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], s));
+            r = run_pairs(ctx, prev0, p0, p1, ctx->d_next, ctx->d_status, ctx->d_keep, ctx->d_mask, ctx->fpitch, mstride, out->mask != nullptr, s);
+            if (r != MD_OK) return r;
+            CK(cudaEventRecord(ctx->ev_comp[i], s));
+            // results of the PREVIOUS chunk are copied out only now, so that (with pageable host memory, where the copy call
+            // blocks) this chunk's kernels are already queued behind it
+            if (i > 0) {
+                CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[i - 1], 0));
+                r = d2h(pprev0, pprev1);
+                if (r != MD_OK) return r;
+            }
+            fdone = fb; pprev0 = p0; pprev1 = p1;
         }
+        CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[nch - 1], 0));
+        r = d2h(pprev0, pprev1);
+        if (r != MD_OK) return r;
+        CK(cudaStreamSynchronize(ctx->copy_out));
         CK(cudaStreamSynchronize(s));
     }
     ctx->slot_base = (prev0 + pairs) % ns;

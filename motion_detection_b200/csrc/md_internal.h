@@ -111,6 +111,8 @@ struct md_ctx {
     md_config cfg;
     int device;
     cudaStream_t own_stream, stream;
+    cudaStream_t copy_in, copy_out;     // H2D / D2H streams of the pipelined host-memory path
+    cudaEvent_t ev_in[8], ev_comp[8];
     std::string err;
     int sm_count;
 

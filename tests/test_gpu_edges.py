@@ -1,0 +1,114 @@
+"""GPU edge cases through the C ABI: tiny / ragged sizes, narrow images (the warp's column-block rule changes below
+64 columns), 4K with projective terms, generic LK window, argument errors, batch limits."""
+import numpy as np
+import pytest
+
+from motion_detection_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(capi, w, h, **kw):
+    kw.setdefault("min_vector_size", 0.2)
+    return capi.Context(width=w, height=h, **kw)
+
+
+@pytest.mark.parametrize("size", [(48, 40), (63, 17), (8, 8), (100, 12), (70, 65)])
+def test_mask_small_and_narrow_images(capi, oracle, size):
+    # w < 64: WarpPerspectiveInvoker's column block is the whole row (bw0 = w); h < 16 changes bh0 as well
+    w, h = size
+    rng = np.random.default_rng(w * 100 + h)
+    a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    b = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    ctx = _ctx(capi, w, h)
+    for H in (np.eye(3), np.array([[1.02, 0.01, -1.3], [-0.02, 0.97, 0.6], [3e-4, -2e-4, 1.0]]),
+              np.array([[1, 0, 0.015625], [0, 1, -0.484375], [0, 0, 1.0]])):
+        for thresh in (190, 50):
+            assert np.array_equal(ctx.motion_mask(a, b, H, thresh=thresh), oracle.motion_mask(a, b, H, thresh=thresh)), (size, thresh)
+
+
+def test_singular_homography_is_handled(capi, oracle):
+    w, h = 64, 48
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    b = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    ctx = _ctx(capi, w, h)
+    H = np.array([[1, 2, 3], [2, 4, 6], [0, 0, 1.0]])            # det = 0: cv::invert returns the zero matrix
+    assert np.array_equal(ctx.motion_mask(a, b, H, thresh=60), oracle.motion_mask(a, b, H, thresh=60))
+
+
+def test_single_level_pyramid_and_tiny_flow(capi, oracle):
+    # 100 x 90: buildOpticalFlowPyramid keeps two levels (50 x 45 > 40), 80 x 60 keeps one
+    for (w, h, levels) in ((100, 90, 2), (80, 60, 1)):
+        fr, _ = synth.sequence(w, h, 2, seed=3, blobs=1, margin=32)
+        ctx = _ctx(capi, w, h, pixel_step=7)
+        assert ctx.levels == levels == len(oracle.pyramid(fr[0]))
+        ctx.pyramid(fr[0], 0)
+        ctx.pyramid(fr[1], 1)
+        nxt, st = ctx.lk_flow(0, 1)
+        ref, rst = oracle.lk(fr[0], fr[1], ctx.grid_points())
+        assert (st != rst).mean() < 0.02
+        ok = (st == 1) & (rst == 1)
+        if ok.any():
+            assert np.linalg.norm(nxt[ok] - ref[ok], axis=1).mean() < 0.01
+
+
+def test_generic_window_kernel(capi, oracle):
+    # windows other than the reference's 40 run the generic kernel (k_lk)
+    fr, _ = synth.sequence(320, 240, 2, seed=9, blobs=1)
+    for win in (21, 32):
+        ctx = _ctx(capi, 320, 240, lk_win=win, pixel_step=12)
+        ctx.pyramid(fr[0], 0)
+        ctx.pyramid(fr[1], 1)
+        nxt, st = ctx.lk_flow(0, 1)
+        ref, rst = oracle.lk(fr[0], fr[1], ctx.grid_points(), win=win)
+        assert (st != rst).mean() < 0.01
+        ok = (st == 1) & (rst == 1)
+        assert np.linalg.norm(nxt[ok] - ref[ok], axis=1).mean() < 0.01
+
+
+def test_4k_projective_chain(capi, oracle):
+    # C3: 3840 x 2160, homography = affine + (h31, h32) = (1e-6, -2e-6); 6 pyramid levels
+    w, h = 3840, 2160
+    fr, Hs = synth.sequence(w, h, 2, seed=1234, h31=1e-6, h32=-2e-6)
+    ctx = _ctx(capi, w, h, pixel_step=40, seed=5)
+    assert ctx.levels == 6
+    res = ctx.process_batch(fr)
+    ref = oracle.process_pair(fr[0], fr[1], pixel_step=40, min_vector_size=0.2, seed=5)
+    ok = (res["status"][0] == 1) & (ref["status"] == 1)
+    assert (res["status"][0] != ref["status"]).mean() < 0.005
+    assert np.linalg.norm(res["next"][0][ok] - ref["next"][ok], axis=1).mean() < 0.01
+    assert np.linalg.norm(res["H"][0] - ref["H"]) / np.linalg.norm(ref["H"]) < 1e-4
+    assert (res["mask"][0] == ref["mask"]).mean() >= 0.999
+    assert np.linalg.norm(res["H"][0] - Hs[0]) / np.linalg.norm(Hs[0]) < 0.02
+
+
+def test_argument_errors_are_status_codes(capi):
+    import ctypes as C
+    ctx = _ctx(capi, 160, 120, max_batch=2)
+    frames = np.zeros((5, 120, 160), np.uint8)
+    with pytest.raises(capi.MotionB200Error) as e:
+        ctx.process_batch(frames)                       # 4 pairs > max_batch
+    assert e.value.code == -1
+    with pytest.raises(capi.MotionB200Error) as e:
+        ctx.lk_flow(0, 7)                               # slot out of range
+    assert e.value.code == -1
+    with pytest.raises(capi.MotionB200Error):
+        ctx.fit_subspace(np.zeros((10, 20, 2), np.float32))      # 2F > 32
+    lib = capi.lib()
+    assert lib.md_process_batch(ctx._h, None, None, 0) == -1
+    # nothing was written on error and the context is still usable
+    fr, _ = synth.sequence(160, 120, 3, seed=2, blobs=1, margin=32)
+    res = ctx.process_batch(fr)
+    assert res["mask"].shape == (2, 120, 160)
+
+
+def test_static_scene_min_vector_filter(capi, oracle):
+    # C1: static camera; with min_vector_size = 0.2 only the moving patch survives the filter (cpp:86)
+    fr, _ = synth.sequence(640, 480, 2, seed=1234, camera=False, blobs=0, patch=True)
+    ctx = _ctx(capi, 640, 480, seed=4)
+    res = ctx.process_batch(fr)
+    ref = oracle.process_pair(fr[0], fr[1], min_vector_size=0.2, seed=4)
+    assert abs(int(res["num_vectors"][0]) - ref["num_vectors"]) <= 3
+    assert np.array_equal(res["keep"][0] != 0, ref["keep"] != 0) or (res["keep"][0] != ref["keep"]).mean() < 0.002
+    assert (res["mask"][0] == ref["mask"]).mean() >= 0.999
