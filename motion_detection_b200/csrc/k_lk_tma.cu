@@ -110,7 +110,43 @@ struct TapLoop {
         b2 += q * ((I & 1) ? (yp >> 16) : (int)(short)yp);
         if constexpr (I + 1 < TW) TapLoop<I + 1, TW>::template iter<NP>(r0, r1, wtop, wbot, Xpk, Ypk, b1, b2);
     }
+    // Same sums, two taps at a time, without unpacking the s16 pairs: q = v >> 9 with v < 2^22, so with u = v >> 1 the low
+    // 8 bits of q are byte 1 of u and the high 5 bits are byte 2 of u.  One PRMT gathers (ql_i, ql_i+1, qh_i, qh_i+1) and
+    // dp2a.lo / dp2a.hi against the packed (Ix_i, Ix_i+1) give sum ql*Ix and sum qh*Ix:  sum q*Ix = 256 * hi + lo.
+    template <int NP>
+    static __device__ __forceinline__ void iter2(const RowWords &r0, const RowWords &r1, int wtop, int wbot, const int (&Xpk)[NP],
+                                                 const int (&Ypk)[NP], int &b1lo, int &b1hi, int &b2lo, int &b2hi)
+    {
+        static_assert((I & 1) == 0, "pairs start at even taps");
+        const int u0 = row_pair<I>(r1, wbot, row_pair<I>(r0, wtop, 1 << (W_BITS - 5 - 1))) >> 1;
+        const int u1 = row_pair<I + 1>(r1, wbot, row_pair<I + 1>(r0, wtop, 1 << (W_BITS - 5 - 1))) >> 1;
+        const uint32_t qb = __byte_perm((uint32_t)u0, (uint32_t)u1, 0x6251);
+        const int xp = Xpk[I >> 1], yp = Ypk[I >> 1];
+        b1lo = dp2a_lo(xp, qb, b1lo); b1hi = dp2a_hi(xp, qb, b1hi);
+        b2lo = dp2a_lo(yp, qb, b2lo); b2hi = dp2a_hi(yp, qb, b2hi);
+        if constexpr (I + 2 < TW) TapLoop<I + 2, TW>::template iter2<NP>(r0, r1, wtop, wbot, Xpk, Ypk, b1lo, b1hi, b2lo, b2hi);
+    }
 };
+
+// rolled row loop of the window build: the finished row is moved into its (compile-time indexed) register row
+template <int R, int TH, int NP>
+struct RowStore {
+    static __device__ __forceinline__ void put(int r, int (&Xpk)[TH][NP], int (&Ypk)[TH][NP], const int (&Xr)[NP], const int (&Yr)[NP])
+    {
+        if (r == R) {
+#pragma unroll
+            for (int i = 0; i < NP; i++) { Xpk[R][i] = Xr[i]; Ypk[R][i] = Yr[i]; }
+        } else if constexpr (R + 1 < TH) RowStore<R + 1, TH, NP>::put(r, Xpk, Ypk, Xr, Yr);
+    }
+};
+
+// exact warp sum of per-lane int32 partial sums (|v| < 2^31): two REDUX adds on the 16-bit halves, one rounding to f32
+__device__ __forceinline__ float warp_sum_exact_f32(int v)
+{
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
+    return (float)((long long)hi * 65536 + (long long)lo);
+}
 
 template <int WIN, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 2) k_lk_tma(const LkParams p, const __grid_constant__ LkTmaMaps maps)
@@ -205,13 +241,16 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_lk_tma(const LkParams p, cons
             const int wtop = (int)__byte_perm((uint32_t)w00, (uint32_t)w01, 0x5410);
             const int wbot = (int)__byte_perm((uint32_t)w10, (uint32_t)w11, 0x5410);
             RowWords r0 = load_row(tI + (TH * ly) * T::IP, wb, sh);
-#pragma unroll
+            // the row loop stays ROLLED (the unrolled build was 26 KB of SASS and thrashed the instruction cache)
+#pragma unroll 1
             for (int r = 0; r < TH; r++) {
                 const RowWords r1 = load_row(tI + (TH * ly + r + 1) * T::IP, wb, sh);
                 const uint32_t *d0 = tD + (TH * ly + r) * T::DP + (gx & 3) + TW * lx, *d1 = d0 + T::DP;
                 int xprev = 0, yprev = 0;
-                TapLoop<0, TW>::template build<NP>(r0, r1, d0, d1, wtop, wbot, w00, w01, w10, w11, Xpk[r], Ypk[r], a11, a12, a22,
-                                                   c1, c2, xprev, yprev);
+                int Xr[NP], Yr[NP];
+                TapLoop<0, TW>::template build<NP>(r0, r1, d0, d1, wtop, wbot, w00, w01, w10, w11, Xr, Yr, a11, a12, a22, c1, c2,
+                                                   xprev, yprev);
+                RowStore<0, TH, NP>::put(r, Xpk, Ypk, Xr, Yr);
                 r0 = r1;
             }
         }
@@ -219,9 +258,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_lk_tma(const LkParams p, cons
         if (level > 0) issue_I(level - 1);
         if (j_ok) { mbar_wait(barJ, phJ); phJ ^= 1; }
 
-        const float A11 = (float)warp_sum((double)a11) * FLT_SCALE;
-        const float A12 = (float)warp_sum((double)a12) * FLT_SCALE;
-        const float A22 = (float)warp_sum((double)a22) * FLT_SCALE;
+        const float A11 = warp_sum_exact_f32(a11) * FLT_SCALE;
+        const float A12 = warp_sum_exact_f32(a12) * FLT_SCALE;
+        const float A22 = warp_sum_exact_f32(a22) * FLT_SCALE;
         float D;
         if (!lk_min_eig_ok(A11, A12, A22, WIN, p.min_eig, D)) {
             if (level == 0) st = 0;
@@ -249,16 +288,17 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_lk_tma(const LkParams p, cons
             const uint32_t *rowp = tJ + ((iny - ty0) + TH * ly) * T::JP;
             const int wtop = (int)__byte_perm((uint32_t)w00, (uint32_t)w01, 0x5410);
             const int wbot = (int)__byte_perm((uint32_t)w10, (uint32_t)w11, 0x5410);
-            int b1 = -c1, b2 = -c2;
+            int b1lo = -c1, b1hi = 0, b2lo = -c2, b2hi = 0;
             RowWords r0 = load_row(rowp, wb, sh);
 #pragma unroll
             for (int r = 0; r < TH; r++) {
                 const RowWords r1 = load_row(rowp + (r + 1) * T::JP, wb, sh);
-                TapLoop<0, TW>::template iter<NP>(r0, r1, wtop, wbot, Xpk[r], Ypk[r], b1, b2);
+                TapLoop<0, TW>::template iter2<NP>(r0, r1, wtop, wbot, Xpk[r], Ypk[r], b1lo, b1hi, b2lo, b2hi);
                 r0 = r1;
             }
-            const float fb1 = (float)warp_sum((double)b1) * FLT_SCALE;
-            const float fb2 = (float)warp_sum((double)b2) * FLT_SCALE;
+            const int b1 = b1hi * 256 + b1lo, b2 = b2hi * 256 + b2lo;
+            const float fb1 = warp_sum_exact_f32(b1) * FLT_SCALE;
+            const float fb2 = warp_sum_exact_f32(b2) * FLT_SCALE;
             if (lk_update(A11, A12, A22, D, fb1, fb2, half, j, p.eps2, s, nxt)) break;
         }
     }
