@@ -522,7 +522,7 @@ static int run_pairs(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uin
     return MD_OK;
 }
 
-#define MD_PIPE_CHUNKS 4      // measured: 4 chunks 2 032 pairs/s, 8 chunks 1 887 (per-chunk LK tails), unpipelined 1 918
+#define MD_PIPE_CHUNKS 5      // 1 + 3 even + 1; measured: 4 even chunks 2 032 pairs/s, 8 even 1 887 (per-chunk LK tails), unpipelined 1 918
 
 extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outputs *out, int mem)
 {
@@ -563,7 +563,19 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
         const int dp = ctx->fpitch * fr->channels;
         const long long ds = (long long)dp * h;
         const long long mstride = (long long)ctx->fpitch * h;
-        const int nch = ctx->profile ? 1 : (pairs < MD_PIPE_CHUNKS ? pairs : MD_PIPE_CHUNKS);
+        // chunk boundaries: a short first chunk (its H2D is exposed) and a short last chunk (its D2H is exposed) around
+        // MD_PIPE_CHUNKS - 2 even middle chunks
+        int bounds[MD_PIPE_CHUNKS + 3];
+        int nch = 0;
+        bounds[0] = 0;
+        if (ctx->profile || pairs < 2) { nch = 1; bounds[1] = pairs; }
+        else if (pairs < 8) { nch = 2; bounds[1] = pairs / 2; bounds[2] = pairs; }
+        else {
+            const int mid = MD_PIPE_CHUNKS - 2 > 0 ? MD_PIPE_CHUNKS - 2 : 1;
+            bounds[++nch] = 1;
+            for (int i = 1; i <= mid; i++) bounds[++nch] = 1 + (int)((long long)(pairs - 2) * i / mid);
+            bounds[++nch] = pairs;
+        }
         auto d2h = [&](int p0, int p1) -> int {
             const int n = p1 - p0;
             cudaStream_t so = ctx->copy_out;
@@ -586,7 +598,7 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
         };
         int fdone = 0, pprev0 = 0, pprev1 = 0;
         for (int i = 0; i < nch; i++) {
-            const int p0 = (int)((long long)pairs * i / nch), p1 = (int)((long long)pairs * (i + 1) / nch);
+            const int p0 = bounds[i], p1 = bounds[i + 1];
             const int fa = fdone, fb = fr->chain ? p1 : p1 + 1;
             for (int f = fa; f < fb; f++)
                 CK(cudaMemcpy2DAsync(ctx->d_frames + f * ds, dp, fr->data + f * fr->frame_stride, fr->pitch, (size_t)w * fr->channels, h,

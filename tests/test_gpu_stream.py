@@ -1,0 +1,46 @@
+"""GPU: long chained streams (ROS-free emulation of the node's frame loop): the pyramid ring wraps many
+times, every pair is still the oracle's pair, and the per-stream counters add up."""
+import numpy as np
+import pytest
+
+from motion_detection_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_long_chained_stream_ring_wraparound(capi, oracle):
+    w, h, n = 320, 240, 121
+    frames, _ = synth.sequence(w, h, n, seed=77, blobs=2)
+    ctx = capi.Context(width=w, height=h, max_batch=7, pixel_step=10, min_vector_size=0.2, seed=100)
+    masks, Hs, nv = [], [], []
+    res = ctx.process_batch(frames[:6])                         # pairs 0..4
+    masks.append(res["mask"]); Hs.append(res["H"]); nv.append(res["num_vectors"])
+    f = 6
+    rng = np.random.default_rng(0)
+    while f < n:
+        k = int(min(n - f, rng.integers(1, 8)))                 # ragged batch sizes 1..7 through a ring of 8 slots
+        res = ctx.process_batch(frames[f:f + k], chain=True)
+        masks.append(res["mask"]); Hs.append(res["H"]); nv.append(res["num_vectors"])
+        f += k
+    masks = np.concatenate(masks); Hs = np.concatenate(Hs); nv = np.concatenate(nv)
+    assert len(masks) == n - 1
+    for p in range(0, n - 1, 17):                               # sampled pairs against the oracle (seed = seed0 + pair index)
+        ref = oracle.process_pair(frames[p], frames[p + 1], min_vector_size=0.2, seed=100 + p)
+        assert abs(int(nv[p]) - ref["num_vectors"]) <= 2
+        assert np.linalg.norm(Hs[p] - ref["H"]) / np.linalg.norm(ref["H"]) < 1e-4, p
+        assert (masks[p] == ref["mask"]).mean() >= 0.999, p
+    st = ctx.stats()
+    assert st["pairs"] == n - 1
+    assert st["mask_pixels"] == int((masks > 0).sum())
+
+
+def test_skip_frames_like_the_node(capi, oracle):
+    # imageCallback keeps every `skip_frames`-th image (node.cpp:237-261): the hot path only ever sees the kept frames
+    frames, _ = synth.sequence(320, 240, 9, seed=5, blobs=1)
+    kept = frames[::2]
+    ctx = capi.Context(width=320, height=240, max_batch=4, pixel_step=10, min_vector_size=0.4, seed=1)
+    res = ctx.process_batch(kept)
+    for p in range(len(kept) - 1):
+        ref = oracle.process_pair(kept[p], kept[p + 1], min_vector_size=0.4, seed=1 + p)
+        assert np.linalg.norm(res["H"][p] - ref["H"]) / np.linalg.norm(ref["H"]) < 1e-4
+        assert (res["mask"][p] == ref["mask"]).mean() >= 0.999
