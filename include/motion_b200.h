@@ -46,6 +46,10 @@ typedef enum md_mem { MD_MEM_HOST = 0, MD_MEM_DEVICE = 1 } md_mem;
  *          (common/src/outlier_detector.cpp:223-234), inlier counting, first-best-wins (:300), LS refit. */
 typedef enum md_ego_mode { MD_EGO_FIRST4 = 0, MD_EGO_RANSAC_HOMOGRAPHY = 1, MD_EGO_RANSAC_AFFINE = 2 } md_ego_mode;
 
+/* Flow engine of the chain: grid pyramidal LK (calculateOpticalFlow, cpp:71) or the dense variational flow
+ * (VarFlow::CalcFlow, VarFlow.cpp:600) sampled at the grid points. */
+typedef enum md_flow_engine { MD_FLOW_LK = 0, MD_FLOW_VARFLOW = 1 } md_flow_engine;
+
 typedef struct md_config {
     int32_t width, height;      /* frame size in pixels */
     int32_t max_batch;          /* max frame PAIRS per md_process_batch call (>= 1) */
@@ -69,7 +73,8 @@ typedef struct md_config {
     int32_t vf_n1, vf_n2;       /* 2, 2 */
     float   vf_rho, vf_alpha, vf_sigma; /* 2.8, 1400, 1.5 */
     int32_t vf_literal;         /* 1 = literal multigrid schedule incl. the (numerically inert) coarse corrections */
-    int32_t reserved[8];
+    int32_t flow_engine;        /* md_flow_engine: which flow feeds the egomotion fit in md_process_batch */
+    int32_t reserved[7];
 } md_config;
 
 typedef struct md_ctx md_ctx;

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libmotion_b200.so")
 MD_OK = 0
 MD_MEM_HOST, MD_MEM_DEVICE = 0, 1
 MD_EGO_FIRST4, MD_EGO_RANSAC_HOMOGRAPHY, MD_EGO_RANSAC_AFFINE = 0, 1, 2
+MD_FLOW_LK, MD_FLOW_VARFLOW = 0, 1
 STATUS_NAMES = {0: "MD_OK", -1: "MD_ERR_INVALID", -2: "MD_ERR_CUDA", -3: "MD_ERR_NOMEM", -4: "MD_ERR_UNSUPPORTED",
                 -5: "MD_ERR_STATE"}
 
@@ -37,7 +38,7 @@ class MdConfig(C.Structure):
         ("ransac_thresh", C.c_double), ("seed", C.c_uint32),
         ("vf_max_level", C.c_int32), ("vf_start_level", C.c_int32), ("vf_n1", C.c_int32), ("vf_n2", C.c_int32),
         ("vf_rho", C.c_float), ("vf_alpha", C.c_float), ("vf_sigma", C.c_float), ("vf_literal", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("flow_engine", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 

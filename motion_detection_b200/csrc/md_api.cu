@@ -90,6 +90,7 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
     if (cfg->ransac_iters < 1 || cfg->ransac_iters > MD_MAX_HYP) return MD_ERR_INVALID;
     if (cfg->ego_mode < 0 || cfg->ego_mode > 2) return MD_ERR_INVALID;
     if (cfg->vf_start_level != 0) return MD_ERR_UNSUPPORTED;
+    if (cfg->flow_engine != MD_FLOW_LK && cfg->flow_engine != MD_FLOW_VARFLOW) return MD_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return MD_ERR_CUDA;
     cudaDeviceProp prop;
@@ -494,9 +495,18 @@ static int run_pairs(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uin
                      int mask_pitch, long long mask_stride, bool want_mask, cudaStream_t s)
 {
     const int P = ctx->P, ns = ctx->g.nslots, n = p1 - p0, it = ctx->cfg.ransac_iters;
-    LkParams lp;
-    fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P);
-    CK(launch_lk(lp, &ctx->lk_maps, n, s));
+    if (ctx->cfg.flow_engine == MD_FLOW_VARFLOW) {
+        // dense variational flow per pair, sampled at the grid points (the gray frames are the level-0 planes)
+        for (int q = p0; q < p1; q++) {
+            const int rc = vf_compute_device(ctx, slot_plane(ctx, (prev0 + q) % ns, 0), slot_plane(ctx, (prev0 + q + 1) % ns, 0), ctx->g.lv[0].pitch);
+            if (rc != MD_OK) return rc;
+            CK(vf_sample_grid(ctx, d_next + (size_t)q * P, d_status + (size_t)q * P, s));
+        }
+    } else {
+        LkParams lp;
+        fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P);
+        CK(launch_lk(lp, &ctx->lk_maps, n, s));
+    }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], s));
     EgoParams ep;
     fill_ego(ctx, ep, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P, d_keep + (size_t)p0 * P, 0, ctx->cfg.ego_mode,

@@ -150,6 +150,8 @@ struct md_ctx {
 };
 
 void vf_free_workspace(void *ws);
+int vf_compute_device(md_ctx *ctx, const uint8_t *dA, const uint8_t *dB, int dpitch);
+cudaError_t vf_sample_grid(md_ctx *ctx, float2 *next, uint8_t *status, cudaStream_t s);
 
 extern long long g_md_launches;   // kernels launched by this library (process wide)
 #define MD_COUNT_LAUNCH(n) (g_md_launches += (n))

@@ -212,6 +212,24 @@ def process_pair(prev, cur, pixel_step=10, min_vector_size=0.2, mode=MODE_RANSAC
                 inlier_mask=inl, mask=mask)
 
 
+def process_pair_varflow(prev, cur, pixel_step=10, min_vector_size=0.2, mode=MODE_RANSAC_HOMOGRAPHY, iters=50, thr=0.5,
+                         seed=1, thresh=190, morph=True):
+    """The same composition with the dense variational flow (VarFlow::CalcFlow, VarFlow.cpp:600-697) as the flow engine:
+    the field is sampled at the grid points, next = (x + U, y - V) since V is y-up (VarFlow.cpp:103-107)."""
+    h, w = prev.shape
+    pts = grid_points(w, h, pixel_step)
+    U, V = varflow(prev, cur)
+    xi = pts[:, 0].astype(np.int64)
+    yi = pts[:, 1].astype(np.int64)
+    p2 = np.stack([pts[:, 0] + U[yi, xi], pts[:, 1] - V[yi, xi]], axis=1).astype(np.float32)
+    st = np.ones(len(pts), np.uint8)
+    nv, keep, flow4 = flow_filter(pts, p2, st, min_vector_size)
+    ninl, H, inl = fit_egomotion(pts, p2, keep, w, h, mode, iters, thr, seed)
+    mask = motion_mask(prev, cur, H, thresh, morph) if ninl > 0 else np.zeros_like(prev)
+    return dict(pts=pts, next=p2, status=st, keep=keep, flow4=flow4, num_vectors=nv, H=H, inliers=ninl, inlier_mask=inl,
+                mask=mask, U=U, V=V)
+
+
 def gaussian_blur_f32(img, sigma):
     img = np.ascontiguousarray(img, np.float32)
     h, w = img.shape
