@@ -103,8 +103,9 @@ __global__ void __launch_bounds__(WARPS * 32) k_lk(const LkParams p)
     }
 }
 
-cudaError_t launch_lk(const LkParams &p, const LkTmaMaps *maps, int pairs, cudaStream_t s)
+cudaError_t launch_lk(const LkParams &p, const LkTmaMaps *maps, const LkPhaseMaps *pmaps, int pairs, cudaStream_t s)
 {
+    if (!p.pts_in && pmaps && pmaps->valid && p.ph && p.win == 40) return launch_lk_phase(p, pmaps, pairs, s);
     if (maps && maps->valid && p.win == 40) return launch_lk_tma(p, maps, pairs, s);
     constexpr int WARPS = 8;
     dim3 grid((p.P + WARPS - 1) / WARPS, pairs);

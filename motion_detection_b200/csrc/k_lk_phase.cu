@@ -1,0 +1,296 @@
+// k_lk_phase.cu -- K2 for GRID points (pts_in == NULL, window 40): pyramidal Lucas-Kanade on precomputed sub-pixel
+// phase planes.
+//
+// Replaces cv::calcOpticalFlowPyrLK(...) as called at common/src/optical_flow_calculator.cpp:71 (grid built at :56-64).
+// Arithmetic is identical to k_lk_tma.cu / k_lk.cu (OpenCV's LKTrackerInvoker fixed-point scheme, lk_common.cuh); only
+// WHERE the window samples are computed differs:
+//
+//  * The tracked grid sits at integer multiples of pixel_step, so at level l a point's window origin
+//    (x / 2^l - 19.5) has one of (2^l / gcd(ps, 2^l))^2 fractional parts.  LKTrackerInvoker's bilinear weights depend
+//    on that fraction only, so the window samples I (5 extra bits), Ix, Iy of ALL points of a class are the same
+//    function of the integer origin.  k_phase_planes evaluates them once per pixel and class (2 N pixel evaluations
+//    per frame at pixel_step 10 instead of 80 N per-point tap evaluations); the per-point window build of k_lk_tma
+//    (48 % of its instructions) becomes one TMA box load + the integer sums A11, A12, A22, sum I*Ix, sum I*Iy.
+//  * The iteration loop (J tile staged by TMA, dp2a bilinear samples, dp2a mismatch accumulation on packed tap pairs,
+//    REDUX reductions) is the one of k_lk_tma.cu.
+#include "lk_tile.cuh"
+#include "tma.h"
+
+// ---- phase planes ----------------------------------------------------------------------------------------------------
+struct PhParams {
+    PyrGeom g;
+    PhaseGeom pg;
+    const uint8_t *img;
+    const short2 *der;
+    int16_t *ph;
+    int prev_slot0, pair0;
+    float half;
+};
+
+// One thread = 8 consecutive plane pixels x 4 rows of one (class, pair): aligned 8-byte / 32-byte loads of the padded
+// pyramid planes, 16-byte stores.  Horizontal partial sums of a source row serve as the bottom half of one output row and
+// the top half of the next.
+__global__ void __launch_bounds__(256) k_phase_planes(const PhParams q, int level)
+{
+    const PhaseLevel PL = q.pg.lv[level];
+    const LevelGeom L = q.g.lv[level];
+    const int nxt = PL.pitch >> 3;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int xt = t % nxt, yt = t / nxt;
+    const int Y0 = yt * 4;
+    if (Y0 >= PL.h) return;
+    const int cls = blockIdx.y, b = blockIdx.z;
+    const int cx = cls % PL.ncx, cy = cls / PL.ncx;
+    int w00, w01, w10, w11;
+    {
+        // the fraction of a class representative's window origin, computed exactly like the LK kernels compute a point's
+        const float scale = 1.f / (float)(1 << level);
+        const float ppx = __fsub_rn((float)(cx << PL.shift) * scale, q.half), ppy = __fsub_rn((float)(cy << PL.shift) * scale, q.half);
+        lk_weights(__fsub_rn(ppx, floorf(ppx)), __fsub_rn(ppy, floorf(ppy)), w00, w01, w10, w11);
+    }
+    const int slot = (q.prev_slot0 + b) % q.g.nslots;
+    const int X0 = xt * 8;
+    // plane pixel (X, Y) <- source pixel (X - margin, Y - margin) of the padded level plane
+    const size_t src0 = (size_t)(q.g.pady - MD_PH_MARGIN + Y0) * L.pitch + (q.g.padx - MD_PH_MARGIN + X0);
+    const uint8_t *ip = q.img + (size_t)slot * q.g.slot_img_bytes + L.img_off + src0;
+    const short2 *dp = q.der + (size_t)slot * q.g.slot_der_elems + L.der_off + src0;
+    const size_t plane = (size_t)PL.pitch * PL.h;
+    int16_t *out = q.ph + (size_t)(q.pair0 + b) * q.pg.pair_elems + PL.off + (size_t)cls * 3 * plane + (size_t)Y0 * PL.pitch + X0;
+
+    int ti[8], tx[8], ty[8];      // top halves carried from the previous source row
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        if (Y0 + r > PL.h) break;             // source row r feeds output rows r-1 and r
+        const uint2 iw = *reinterpret_cast<const uint2 *>(ip + (size_t)r * L.pitch);
+        const uint32_t i8 = ip[(size_t)r * L.pitch + 8];
+        const uint4 da = *reinterpret_cast<const uint4 *>(dp + (size_t)r * L.pitch);
+        const uint4 db = *reinterpret_cast<const uint4 *>(dp + (size_t)r * L.pitch + 4);
+        const uint32_t d8 = *reinterpret_cast<const uint32_t *>(dp + (size_t)r * L.pitch + 8);
+        int pv[9], dx[9], dy[9];
+        const uint32_t dd[9] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w, d8};
+#pragma unroll
+        for (int i = 0; i < 9; i++) {
+            pv[i] = i < 4 ? (int)((iw.x >> (8 * i)) & 0xffu) : (i < 8 ? (int)((iw.y >> (8 * (i - 4))) & 0xffu) : (int)i8);
+            dx[i] = (int)(short)(dd[i] & 0xffffu);
+            dy[i] = (int)dd[i] >> 16;
+        }
+        uint32_t oi[4], ox[4], oy[4];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int bi = w10 * pv[i] + w11 * pv[i + 1], bx = w10 * dx[i] + w11 * dx[i + 1], by = w10 * dy[i] + w11 * dy[i + 1];
+            if (r > 0) {
+                const int iv = (ti[i] + bi + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                const int xv = (tx[i] + bx + (1 << (W_BITS - 1))) >> W_BITS;
+                const int yv = (ty[i] + by + (1 << (W_BITS - 1))) >> W_BITS;
+                if (i & 1) {
+                    oi[i >> 1] |= (uint32_t)iv << 16; ox[i >> 1] |= (uint32_t)xv << 16; oy[i >> 1] |= (uint32_t)yv << 16;
+                } else {
+                    oi[i >> 1] = (uint32_t)iv & 0xffffu; ox[i >> 1] = (uint32_t)xv & 0xffffu; oy[i >> 1] = (uint32_t)yv & 0xffffu;
+                }
+            }
+            ti[i] = w00 * pv[i] + w01 * pv[i + 1]; tx[i] = w00 * dx[i] + w01 * dx[i + 1]; ty[i] = w00 * dy[i] + w01 * dy[i + 1];
+        }
+        if (r > 0) {
+            int16_t *o = out + (size_t)(r - 1) * PL.pitch;
+            *reinterpret_cast<uint4 *>(o) = make_uint4(oi[0], oi[1], oi[2], oi[3]);
+            *reinterpret_cast<uint4 *>(o + plane) = make_uint4(ox[0], ox[1], ox[2], ox[3]);
+            *reinterpret_cast<uint4 *>(o + 2 * plane) = make_uint4(oy[0], oy[1], oy[2], oy[3]);
+        }
+    }
+}
+
+// ---- LK on phase planes ------------------------------------------------------------------------------------------------
+struct PhTile {
+    static constexpr int WIN = 40, LXN = 4, LYN = 8;
+    static constexpr int TW = WIN / LXN, TH = WIN / LYN, NP = TW / 2;
+    static constexpr int PW = MD_PH_BOX_W / 2;        // phase tile pitch in words (24)
+    static constexpr int PLANE_WORDS = PW * WIN;      // 960
+    static constexpr int JP = MD_LK_J_BOX_W / 4;      // J tile pitch in words (20)
+    static constexpr int JROWS = WIN + 1 + 2 * MD_LK_J_MARGIN_Y;
+    static constexpr int P_BYTES = 3 * PLANE_WORDS * 4, J_BYTES = MD_LK_J_BOX_W * JROWS;
+    static constexpr int P_OFF = 0;
+    static constexpr int J_OFF = (P_BYTES + 127) / 128 * 128;
+    static constexpr int BAR_OFF = J_OFF + (J_BYTES + 127) / 128 * 128;
+    static constexpr int WARP_BYTES = BAR_OFF + 128;
+    static constexpr int JX_MAX = MD_LK_J_BOX_W - (WIN + 1) - 3;
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) k_lk_phase(const LkParams p, const __grid_constant__ LkPhaseMaps maps)
+{
+    using T = PhTile;
+    constexpr int WIN = T::WIN, TW = T::TW, TH = T::TH, NP = T::NP;
+    extern __shared__ __align__(1024) uint8_t lkp_sm_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int k = blockIdx.x * WARPS + warp;
+    const int b = blockIdx.y;
+    if (k >= p.P) return;
+    uint8_t *wbase = lkp_sm_raw + (size_t)warp * T::WARP_BYTES;
+    uint32_t *tP = reinterpret_cast<uint32_t *>(wbase + T::P_OFF);
+    uint32_t *tJ = reinterpret_cast<uint32_t *>(wbase + T::J_OFF);
+    uint64_t *barP = reinterpret_cast<uint64_t *>(wbase + T::BAR_OFF), *barJ = barP + 1;
+    const int lx = lane & 3, ly = lane >> 2;
+    if (lane == 0) {
+        mbar_init(barP, 1);
+        mbar_init(barJ, 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    uint32_t phP = 0, phJ = 0;
+
+    const int gxi = p.ps * (k / p.gy), gyi = p.ps * (k % p.gy);       // the grid point (cpp:56-64: x outer, y inner)
+    const float2 pt = make_float2((float)gxi, (float)gyi);
+    const int slotJ = (p.next_slot0 + b) % p.g.nslots;
+    const float half = (WIN - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    float2 nxt = make_float2(0.f, 0.f);
+    int st = 1;
+
+    // request the window (I, Ix, Iy planes of the point's phase class) of `level`
+    auto issue_P = [&](int level) {
+        const float scale = 1.f / (float)(1 << level);
+        const float ppx = __fsub_rn(pt.x * scale, half), ppy = __fsub_rn(pt.y * scale, half);
+        const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
+        if (ipx < -WIN || ipx >= p.g.lv[level].w || ipy < -WIN || ipy >= p.g.lv[level].h) return;
+        if (lane == 0) {
+            const int msk = (1 << level) - 1, sh = p.pg.lv[level].shift;
+            const int cls = ((gyi & msk) >> sh) * p.pg.lv[level].ncx + ((gxi & msk) >> sh);
+            mbar_expect_tx(barP, T::P_BYTES);
+            tma_load_5d(tP, &maps.ph[level], (ipx + MD_PH_MARGIN) & ~7, ipy + MD_PH_MARGIN, 0, cls, p.ph_pair0 + b, barP);
+        }
+    };
+    issue_P(p.g.nlev - 1);
+
+    for (int level = p.g.nlev - 1; level >= 0; level--) {
+        const int Lw = p.g.lv[level].w, Lh = p.g.lv[level].h;
+        const float scale = 1.f / (float)(1 << level);
+        float ppx = pt.x * scale, ppy = pt.y * scale;
+        LkIterState s;
+        if (level == p.g.nlev - 1) { s.npx = ppx; s.npy = ppy; }
+        else { s.npx = nxt.x * 2.f; s.npy = nxt.y * 2.f; }
+        nxt = make_float2(s.npx, s.npy);
+        ppx = __fsub_rn(ppx, half); ppy = __fsub_rn(ppy, half);
+        const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
+        if (ipx < -WIN || ipx >= Lw || ipy < -WIN || ipy >= Lh) {
+            if (level == 0) st = 0;
+            else issue_P(level - 1);
+            continue;
+        }
+        // ---- request the next-frame tile around the initial guess; it lands while the window sums are formed ---------
+        s.npx = __fsub_rn(s.npx, half); s.npy = __fsub_rn(s.npy, half);
+        int tx0 = 0, ty0 = 0;
+        bool j_ok = false;
+        {
+            const int inx = __float2int_rd(s.npx), iny = __float2int_rd(s.npy);
+            if (!(inx < -WIN || inx >= Lw || iny < -WIN || iny >= Lh)) {
+                tx0 = ((inx - MD_LK_J_MARGIN_X + p.g.padx) & ~15) - p.g.padx; ty0 = iny - MD_LK_J_MARGIN_Y;
+                j_ok = true;
+                __syncwarp();      // every lane is done with the J tile of the previous level
+                if (lane == 0) {
+                    mbar_expect_tx(barJ, T::J_BYTES);
+                    tma_load_3d(tJ, &maps.imgJ[level], tx0 + p.g.padx, ty0 + p.g.pady, slotJ, barJ);
+                }
+            }
+        }
+
+        // ---- window samples from the phase planes into registers, structure tensor, constant part of the mismatch ----
+        mbar_wait(barP, phP); phP ^= 1;
+        int Xpk[TH][NP], Ypk[TH][NP];
+        int a11 = 0, a12 = 0, a22 = 0, c1 = 0, c2 = 0;
+        {
+            const int e0 = ((ipx + MD_PH_MARGIN) & 7) + TW * lx;       // first tap column of this lane inside the box
+            const int sh = (e0 & 1) * 16;
+            const uint32_t *pI = tP + (TH * ly) * T::PW + (e0 >> 1), *pX = pI + T::PLANE_WORDS, *pY = pX + T::PLANE_WORDS;
+#pragma unroll
+            for (int r = 0; r < TH; r++) {
+                uint32_t wi[NP + 1], wx[NP + 1], wy[NP + 1];
+#pragma unroll
+                for (int i = 0; i <= NP; i++) { wi[i] = pI[r * T::PW + i]; wx[i] = pX[r * T::PW + i]; wy[i] = pY[r * T::PW + i]; }
+#pragma unroll
+                for (int i = 0; i < NP; i++) {
+                    const uint32_t qi = __funnelshift_r(wi[i], wi[i + 1], sh);
+                    const int X = (int)__funnelshift_r(wx[i], wx[i + 1], sh), Y = (int)__funnelshift_r(wy[i], wy[i + 1], sh);
+                    const int x0 = (int)(short)X, x1 = X >> 16, y0 = (int)(short)Y, y1 = Y >> 16;
+                    const int i0 = (int)(qi & 0xffffu), i1 = (int)(qi >> 16);
+                    a11 += x0 * x0 + x1 * x1; a12 += x0 * y0 + x1 * y1; a22 += y0 * y0 + y1 * y1;
+                    c1 += i0 * x0 + i1 * x1; c2 += i0 * y0 + i1 * y1;
+                    Xpk[r][i] = X; Ypk[r][i] = Y;
+                }
+            }
+        }
+        __syncwarp();                       // the phase tile is consumed: prefetch the next level's
+        if (level > 0) issue_P(level - 1);
+        if (j_ok) { mbar_wait(barJ, phJ); phJ ^= 1; }
+
+        const float A11 = warp_sum_exact_f32(a11) * FLT_SCALE;
+        const float A12 = warp_sum_exact_f32(a12) * FLT_SCALE;
+        const float A22 = warp_sum_exact_f32(a22) * FLT_SCALE;
+        float D;
+        if (!lk_min_eig_ok(A11, A12, A22, WIN, p.min_eig, D)) {
+            if (level == 0) st = 0;
+            continue;
+        }
+        s.pdx = 0.f; s.pdy = 0.f;
+        for (int j = 0; j < p.max_iters; j++) {
+            const int inx = __float2int_rd(s.npx), iny = __float2int_rd(s.npy);
+            if (inx < -WIN || inx >= Lw || iny < -WIN || iny >= Lh) {
+                if (level == 0) st = 0;
+                break;
+            }
+            int w00, w01, w10, w11;
+            lk_weights(__fsub_rn(s.npx, (float)inx), __fsub_rn(s.npy, (float)iny), w00, w01, w10, w11);
+            // ---- restage the J tile when the window drifts out of it (warp-uniform, rare) -----------------------------
+            if (inx < tx0 || inx - tx0 > T::JX_MAX || iny < ty0 || iny - ty0 > 2 * MD_LK_J_MARGIN_Y) {
+                tx0 = ((inx - MD_LK_J_MARGIN_X + p.g.padx) & ~15) - p.g.padx; ty0 = iny - MD_LK_J_MARGIN_Y;
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_expect_tx(barJ, T::J_BYTES);
+                    tma_load_3d(tJ, &maps.imgJ[level], tx0 + p.g.padx, ty0 + p.g.pady, slotJ, barJ);
+                }
+                mbar_wait(barJ, phJ); phJ ^= 1;
+            }
+            const int c0 = (inx - tx0) + TW * lx, wb = c0 >> 2, sh = (c0 & 3) * 8;
+            const uint32_t *rowp = tJ + ((iny - ty0) + TH * ly) * T::JP;
+            const int wtop = (int)__byte_perm((uint32_t)w00, (uint32_t)w01, 0x5410);
+            const int wbot = (int)__byte_perm((uint32_t)w10, (uint32_t)w11, 0x5410);
+            int b1lo = -c1, b1hi = 0, b2lo = -c2, b2hi = 0;
+            RowWords r0 = load_row(rowp, wb, sh);
+#pragma unroll
+            for (int r = 0; r < TH; r++) {
+                const RowWords r1 = load_row(rowp + (r + 1) * T::JP, wb, sh);
+                TapLoop<0, TW>::template iter2<NP>(r0, r1, wtop, wbot, Xpk[r], Ypk[r], b1lo, b1hi, b2lo, b2hi);
+                r0 = r1;
+            }
+            const int b1 = b1hi * 256 + b1lo, b2 = b2hi * 256 + b2lo;
+            const float fb1 = warp_sum_exact_f32(b1) * FLT_SCALE;
+            const float fb2 = warp_sum_exact_f32(b2) * FLT_SCALE;
+            if (lk_update(A11, A12, A22, D, fb1, fb2, half, j, p.eps2, s, nxt)) break;
+        }
+    }
+    if (lane == 0) {
+        p.next[(size_t)b * p.P + k] = nxt;
+        p.status[(size_t)b * p.P + k] = (uint8_t)st;
+    }
+}
+
+cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pairs, cudaStream_t s)
+{
+    PhParams q;
+    q.g = p.g; q.pg = p.pg; q.img = p.img; q.der = p.der; q.ph = p.ph; q.prev_slot0 = p.prev_slot0; q.pair0 = p.ph_pair0;
+    q.half = (p.win - 1) * 0.5f;
+    for (int l = 0; l < p.g.nlev; l++) {
+        const PhaseLevel &PL = p.pg.lv[l];
+        const int threads = (PL.pitch / 8) * ((PL.h + 3) / 4);
+        dim3 grid((threads + 255) / 256, PL.ncx * PL.ncx, pairs);
+        k_phase_planes<<<grid, 256, 0, s>>>(q, l);
+    }
+    MD_COUNT_LAUNCH(p.g.nlev);
+    constexpr int WARPS = 7;
+    const size_t smem = (size_t)WARPS * PhTile::WARP_BYTES + 128;
+    cudaError_t e = cudaFuncSetAttribute(k_lk_phase<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((p.P + WARPS - 1) / WARPS, pairs);
+    k_lk_phase<WARPS><<<grid, WARPS * 32, smem, s>>>(p, *maps);
+    MD_COUNT_LAUNCH(1);
+    return cudaGetLastError();
+}

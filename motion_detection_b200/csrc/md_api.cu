@@ -62,6 +62,58 @@ static int pyr_levels(int w, int h, int win, int max_level)
     return max_level;
 }
 
+// ---- sub-pixel phase planes of the tracked grid (k_lk_phase.cu) -----------------------------------------------------
+static void phase_geometry(md_ctx *ctx)
+{
+    PhaseGeom &pg = ctx->pg;
+    const int ps = ctx->cfg.pixel_step;
+    int tz = 0;
+    while (tz < 30 && !((ps >> tz) & 1)) tz++;
+    size_t off = 0, px = 0;
+    for (int l = 0; l < ctx->g.nlev; l++) {
+        PhaseLevel &PL = pg.lv[l];
+        PL.w = ctx->g.lv[l].w + 2 * MD_PH_MARGIN;
+        PL.h = ctx->g.lv[l].h + 2 * MD_PH_MARGIN;
+        PL.pitch = align_up(PL.w, 8);
+        PL.shift = tz < l ? tz : l;
+        PL.ncx = 1 << (l - PL.shift);
+        PL.off = off;
+        const size_t n = (size_t)PL.ncx * PL.ncx * PL.pitch * PL.h;
+        off += 3 * n; px += n;
+    }
+    pg.pair_elems = off;
+    pg.px_per_pair = px;
+    ctx->phase_state = 0;
+}
+
+// Allocates the phase-plane arenas and encodes their tensor maps on the first grid-mode LK call.  The planes pay off
+// when the per-point window builds they replace (P x levels x 1600 taps) outweigh the per-pixel evaluations.
+static bool ensure_phase(md_ctx *ctx)
+{
+    if (ctx->phase_state) return ctx->phase_state > 0;
+    ctx->phase_state = -1;
+    if (!ctx->lk_maps.valid || ctx->cfg.lk_win != 40) return false;
+    const PhaseGeom &pg = ctx->pg;
+    if ((double)ctx->P * ctx->g.nlev * 1600.0 < 4.0 * (double)pg.px_per_pair) return false;
+    const size_t bytes = pg.pair_elems * sizeof(int16_t) * ctx->cfg.max_batch;
+    if (bytes > ((size_t)24 << 30)) return false;
+    if (cudaMalloc((void **)&ctx->d_phase, bytes) != cudaSuccess) { cudaGetLastError(); ctx->d_phase = nullptr; return false; }
+    for (int l = 0; l < ctx->g.nlev; l++) {
+        const PhaseLevel &PL = pg.lv[l];
+        const uint64_t plane = (uint64_t)PL.pitch * PL.h * 2;
+        const uint64_t dims[5] = {(uint64_t)PL.pitch, (uint64_t)PL.h, 3, (uint64_t)PL.ncx * PL.ncx, (uint64_t)ctx->cfg.max_batch};
+        const uint64_t str[4] = {(uint64_t)PL.pitch * 2, plane, 3 * plane, (uint64_t)pg.pair_elems * 2};
+        if (!tma_encode_5d_u16(&ctx->ph_maps.ph[l], ctx->d_phase + PL.off, dims, str, MD_PH_BOX_W, 40, 3)) {
+            cudaFree(ctx->d_phase); ctx->d_phase = nullptr;
+            return false;
+        }
+        ctx->ph_maps.imgJ[l] = ctx->lk_maps.imgJ[l];
+    }
+    ctx->ph_maps.valid = 1;
+    ctx->phase_state = 1;
+    return true;
+}
+
 static void free_ctx(md_ctx *ctx)
 {
     if (!ctx) return;
@@ -69,7 +121,7 @@ static void free_ctx(md_ctx *ctx)
     void *ptrs[] = {ctx->d_img, ctx->d_der, ctx->d_frames, ctx->d_mask, ctx->d_pts_in, ctx->d_next, ctx->d_status, ctx->d_keep,
                     ctx->d_inlier_mask, ctx->d_blockcnt, ctx->d_kept_idx, ctx->d_M, ctx->d_hyp_valid, ctx->d_counts,
                     ctx->d_inliers, ctx->d_valid, ctx->d_hyp, ctx->d_partial, ctx->d_H, ctx->d_Hinv, ctx->d_stats,
-                    ctx->d_traj, ctx->d_traj_len};
+                    ctx->d_traj, ctx->d_traj_len, ctx->d_phase};
     for (void *p : ptrs) if (p) cudaFree(p);
     vf_free_workspace(ctx->vf_ws);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
@@ -188,6 +240,7 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
         if (!mok) { free_ctx(ctx); return MD_ERR_CUDA; }
         ctx->lk_maps.valid = 1;
     }
+    phase_geometry(ctx);
     ctx->stats.device = device;
     *out = ctx;
     return MD_OK;
@@ -337,9 +390,12 @@ extern "C" int md_pyramid_read_deriv(md_ctx *ctx, int slot, int level, int16_t *
 
 // ---- K2 ------------------------------------------------------------------------------------------------------------
 static void fill_lk(md_ctx *ctx, LkParams &p, int prev_slot0, int next_slot0, const float2 *pts_in, int P, float2 *next,
-                    uint8_t *status)
+                    uint8_t *status, int ph_pair0 = 0)
 {
     p.g = ctx->g;
+    p.pg = ctx->pg;
+    p.ph = (!pts_in && ensure_phase(ctx)) ? ctx->d_phase : nullptr;
+    p.ph_pair0 = ph_pair0;
     p.img = ctx->d_img; p.der = ctx->d_der;
     p.prev_slot0 = prev_slot0; p.next_slot0 = next_slot0;
     p.pts_in = pts_in;
@@ -372,7 +428,7 @@ extern "C" int md_lk_flow(md_ctx *ctx, int slot_prev, int slot_next, const float
     } else d_in = (const float2 *)pts_in;
     LkParams p;
     fill_lk(ctx, p, slot_prev, slot_next, d_in, npts, d_out, d_st);
-    CK(launch_lk(p, &ctx->lk_maps, 1, ctx->stream));
+    CK(launch_lk(p, &ctx->lk_maps, &ctx->ph_maps, 1, ctx->stream));
     if (mem == MD_MEM_HOST) {
         CK(cudaMemcpyAsync(pts_out, d_out, sizeof(float2) * npts, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(status, d_st, npts, cudaMemcpyDeviceToHost, ctx->stream));
@@ -504,8 +560,8 @@ static int run_pairs(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uin
         }
     } else {
         LkParams lp;
-        fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P);
-        CK(launch_lk(lp, &ctx->lk_maps, n, s));
+        fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P, p0);
+        CK(launch_lk(lp, &ctx->lk_maps, &ctx->ph_maps, n, s));
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], s));
     EgoParams ep;
@@ -689,8 +745,9 @@ extern "C" int md_track_trajectories(md_ctx *ctx, const md_frames *fr, float *tr
     const cudaMemcpyKind outk = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     for (int j = 0; j < F - 1; j++) {
         LkParams lp;
-        fill_lk(ctx, lp, j, j + 1, cur, P, ctx->d_next, ctx->d_status);
-        CK(launch_lk(lp, &ctx->lk_maps, 1, s));
+        // the first pair starts at the grid itself (cpp:161-165): phase-plane kernel; later pairs track arbitrary points
+        fill_lk(ctx, lp, j, j + 1, j == 0 ? nullptr : cur, P, ctx->d_next, ctx->d_status);
+        CK(launch_lk(lp, &ctx->lk_maps, &ctx->ph_maps, 1, s));
         if (j == F - 2) {
             if (last_prev) CK(cudaMemcpyAsync(last_prev, cur, sizeof(float2) * P, outk, s));
             if (last_next) CK(cudaMemcpyAsync(last_next, ctx->d_next, sizeof(float2) * P, outk, s));

@@ -47,6 +47,32 @@ struct alignas(64) LkTmaMaps {
     int valid;
 };
 
+// ---- sub-pixel phase planes (k_lk_phase.cu) -------------------------------------------------------------------------
+// Grid points sit at integer multiples of pixel_step, so at pyramid level l the fractional part of a point's window
+// origin takes only (2^l / gcd(ps, 2^l))^2 distinct values ("phase classes").  For every class the bilinearly
+// interpolated window samples (I with 5 extra bits, Ix, Iy: the values LKTrackerInvoker builds per point) are
+// computed ONCE per pixel into s16 planes; a point's 40x40 window is then a plain TMA box of its class's planes.
+// Plane pixel (X, Y) holds the samples of the window tap whose integer origin is (X - margin, Y - margin).
+#define MD_PH_MARGIN 24         // window origins of in-image grid points reach from -20 to w - 20
+#define MD_PH_BOX_W 48          // s16 elements: <= 7 alignment offset + 40 window columns, multiple of 8 (16 bytes)
+struct PhaseLevel {
+    int w, h;            // plane size: level size + 2 * margin
+    int pitch;           // s16 elements per row, multiple of 8
+    int ncx;             // classes per axis
+    int shift;           // log2 gcd(ps, 2^level): class = (coordinate & (2^level - 1)) >> shift
+    size_t off;          // s16 offset of (class 0, plane 0) inside a pair's arena; layout [class][I, Ix, Iy][row][pitch]
+};
+struct PhaseGeom {
+    PhaseLevel lv[MD_MAX_LEVELS];
+    size_t pair_elems;   // s16 per pair (all levels, classes, planes)
+    size_t px_per_pair;  // plane pixels per pair (work estimate)
+};
+struct alignas(64) LkPhaseMaps {
+    CUtensorMap imgJ[MD_MAX_LEVELS];   // u8, box 80 x 47 (same as LkTmaMaps::imgJ)
+    CUtensorMap ph[MD_MAX_LEVELS];     // s16, dims (x, y, plane, class, pair), box 48 x 40 x 3
+    int valid;
+};
+
 struct LkParams {
     PyrGeom g;
     const uint8_t *img;      // slot 0 image arena
@@ -60,6 +86,10 @@ struct LkParams {
     int win, max_iters;
     double eps2;
     float min_eig;
+    // grid mode with phase planes (pts_in == nullptr): pair b uses arena ph + b * pg.pair_elems
+    PhaseGeom pg;
+    int16_t *ph;
+    int ph_pair0;            // pair b of this launch uses arena ph_pair0 + b
 };
 
 struct EgoParams {
@@ -146,6 +176,10 @@ struct md_ctx {
     int profile;
     cudaEvent_t ev[5];
     LkTmaMaps lk_maps;
+    LkPhaseMaps ph_maps;
+    PhaseGeom pg;
+    int16_t *d_phase;     // [max_batch] pair arenas of phase planes, allocated on the first grid-mode LK call
+    int phase_state;      // 0 = not tried, 1 = ready, -1 = not used (not worth it / allocation failed)
     void *vf_ws;          // VarFlow workspace (k_varflow.cu), allocated on the first md_varflow call
 };
 
@@ -160,9 +194,10 @@ extern long long g_md_launches;   // kernels launched by this library (process w
 cudaError_t launch_gray(const uint8_t *src3, int src_pitch, int w, int h, uint8_t *dst, int dst_pitch, cudaStream_t s);
 cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot0, int nframes, const uint8_t *frames,
                            int channels, int fpitch, long long fstride, cudaStream_t s);
-cudaError_t launch_lk(const LkParams &p, const LkTmaMaps *maps, int pairs, cudaStream_t s);
+cudaError_t launch_lk(const LkParams &p, const LkTmaMaps *maps, const LkPhaseMaps *pmaps, int pairs, cudaStream_t s);
 cudaError_t launch_ego(const EgoParams &p, int pairs, cudaStream_t s);
 cudaError_t launch_mask(const MaskParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pairs, cudaStream_t s);
 cudaError_t launch_traj_step(float2 *pts_cur, const float2 *next, const uint8_t *status, float2 *traj, int32_t *len,
                              int P, int F, int w, int h, cudaStream_t s);
 cudaError_t launch_traj_init(float2 *pts_cur, float2 *traj, int32_t *len, int P, int F, int ps, int gy, cudaStream_t s);

@@ -28,6 +28,29 @@ static inline bool tma_encode_3d(CUtensorMap *map, int elem_bytes, void *base, u
               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- host: 5-D tiled tensor map of 16-bit elements (x fastest); box = (box0, box1, box2, 1, 1) ---------------------------
+static inline bool tma_encode_5d_u16(CUtensorMap *map, void *base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                                     uint32_t box0, uint32_t box1, uint32_t box2)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return false;
+        fn = (encode_fn)p;
+    }
+    cuuint64_t gdim[5], gstr[4];
+    for (int i = 0; i < 5; i++) gdim[i] = dims[i];
+    for (int i = 0; i < 4; i++) gstr[i] = strides_bytes[i];
+    cuuint32_t box[5] = {box0, box1, box2, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 5, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 #ifdef __CUDACC__
 // ---- device ----------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -59,6 +82,12 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
 {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar)) : "memory");
+}
+// 5-D tile load (x, y, plane, class, pair)
+__device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
 {

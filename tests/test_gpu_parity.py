@@ -85,6 +85,25 @@ def test_lk_flow_explicit_points_and_borders(capi, oracle, seq640):
     assert np.linalg.norm(nxt[ok] - ref[ok], axis=1).mean() < FLOW_EPE_TOL
 
 
+@pytest.mark.parametrize("size,ps", [((640, 480), 10), ((640, 480), 7), ((640, 480), 8), ((333, 211), 3), ((1920, 1080), 10),
+                                     ((320, 240), 1), ((640, 480), 4), ((97, 131), 2)])
+def test_lk_grid_phase_planes_bit_identical_to_point_kernel(capi, size, ps):
+    """Grid mode (pts = NULL) runs k_lk_phase on precomputed sub-pixel phase planes; handing the SAME grid in as explicit
+    points runs the per-point window build of k_lk_tma.  Both are the same integer arithmetic: results must be identical
+    to the last bit, for every phase-class layout (even / odd / power-of-two pixel_step, dense)."""
+    w, h = size
+    frames, _ = synth.sequence(w, h, 2, seed=99 + ps)
+    ctx = _ctx(capi, w, h, max_batch=1, pixel_step=ps)
+    ctx.pyramid(frames[0], 0)
+    ctx.pyramid(frames[1], 1)
+    pts = ctx.grid_points()
+    a, sa = ctx.lk_flow(0, 1)
+    b, sb = ctx.lk_flow(0, 1, pts)
+    assert np.array_equal(sa, sb)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), np.abs(a - b).max()
+    assert sa.mean() > 0.5
+
+
 def test_lk_flow_vs_cv2_direct(capi, seq640):
     cvref = pytest.importorskip("cvref")
     if not cvref.have_cv2():
