@@ -167,6 +167,60 @@ int md_process_pair(md_ctx *ctx, const uint8_t *prev, const uint8_t *cur, int32_
 int md_track_trajectories(md_ctx *ctx, const md_frames *frames, float *traj, int32_t *traj_len, float *last_prev,
                           float *last_next, uint8_t *last_status, int mem);
 
+/* ---- the node's LIVE path: MotionDetectionNode::imageCallback (ros/src/motion_detection_node.cpp:235-430) --------- */
+/* The node keeps the last F = 2 * num_motions + 1 frames in a deque (node.cpp:248-261), re-tracks the grid through them on
+ * every callback (runOpticalFlowTrajectory -> calculateOpticalFlowTrajectory, cpp:133-257), fits the motion subspace
+ * (od_.fitSubspace, node.cpp:348), groups the outlier points (fc_.clusterEuclidean, node.cpp:355 /
+ * common/src/flow_clusterer.cpp:227-269) and boxes every group of more than 5 points (ofv_.showBoundingBoxes, node.cpp:395 /
+ * common/src/optical_flow_visualizer.cpp:223-240); ml_.writeBoundingBox logs "frame, id, x0, y0, x1, y1"
+ * (common/src/motion_logger.cpp:43-47).  Here the deque is a ring of pyramid slots: every frame is converted and its
+ * pyramid built ONCE (the reference rebuilds F-1 pyramids per callback), the rest runs on the device. */
+typedef struct md_live_params {
+    int32_t num_motions;        /* ROS param num_motions (node.cpp:239), F = 2 * num_motions + 1 frames */
+    double  sigma;              /* ROS param sigma (node.cpp:346), default 0.5 */
+    double  distance_threshold; /* ROS param distance_threshold (node.cpp:317), launch files: 50 */
+    uint32_t seed;              /* srand() seed of fitSubspace's rand() % T draws */
+    int32_t subspace_iters;     /* 50 (outlier_detector.cpp:250) */
+    int32_t min_cluster_size;   /* clusters with MORE than this many points are reported: 5 (flow_clusterer.cpp:264) */
+    int32_t reserved[4];
+} md_live_params;
+
+typedef struct md_live_result {
+    /* counts: always written (host memory) */
+    int32_t num_trajectories;   /* complete trajectories T (cpp:244-254); 0 = "no trajectories found" (node.cpp:298) */
+    int32_t subspace_inliers;   /* inliers of the winning subspace hypothesis */
+    int32_t num_outliers;       /* outlier_points.size() (outlier_detector.cpp:318-324) */
+    int32_t num_clusters_all;   /* clusters founded by clusterEuclidean, any size */
+    int32_t num_clusters;       /* clusters with more than min_cluster_size points = rectangles */
+    int32_t reserved[3];
+    /* arrays: each may be NULL; capacity md_grid_size() entries; memory space = `mem` of the call */
+    float   *traj;              /* [T][F][2] complete trajectories in grid order */
+    int32_t *traj_index;        /* [T] grid index of each */
+    float   *residual;          /* [T] */
+    uint8_t *outlier;           /* [T] */
+    int32_t *best_cols;         /* [4 * num_motions] trajectories spanning the winning subspace (return value of fitSubspace) */
+    float   *outlier_points;    /* [num_outliers][2] */
+    int32_t *labels;            /* [num_outliers] cluster id (creation order, any size) of every outlier point */
+    int32_t *boxes;             /* [num_clusters][4] tl.x, tl.y, br.x, br.y of cv::boundingRect (the CSV columns) */
+    int32_t *cluster_sizes;     /* [num_clusters] */
+    int32_t *cluster_ids;       /* [num_clusters] id (as in labels) of every reported cluster */
+} md_live_result;
+
+int md_live_params_default(md_live_params *p);
+/* Forgets the frames pushed so far. */
+int md_window_reset(md_ctx *ctx);
+/* raw_images_.push_back(image) (+ pop_front when full): converts (channels 3: cv::cvtColor(CV_BGR2GRAY) on the rgb8 data,
+ * cpp:166-167) and builds the pyramid of ONE frame into the next ring slot.  *fill = frames held (<= max_batch + 1). */
+int md_window_push(md_ctx *ctx, const uint8_t *frame, int32_t channels, int32_t pitch, int32_t *fill, int mem);
+/* Runs the callback body over the newest F frames (needs F <= frames held).  Returns after the results are complete. */
+int md_window_detect(md_ctx *ctx, const md_live_params *params, md_live_result *res, int mem);
+
+/* ---- FlowClusterer::clusterEuclidean + showBoundingBoxes on a caller-supplied point list ----------------------------- */
+/* pts [n][2]; labels [n]; boxes [n][4] / sizes [n] / ids [n] capacity n; counts are host memory. */
+int md_cluster_points(md_ctx *ctx, const float *pts, int32_t n, double distance_threshold, int32_t min_cluster_size,
+                      int32_t *labels, int32_t *num_clusters_all, int32_t *num_clusters, int32_t *boxes, int32_t *sizes,
+                      int32_t *ids, int mem);
+
 /* ---- OutlierDetector::fitSubspace (common/src/outlier_detector.cpp:236-331) ------------------------------------ */
 /* traj [T][F][2]; forced_cols NULL (rand() % T after srand(seed)) or [iters][4*num_motions] host indices.
  * residual[T] f32, best_cols[4*num_motions] i32, outlier[T] u8 (residual > threshold, :318-324). */

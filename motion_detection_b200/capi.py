@@ -24,7 +24,8 @@ SYMBOLS = [
     "md_grid_size", "md_grid_points", "md_pyramid_levels", "md_pyramid_level_size", "md_gray_u8", "md_pyramid_u8",
     "md_pyramid_read", "md_pyramid_read_deriv", "md_lk_flow", "md_fit_egomotion", "md_motion_mask",
     "md_process_batch", "md_process_pair", "md_track_trajectories", "md_fit_subspace", "md_varflow", "md_stats_get",
-    "md_stats_reset", "md_profile", "md_profile_read",
+    "md_stats_reset", "md_profile", "md_profile_read", "md_live_params_default", "md_window_reset", "md_window_push",
+    "md_window_detect", "md_cluster_points",
 ]
 
 
@@ -56,6 +57,19 @@ class MdOutputs(C.Structure):
 class MdStats(C.Structure):
     _fields_ = [("pairs", C.c_int64), ("mask_pixels", C.c_int64), ("tracked", C.c_int64), ("inliers", C.c_int64),
                 ("last_H", C.c_double * 9), ("kernel_launches", C.c_int64), ("device", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+class MdLiveParams(C.Structure):
+    _fields_ = [("num_motions", C.c_int32), ("sigma", C.c_double), ("distance_threshold", C.c_double), ("seed", C.c_uint32),
+                ("subspace_iters", C.c_int32), ("min_cluster_size", C.c_int32), ("reserved", C.c_int32 * 4)]
+
+
+class MdLiveResult(C.Structure):
+    _fields_ = [("num_trajectories", C.c_int32), ("subspace_inliers", C.c_int32), ("num_outliers", C.c_int32),
+                ("num_clusters_all", C.c_int32), ("num_clusters", C.c_int32), ("reserved", C.c_int32 * 3),
+                ("traj", C.c_void_p), ("traj_index", C.c_void_p), ("residual", C.c_void_p), ("outlier", C.c_void_p),
+                ("best_cols", C.c_void_p), ("outlier_points", C.c_void_p), ("labels", C.c_void_p), ("boxes", C.c_void_p),
+                ("cluster_sizes", C.c_void_p), ("cluster_ids", C.c_void_p)]
 
 
 class MotionB200Error(RuntimeError):
@@ -262,6 +276,51 @@ class Context:
         self._ck(lib().md_fit_subspace(self._h, _ptr(traj), T, F, num_motions, C.c_double(sigma), C.c_uint32(seed), fc, iters,
                                        _ptr(res), _ptr(cols), _ptr(outl), C.byref(ninl), MD_MEM_HOST))
         return dict(inliers=ninl.value, residual=res, best_cols=cols, outlier=outl)
+
+    # ---- the node's live path (imageCallback): ring of the last F frames ----------------------------------------
+    def window_reset(self):
+        self._ck(lib().md_window_reset(self._h))
+
+    def window_push(self, frame):
+        frame = np.ascontiguousarray(frame, np.uint8)
+        ch = 3 if frame.ndim == 3 else 1
+        fill = C.c_int32()
+        self._ck(lib().md_window_push(self._h, _ptr(frame), ch, self.w * ch, C.byref(fill), MD_MEM_HOST))
+        return fill.value
+
+    def window_detect(self, num_motions=2, sigma=0.5, distance_threshold=50.0, seed=1, iters=50, min_cluster_size=5):
+        lp = MdLiveParams()
+        lib().md_live_params_default(C.byref(lp))
+        lp.num_motions, lp.sigma, lp.distance_threshold, lp.seed = num_motions, sigma, distance_threshold, seed
+        lp.subspace_iters, lp.min_cluster_size = iters, min_cluster_size
+        F, P = 2 * num_motions + 1, self.P
+        a = dict(traj=np.zeros((P, F, 2), np.float32), traj_index=np.zeros(P, np.int32), residual=np.zeros(P, np.float32),
+                 outlier=np.zeros(P, np.uint8), best_cols=np.zeros(4 * num_motions, np.int32),
+                 outlier_points=np.zeros((P, 2), np.float32), labels=np.zeros(P, np.int32), boxes=np.zeros((P, 4), np.int32),
+                 cluster_sizes=np.zeros(P, np.int32), cluster_ids=np.zeros(P, np.int32))
+        r = MdLiveResult()
+        for k, v in a.items():
+            setattr(r, k, v.ctypes.data)
+        self._ck(lib().md_window_detect(self._h, C.byref(lp), C.byref(r), MD_MEM_HOST))
+        T, no, K = r.num_trajectories, r.num_outliers, r.num_clusters
+        out = dict(num_trajectories=T, subspace_inliers=r.subspace_inliers, num_outliers=no, num_clusters_all=r.num_clusters_all,
+                   num_clusters=K)
+        out.update(traj=a["traj"][:T], traj_index=a["traj_index"][:T], residual=a["residual"][:T], outlier=a["outlier"][:T],
+                   best_cols=a["best_cols"], outlier_points=a["outlier_points"][:no], labels=a["labels"][:no],
+                   boxes=a["boxes"][:K], cluster_sizes=a["cluster_sizes"][:K], cluster_ids=a["cluster_ids"][:K])
+        return out
+
+    def cluster_points(self, pts, distance_threshold=50.0, min_cluster_size=5):
+        pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+        n = len(pts)
+        labels = np.zeros(max(n, 1), np.int32)
+        boxes = np.zeros((max(n, 1), 4), np.int32)
+        sizes = np.zeros(max(n, 1), np.int32)
+        ids = np.zeros(max(n, 1), np.int32)
+        nall, k = C.c_int32(), C.c_int32()
+        self._ck(lib().md_cluster_points(self._h, _ptr(pts), n, C.c_double(distance_threshold), min_cluster_size, _ptr(labels),
+                                         C.byref(nall), C.byref(k), _ptr(boxes), _ptr(sizes), _ptr(ids), MD_MEM_HOST))
+        return labels[:n], nall.value, boxes[:k.value], sizes[:k.value], ids[:k.value]
 
     def varflow(self, A, B):
         A = np.ascontiguousarray(A, np.uint8)

@@ -221,13 +221,87 @@ __global__ void __launch_bounds__(256) k_sub_final(const SubParams p)
     }
 }
 
+// ---- persistent workspace (grown on demand; freed with the context) ---------------------------------------------------
+struct SubWs {
+    double *mean = nullptr, *P = nullptr;
+    int *cols = nullptr, *counts = nullptr, *forced = nullptr, *best = nullptr, *ninl = nullptr;
+    float *traj = nullptr, *res = nullptr;
+    uint8_t *out = nullptr;
+    size_t capP = 0, capCols = 0, capIters = 0, capForced = 0, capTraj = 0, capT = 0, capOut = 0;
+};
+
+void sub_free_workspace(void *w)
+{
+    SubWs *ws = (SubWs *)w;
+    if (!ws) return;
+    void *ptrs[] = {ws->mean, ws->P, ws->cols, ws->counts, ws->forced, ws->best, ws->ninl, ws->traj, ws->res, ws->out};
+    for (void *q : ptrs) if (q) cudaFree(q);
+    delete ws;
+}
+
+template <class T>
+static bool sub_grow(T **ptr, size_t *cap, size_t need, cudaStream_t s)
+{
+    if (*cap >= need) return true;
+    cudaStreamSynchronize(s);
+    if (*ptr) cudaFree(*ptr);
+    *ptr = nullptr; *cap = 0;
+    if (cudaMalloc((void **)ptr, need * sizeof(T)) != cudaSuccess) { cudaGetLastError(); return false; }
+    *cap = need;
+    return true;
+}
+
+// Enqueues the whole fit on the context's stream; every pointer is device memory except forced_host.
+int sub_enqueue(md_ctx *ctx, const float *d_traj, int T, int F, int num_motions, double sigma, uint32_t seed,
+                const int32_t *forced_host, int iters, float *d_res, uint8_t *d_out, int *d_best, int *d_ninl)
+{
+    const int n = 2 * F, d = 4 * num_motions;
+    if (!d_traj || !d_res || !d_best || !d_out || T < 1 || F < 1 || n > SUB_MAXN || d < 1 || d > SUB_MAXN || d > n || iters < 1 ||
+        iters > 4096) {
+        ctx->err = "md_fit_subspace: bad arguments (need 2F <= 32, 4*num_motions <= 2F)";
+        return MD_ERR_INVALID;
+    }
+    cudaStream_t s = ctx->stream;
+    if (!ctx->sub_ws) ctx->sub_ws = new SubWs();
+    SubWs *ws = (SubWs *)ctx->sub_ws;
+    size_t two = ws->mean ? 2 : 0, one = ws->ninl ? 1 : 0;
+    bool ok = sub_grow(&ws->mean, &two, 2, s) && sub_grow(&ws->P, &ws->capP, (size_t)iters * n * n, s) &&
+              sub_grow(&ws->cols, &ws->capCols, (size_t)iters * d, s) && sub_grow(&ws->counts, &ws->capIters, (size_t)iters, s) &&
+              sub_grow(&ws->ninl, &one, 1, s);
+    if (ok && forced_host) ok = sub_grow(&ws->forced, &ws->capForced, (size_t)iters * d, s);
+    if (!ok) { ctx->err = "md_fit_subspace: out of device memory"; return MD_ERR_NOMEM; }
+    cudaError_t e = cudaSuccess;
+    if (forced_host) e = cudaMemcpyAsync(ws->forced, forced_host, sizeof(int) * iters * d, cudaMemcpyHostToDevice, s);
+    SubParams p;
+    p.traj = d_traj;
+    p.T = T; p.F = F; p.n = n; p.d = d; p.iters = iters; p.sigma = sigma; p.seed = seed;
+    p.forced_cols = forced_host ? ws->forced : nullptr; p.mean = ws->mean; p.P = ws->P; p.cols = ws->cols; p.counts = ws->counts;
+    p.residual = d_res; p.outlier = d_out; p.best_cols = d_best; p.num_inliers = d_ninl ? d_ninl : ws->ninl;
+    k_sub_mean<<<1, 1024, 0, s>>>(p);
+    const size_t cols_smem = sizeof(int) * iters * d;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sub_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem);
+    k_sub_hyp<<<1, 64, cols_smem, s>>>(p);
+    int hb = (int)(96 * 1024 / (sizeof(double) * n * n));
+    if (hb > iters) hb = iters;
+    if (hb < 1) hb = 1;
+    const size_t psm = sizeof(double) * (size_t)hb * n * n;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sub_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+    int nb = (T + 255) / 256;
+    if (nb > 592) nb = 592;
+    k_sub_score<<<nb, 256, psm, s>>>(p, hb);
+    k_sub_final<<<nb, 256, sizeof(double) * n * n, s>>>(p);
+    MD_COUNT_LAUNCH(4);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { ctx->err = std::string("md_fit_subspace: ") + cudaGetErrorString(e); return MD_ERR_CUDA; }
+    return MD_OK;
+}
+
 #define SCK(call)                                                                                               \
     do {                                                                                                        \
         cudaError_t e_ = (call);                                                                                \
         if (e_ != cudaSuccess) {                                                                                \
             ctx->err = std::string("md_fit_subspace: ") + #call + " -> " + cudaGetErrorString(e_);             \
-            rc = MD_ERR_CUDA;                                                                                   \
-            goto done;                                                                                          \
+            return MD_ERR_CUDA;                                                                                 \
         }                                                                                                       \
     } while (0)
 
@@ -244,58 +318,26 @@ extern "C" int md_fit_subspace(md_ctx *ctx, const float *traj, int32_t T, int32_
     }
     if (cudaSetDevice(ctx->device) != cudaSuccess) return MD_ERR_CUDA;
     cudaStream_t s = ctx->stream;
-    int rc = MD_OK;
-    const bool host = mem == MD_MEM_HOST;
-    float *d_traj = nullptr, *d_res = nullptr;
-    int *d_forced = nullptr, *d_cols = nullptr, *d_counts = nullptr, *d_best = nullptr, *d_ninl = nullptr;
-    double *d_mean = nullptr, *d_P = nullptr;
-    uint8_t *d_out = nullptr;
-    SubParams p;
-    {
-        const size_t tb = sizeof(float) * 2 * (size_t)T * F;
-        if (host) { SCK(cudaMalloc((void **)&d_traj, tb)); SCK(cudaMemcpyAsync(d_traj, traj, tb, cudaMemcpyHostToDevice, s)); }
-        if (forced_cols) {
-            SCK(cudaMalloc((void **)&d_forced, sizeof(int) * iters * d));
-            SCK(cudaMemcpyAsync(d_forced, forced_cols, sizeof(int) * iters * d, cudaMemcpyHostToDevice, s));
-        }
-        SCK(cudaMalloc((void **)&d_mean, 2 * sizeof(double)));
-        SCK(cudaMalloc((void **)&d_P, sizeof(double) * (size_t)iters * n * n));
-        SCK(cudaMalloc((void **)&d_cols, sizeof(int) * iters * d));
-        SCK(cudaMalloc((void **)&d_counts, sizeof(int) * iters));
-        SCK(cudaMalloc((void **)&d_best, sizeof(int) * d));
-        SCK(cudaMalloc((void **)&d_ninl, sizeof(int)));
-        if (host) { SCK(cudaMalloc((void **)&d_res, sizeof(float) * T)); SCK(cudaMalloc((void **)&d_out, T)); }
-        p.traj = host ? d_traj : traj;
-        p.T = T; p.F = F; p.n = n; p.d = d; p.iters = iters; p.sigma = sigma; p.seed = seed;
-        p.forced_cols = d_forced; p.mean = d_mean; p.P = d_P; p.cols = d_cols; p.counts = d_counts;
-        p.residual = host ? d_res : residual; p.outlier = host ? d_out : outlier;
-        p.best_cols = d_best; p.num_inliers = d_ninl;
-        k_sub_mean<<<1, 1024, 0, s>>>(p);
-        const size_t cols_smem = sizeof(int) * iters * d;
-        SCK(cudaFuncSetAttribute(k_sub_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem));
-        k_sub_hyp<<<1, 64, cols_smem, s>>>(p);
-        int hb = (int)(96 * 1024 / (sizeof(double) * n * n));
-        if (hb > iters) hb = iters;
-        if (hb < 1) hb = 1;
-        const size_t psm = sizeof(double) * (size_t)hb * n * n;
-        SCK(cudaFuncSetAttribute(k_sub_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
-        int nb = (T + 255) / 256;
-        if (nb > 592) nb = 592;
-        k_sub_score<<<nb, 256, psm, s>>>(p, hb);
-        k_sub_final<<<nb, 256, sizeof(double) * n * n, s>>>(p);
-        MD_COUNT_LAUNCH(4);
-        SCK(cudaGetLastError());
-        const cudaMemcpyKind k = host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-        if (host) {
-            SCK(cudaMemcpyAsync(residual, d_res, sizeof(float) * T, k, s));
-            SCK(cudaMemcpyAsync(outlier, d_out, T, k, s));
-        }
-        SCK(cudaMemcpyAsync(best_cols, d_best, sizeof(int) * d, k, s));
-        if (num_inliers) SCK(cudaMemcpyAsync(num_inliers, d_ninl, sizeof(int), k, s));
-        SCK(cudaStreamSynchronize(s));     // temporaries are freed below
+    if (!ctx->sub_ws) ctx->sub_ws = new SubWs();
+    SubWs *ws = (SubWs *)ctx->sub_ws;
+    size_t capBest = ws->best ? SUB_MAXN : 0;
+    if (!sub_grow(&ws->best, &capBest, SUB_MAXN, s)) { ctx->err = "md_fit_subspace: out of device memory"; return MD_ERR_NOMEM; }
+    if (mem == MD_MEM_DEVICE) {
+        // stream ordered; best_cols / num_inliers are device pointers too
+        return sub_enqueue(ctx, traj, T, F, num_motions, sigma, seed, forced_cols, iters, residual, outlier, best_cols, num_inliers);
     }
-done:
-    cudaFree(d_traj); cudaFree(d_forced); cudaFree(d_mean); cudaFree(d_P); cudaFree(d_cols); cudaFree(d_counts);
-    cudaFree(d_best); cudaFree(d_ninl); cudaFree(d_res); cudaFree(d_out);
-    return rc;
+    const size_t tb = (size_t)2 * T * F;
+    if (!sub_grow(&ws->traj, &ws->capTraj, tb, s) || !sub_grow(&ws->res, &ws->capT, (size_t)T, s) || !sub_grow(&ws->out, &ws->capOut, (size_t)T, s)) {
+        ctx->err = "md_fit_subspace: out of device memory";
+        return MD_ERR_NOMEM;
+    }
+    SCK(cudaMemcpyAsync(ws->traj, traj, tb * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = sub_enqueue(ctx, ws->traj, T, F, num_motions, sigma, seed, forced_cols, iters, ws->res, ws->out, ws->best, nullptr);
+    if (rc != MD_OK) return rc;
+    SCK(cudaMemcpyAsync(residual, ws->res, sizeof(float) * T, cudaMemcpyDeviceToHost, s));
+    SCK(cudaMemcpyAsync(outlier, ws->out, T, cudaMemcpyDeviceToHost, s));
+    SCK(cudaMemcpyAsync(best_cols, ws->best, sizeof(int) * d, cudaMemcpyDeviceToHost, s));
+    if (num_inliers) SCK(cudaMemcpyAsync(num_inliers, ws->ninl, sizeof(int), cudaMemcpyDeviceToHost, s));
+    SCK(cudaStreamSynchronize(s));
+    return MD_OK;
 }

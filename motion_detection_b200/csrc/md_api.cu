@@ -62,6 +62,28 @@ static int pyr_levels(int w, int h, int win, int max_level)
     return max_level;
 }
 
+// ---- live-path workspace ------------------------------------------------------------------------------------------------
+struct LiveWs {
+    int *ints = nullptr;          // one arena, see live_ensure
+    float *floats = nullptr;
+    uint8_t *bytes = nullptr;
+    int cap = 0, capF = 0;        // capacity in points / frames
+    int *blockcnt, *idx, *total, *oidx, *ototal, *cand, *ncand, *label, *nclusters, *sizes, *box, *nout, *out_box, *out_size,
+        *out_id, *best, *ninl, *n_dev;
+    float *traj_c, *opts, *m2, *res;
+    uint8_t *outl;
+};
+
+static void live_free(void *w)
+{
+    LiveWs *ws = (LiveWs *)w;
+    if (!ws) return;
+    if (ws->ints) cudaFree(ws->ints);
+    if (ws->floats) cudaFree(ws->floats);
+    if (ws->bytes) cudaFree(ws->bytes);
+    delete ws;
+}
+
 // ---- sub-pixel phase planes of the tracked grid (k_lk_phase.cu) -----------------------------------------------------
 static void phase_geometry(md_ctx *ctx)
 {
@@ -124,6 +146,8 @@ static void free_ctx(md_ctx *ctx)
                     ctx->d_traj, ctx->d_traj_len, ctx->d_phase};
     for (void *p : ptrs) if (p) cudaFree(p);
     vf_free_workspace(ctx->vf_ws);
+    sub_free_workspace(ctx->sub_ws);
+    live_free(ctx->live_ws);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 8; i++) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]); }
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -694,6 +718,7 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
     }
     ctx->slot_base = (prev0 + pairs) % ns;
     ctx->have_cached = 1;
+    ctx->win_fill = 0;               // the ring now belongs to the batch API
     ctx->pair_counter += pairs;
     ctx->stats.pairs += pairs;
     return MD_OK;
@@ -713,6 +738,43 @@ extern "C" int md_process_pair(md_ctx *ctx, const uint8_t *prev, const uint8_t *
 }
 
 // ---- trajectories ----------------------------------------------------------------------------------------------------
+// The tracking loop of calculateOpticalFlowTrajectory (cpp:161-241) over F frames whose pyramids sit in the ring slots
+// slot0, slot0+1, ... (mod nslots).  d_traj [P][F], d_len [P] are device memory.
+static int track_window(md_ctx *ctx, int slot0, int F, float2 *d_traj, int32_t *d_len, float *last_prev, float *last_next,
+                        uint8_t *last_status, bool dev, cudaStream_t s)
+{
+    const int P = ctx->P, ns = ctx->g.nslots;
+    float2 *cur = ctx->d_pts_in;
+    CK(launch_traj_init(cur, d_traj, d_len, P, F, ctx->cfg.pixel_step, ctx->gy, s));
+    const cudaMemcpyKind outk = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    for (int j = 0; j < F - 1; j++) {
+        LkParams lp;
+        // the first pair starts at the grid itself (cpp:148-159): phase-plane kernel; later pairs track arbitrary points
+        fill_lk(ctx, lp, (slot0 + j) % ns, (slot0 + j + 1) % ns, j == 0 ? nullptr : cur, P, ctx->d_next, ctx->d_status);
+        CK(launch_lk(lp, &ctx->lk_maps, &ctx->ph_maps, 1, s));
+        if (j == F - 2) {
+            if (last_prev) CK(cudaMemcpyAsync(last_prev, cur, sizeof(float2) * P, outk, s));
+            if (last_next) CK(cudaMemcpyAsync(last_next, ctx->d_next, sizeof(float2) * P, outk, s));
+            if (last_status) CK(cudaMemcpyAsync(last_status, ctx->d_status, P, outk, s));
+        }
+        CK(launch_traj_step(cur, ctx->d_next, ctx->d_status, d_traj, d_len, P, F, ctx->cfg.width, ctx->cfg.height, s));
+    }
+    return MD_OK;
+}
+
+static int ensure_traj(md_ctx *ctx, int F)
+{
+    if (ctx->d_traj && ctx->traj_F >= F) return MD_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_traj) cudaFree(ctx->d_traj);
+    if (ctx->d_traj_len) cudaFree(ctx->d_traj_len);
+    ctx->d_traj = nullptr; ctx->d_traj_len = nullptr; ctx->traj_F = 0;
+    CK(cudaMalloc((void **)&ctx->d_traj, sizeof(float2) * ctx->P * F));
+    CK(cudaMalloc((void **)&ctx->d_traj_len, sizeof(int32_t) * ctx->P));
+    ctx->traj_F = F;
+    return MD_OK;
+}
+
 extern "C" int md_track_trajectories(md_ctx *ctx, const md_frames *fr, float *traj, int32_t *traj_len, float *last_prev,
                                      float *last_next, uint8_t *last_status, int mem)
 {
@@ -723,43 +785,194 @@ extern "C" int md_track_trajectories(md_ctx *ctx, const md_frames *fr, float *tr
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int P = ctx->P, F = fr->count;
-    if (!ctx->d_traj || ctx->traj_F < F) {
-        CK(cudaStreamSynchronize(s));
-        if (ctx->d_traj) cudaFree(ctx->d_traj);
-        if (ctx->d_traj_len) cudaFree(ctx->d_traj_len);
-        ctx->d_traj = nullptr; ctx->d_traj_len = nullptr;
-        CK(cudaMalloc((void **)&ctx->d_traj, sizeof(float2) * P * F));
-        CK(cudaMalloc((void **)&ctx->d_traj_len, sizeof(int32_t) * P));
-        ctx->traj_F = F;
-    }
+    { int ra = ensure_traj(ctx, F); if (ra != MD_OK) return ra; }
     const uint8_t *df; int dp; long long ds;
     int r = stage_frames(ctx, fr->data, fr->channels, fr->pitch, fr->frame_stride, F, mem, &df, &dp, &ds);
     if (r != MD_OK) return r;
     CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, 0, F, df, fr->channels, dp, ds, s));
-    ctx->slot_base = 0; ctx->have_cached = 0;
+    ctx->slot_base = 0; ctx->have_cached = 0; ctx->win_fill = 0;
     const bool dev = mem == MD_MEM_DEVICE;
     float2 *d_traj = dev ? (float2 *)traj : ctx->d_traj;
     int32_t *d_len = dev ? traj_len : ctx->d_traj_len;
-    float2 *cur = ctx->d_pts_in;
-    CK(launch_traj_init(cur, d_traj, d_len, P, F, ctx->cfg.pixel_step, ctx->gy, s));
-    const cudaMemcpyKind outk = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-    for (int j = 0; j < F - 1; j++) {
-        LkParams lp;
-        // the first pair starts at the grid itself (cpp:161-165): phase-plane kernel; later pairs track arbitrary points
-        fill_lk(ctx, lp, j, j + 1, j == 0 ? nullptr : cur, P, ctx->d_next, ctx->d_status);
-        CK(launch_lk(lp, &ctx->lk_maps, &ctx->ph_maps, 1, s));
-        if (j == F - 2) {
-            if (last_prev) CK(cudaMemcpyAsync(last_prev, cur, sizeof(float2) * P, outk, s));
-            if (last_next) CK(cudaMemcpyAsync(last_next, ctx->d_next, sizeof(float2) * P, outk, s));
-            if (last_status) CK(cudaMemcpyAsync(last_status, ctx->d_status, P, outk, s));
-        }
-        CK(launch_traj_step(cur, ctx->d_next, ctx->d_status, d_traj, d_len, P, F, ctx->cfg.width, ctx->cfg.height, s));
-    }
+    r = track_window(ctx, 0, F, d_traj, d_len, last_prev, last_next, last_status, dev, s);
+    if (r != MD_OK) return r;
     if (!dev) {
         CK(cudaMemcpyAsync(traj, d_traj, sizeof(float2) * P * F, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(traj_len, d_len, sizeof(int32_t) * P, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     }
+    return MD_OK;
+}
+
+// ---- the live path (imageCallback) -------------------------------------------------------------------------------------
+static int live_ensure(md_ctx *ctx, int npts, int F)
+{
+    if (!ctx->live_ws) ctx->live_ws = new (std::nothrow) LiveWs();
+    LiveWs *ws = (LiveWs *)ctx->live_ws;
+    if (!ws) FAIL(MD_ERR_NOMEM, "live path: out of host memory");
+    if (ws->cap < npts || ws->capF < F) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ws->ints) cudaFree(ws->ints);
+        if (ws->floats) cudaFree(ws->floats);
+        if (ws->bytes) cudaFree(ws->bytes);
+        ws->ints = nullptr; ws->floats = nullptr; ws->bytes = nullptr; ws->cap = 0; ws->capF = 0;
+        const size_t n = (size_t)npts, nblk = (n + 2047) / 2048 + 1;
+        const size_t ni = nblk + n * 2 + 8 * n + n * 3 + 4 * n + 4 * n + 2 * n + 64 + 16;
+        CK(cudaMalloc((void **)&ws->ints, ni * sizeof(int)));
+        CK(cudaMalloc((void **)&ws->floats, (n * F * 2 + 2 * n + n + n) * sizeof(float)));
+        CK(cudaMalloc((void **)&ws->bytes, n));
+        int *q = ws->ints;
+        ws->cand = q; q += 8 * n;                      // 32-byte aligned rows first
+        ws->blockcnt = q; q += nblk;
+        ws->idx = q; q += n; ws->oidx = q; q += n; ws->ncand = q; q += n; ws->label = q; q += n; ws->sizes = q; q += n;
+        ws->box = q; q += 4 * n; ws->out_box = q; q += 4 * n; ws->out_size = q; q += n; ws->out_id = q; q += n;
+        ws->best = q; q += 64;
+        ws->total = q++; ws->ototal = q++; ws->nclusters = q++; ws->nout = q++; ws->ninl = q++; ws->n_dev = q++;
+        float *f = ws->floats;
+        ws->traj_c = f; f += n * F * 2; ws->opts = f; f += 2 * n; ws->m2 = f; f += n; ws->res = f; f += n;
+        ws->outl = ws->bytes;
+        ws->cap = npts; ws->capF = F;
+    }
+    return MD_OK;
+}
+
+extern "C" int md_live_params_default(md_live_params *p)
+{
+    if (!p) return MD_ERR_INVALID;
+    memset(p, 0, sizeof *p);
+    p->num_motions = 2;              // ros/src/motion_detection_node.cpp:239
+    p->sigma = 0.5;                  // node.cpp:346
+    p->distance_threshold = 50.0;    // ros/launch/bag.launch:28
+    p->seed = 1;
+    p->subspace_iters = 50;          // outlier_detector.cpp:250
+    p->min_cluster_size = 5;         // flow_clusterer.cpp:264
+    return MD_OK;
+}
+
+extern "C" int md_window_reset(md_ctx *ctx)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    ctx->win_fill = 0;
+    ctx->win_head = 0;
+    return MD_OK;
+}
+
+extern "C" int md_window_push(md_ctx *ctx, const uint8_t *frame, int32_t channels, int32_t pitch, int32_t *fill, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!frame || (channels != 1 && channels != 3) || pitch < ctx->cfg.width * channels) FAIL(MD_ERR_INVALID, "md_window_push: bad frame");
+    CK(cudaSetDevice(ctx->device));
+    const int ns = ctx->g.nslots;
+    const int slot = ctx->win_fill ? (ctx->win_head + 1) % ns : 0;
+    const uint8_t *df; int dp; long long ds;
+    int r = stage_frames(ctx, frame, channels, pitch, 0, 1, mem, &df, &dp, &ds);
+    if (r != MD_OK) return r;
+    CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, slot, 1, df, channels, dp, ds, ctx->stream));
+    // the pageable staging buffer is reused by the next push: host-memory pushes complete before returning
+    if (mem == MD_MEM_HOST) CK(cudaStreamSynchronize(ctx->stream));
+    ctx->win_head = slot;
+    if (ctx->win_fill < ns) ctx->win_fill++;
+    ctx->have_cached = 0;            // the ring now belongs to the window API
+    if (fill) *fill = ctx->win_fill;
+    return MD_OK;
+}
+
+// clusterEuclidean + boxes on ws->opts[0 .. *n_dev), results to the caller
+static int live_cluster(md_ctx *ctx, LiveWs *ws, const int *n_dev, int n_max, double thr, int min_size, cudaStream_t s)
+{
+    CK(launch_cluster((const float2 *)ws->opts, n_dev, n_max, thr, min_size, ws->m2, ws->cand, ws->ncand, ws->label, ws->nclusters,
+                      ws->sizes, ws->box, ws->nout, ws->out_box, ws->out_size, ws->out_id, s));
+    return MD_OK;
+}
+
+extern "C" int md_window_detect(md_ctx *ctx, const md_live_params *lp, md_live_result *res, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!lp || !res || lp->num_motions < 1) FAIL(MD_ERR_INVALID, "md_window_detect: bad arguments");
+    const int F = 2 * lp->num_motions + 1, P = ctx->P, ns = ctx->g.nslots;
+    if (F > ns) FAIL(MD_ERR_INVALID, "md_window_detect: 2 * num_motions + 1 frames need max_batch >= 2 * num_motions");
+    if (ctx->win_fill < F) FAIL(MD_ERR_STATE, "md_window_detect: fewer than 2 * num_motions + 1 frames pushed");
+    if (2 * F > 32 || 4 * lp->num_motions > 2 * F) FAIL(MD_ERR_INVALID, "md_window_detect: num_motions too large");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int r = ensure_traj(ctx, F);
+    if (r != MD_OK) return r;
+    r = live_ensure(ctx, P, F);
+    if (r != MD_OK) return r;
+    LiveWs *ws = (LiveWs *)ctx->live_ws;
+    const cudaMemcpyKind outk = mem == MD_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    res->num_trajectories = res->subspace_inliers = res->num_outliers = res->num_clusters_all = res->num_clusters = 0;
+
+    const int slot0 = ((ctx->win_head - (F - 1)) % ns + ns) % ns;
+    r = track_window(ctx, slot0, F, ctx->d_traj, ctx->d_traj_len, nullptr, nullptr, nullptr, true, s);
+    if (r != MD_OK) return r;
+    CK(launch_compact_trajectories(ctx->d_traj, ctx->d_traj_len, P, F, ws->blockcnt, ws->idx, ws->total, (float2 *)ws->traj_c, s));
+    int T = 0;
+    CK(cudaMemcpyAsync(&T, ws->total, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    res->num_trajectories = T;
+    if (T < 1) return MD_OK;                                    // "no trajectories found" (node.cpp:296-321)
+
+    r = sub_enqueue(ctx, ws->traj_c, T, F, lp->num_motions, lp->sigma, lp->seed, nullptr, lp->subspace_iters > 0 ? lp->subspace_iters : 50,
+                    ws->res, ws->outl, ws->best, ws->ninl);
+    if (r != MD_OK) return r;
+    CK(launch_compact_outliers((const float2 *)ws->traj_c, ws->outl, T, F, ws->blockcnt, ws->oidx, ws->ototal, (float2 *)ws->opts, s));
+    r = live_cluster(ctx, ws, ws->ototal, T, lp->distance_threshold, lp->min_cluster_size, s);
+    if (r != MD_OK) return r;
+    int counts[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(&counts[0], ws->ninl, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&counts[1], ws->ototal, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&counts[2], ws->nclusters, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&counts[3], ws->nout, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    res->subspace_inliers = counts[0]; res->num_outliers = counts[1]; res->num_clusters_all = counts[2]; res->num_clusters = counts[3];
+    const int no = counts[1], K = counts[3];
+    if (res->traj) CK(cudaMemcpyAsync(res->traj, ws->traj_c, sizeof(float2) * (size_t)T * F, outk, s));
+    if (res->traj_index) CK(cudaMemcpyAsync(res->traj_index, ws->idx, sizeof(int) * T, outk, s));
+    if (res->residual) CK(cudaMemcpyAsync(res->residual, ws->res, sizeof(float) * T, outk, s));
+    if (res->outlier) CK(cudaMemcpyAsync(res->outlier, ws->outl, T, outk, s));
+    if (res->best_cols) CK(cudaMemcpyAsync(res->best_cols, ws->best, sizeof(int) * 4 * lp->num_motions, outk, s));
+    if (res->outlier_points && no) CK(cudaMemcpyAsync(res->outlier_points, ws->opts, sizeof(float2) * no, outk, s));
+    if (res->labels && no) CK(cudaMemcpyAsync(res->labels, ws->label, sizeof(int) * no, outk, s));
+    if (res->boxes && K) CK(cudaMemcpyAsync(res->boxes, ws->out_box, sizeof(int) * 4 * K, outk, s));
+    if (res->cluster_sizes && K) CK(cudaMemcpyAsync(res->cluster_sizes, ws->out_size, sizeof(int) * K, outk, s));
+    if (res->cluster_ids && K) CK(cudaMemcpyAsync(res->cluster_ids, ws->out_id, sizeof(int) * K, outk, s));
+    CK(cudaStreamSynchronize(s));
+    return MD_OK;
+}
+
+extern "C" int md_cluster_points(md_ctx *ctx, const float *pts, int32_t n, double distance_threshold, int32_t min_cluster_size,
+                                 int32_t *labels, int32_t *num_clusters_all, int32_t *num_clusters, int32_t *boxes, int32_t *sizes,
+                                 int32_t *ids, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!pts || n < 0 || n > (1 << 24)) FAIL(MD_ERR_INVALID, "md_cluster_points: bad arguments");
+    if (num_clusters_all) *num_clusters_all = 0;
+    if (num_clusters) *num_clusters = 0;
+    if (n == 0) return MD_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    int r = live_ensure(ctx, n > ctx->P ? n : ctx->P, 1);
+    if (r != MD_OK) return r;
+    LiveWs *ws = (LiveWs *)ctx->live_ws;
+    const cudaMemcpyKind ink = mem == MD_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    const cudaMemcpyKind outk = mem == MD_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(ws->opts, pts, sizeof(float2) * n, ink, s));
+    CK(cudaMemcpyAsync(ws->n_dev, &n, sizeof(int), cudaMemcpyHostToDevice, s));
+    r = live_cluster(ctx, ws, ws->n_dev, n, distance_threshold, min_cluster_size, s);
+    if (r != MD_OK) return r;
+    int counts[2] = {0, 0};
+    CK(cudaMemcpyAsync(&counts[0], ws->nclusters, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&counts[1], ws->nout, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (num_clusters_all) *num_clusters_all = counts[0];
+    if (num_clusters) *num_clusters = counts[1];
+    const int K = counts[1];
+    if (labels) CK(cudaMemcpyAsync(labels, ws->label, sizeof(int) * n, outk, s));
+    if (boxes && K) CK(cudaMemcpyAsync(boxes, ws->out_box, sizeof(int) * 4 * K, outk, s));
+    if (sizes && K) CK(cudaMemcpyAsync(sizes, ws->out_size, sizeof(int) * K, outk, s));
+    if (ids && K) CK(cudaMemcpyAsync(ids, ws->out_id, sizeof(int) * K, outk, s));
+    CK(cudaStreamSynchronize(s));
     return MD_OK;
 }
 

@@ -172,6 +172,7 @@ struct md_ctx {
     float2 *d_traj;       // [P][F] trajectory staging (host-memory calls)
     int32_t *d_traj_len;
     int traj_F;
+    int win_head, win_fill;   // live-path ring: slot of the newest frame, frames held
     md_stats stats;
     int profile;
     cudaEvent_t ev[5];
@@ -180,10 +181,15 @@ struct md_ctx {
     PhaseGeom pg;
     int16_t *d_phase;     // [max_batch] pair arenas of phase planes, allocated on the first grid-mode LK call
     int phase_state;      // 0 = not tried, 1 = ready, -1 = not used (not worth it / allocation failed)
+    void *sub_ws;         // fitSubspace workspace (k_subspace.cu)
+    void *live_ws;        // live-path workspace (md_api.cu: md_window_*)
     void *vf_ws;          // VarFlow workspace (k_varflow.cu), allocated on the first md_varflow call
 };
 
 void vf_free_workspace(void *ws);
+void sub_free_workspace(void *ws);
+int sub_enqueue(md_ctx *ctx, const float *d_traj, int T, int F, int num_motions, double sigma, uint32_t seed,
+                const int32_t *forced_host, int iters, float *d_res, uint8_t *d_out, int *d_best, int *d_ninl);
 int vf_compute_device(md_ctx *ctx, const uint8_t *dA, const uint8_t *dB, int dpitch);
 cudaError_t vf_sample_grid(md_ctx *ctx, float2 *next, uint8_t *status, cudaStream_t s);
 
@@ -197,6 +203,13 @@ cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot
 cudaError_t launch_lk(const LkParams &p, const LkTmaMaps *maps, const LkPhaseMaps *pmaps, int pairs, cudaStream_t s);
 cudaError_t launch_ego(const EgoParams &p, int pairs, cudaStream_t s);
 cudaError_t launch_mask(const MaskParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_compact_trajectories(const float2 *traj, const int32_t *len, int P, int F, int *blockcnt, int *idx, int *total,
+                                        float2 *traj_c, cudaStream_t s);
+cudaError_t launch_compact_outliers(const float2 *traj_c, const uint8_t *outlier, int T, int F, int *blockcnt, int *oidx, int *total,
+                                    float2 *pts, cudaStream_t s);
+cudaError_t launch_cluster(const float2 *pts, const int *n_ptr, int n_max, double thr, int min_size, float *m2, int *cand, int *ncand,
+                           int *label, int *nclusters, int *sizes, int *box, int *nout, int32_t *out_box, int32_t *out_size,
+                           int32_t *out_id, cudaStream_t s);
 cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pairs, cudaStream_t s);
 cudaError_t launch_traj_step(float2 *pts_cur, const float2 *next, const uint8_t *status, float2 *traj, int32_t *len,
                              int P, int F, int w, int h, cudaStream_t s);

@@ -43,6 +43,12 @@ int orc_fit_subspace(const float *traj, int T, int F, int num_motions, double si
                      double *threshold_out);
 void orc_subspace_projector(const float *data, int n, int T, const int *cols, int d, float *Pnd);
 
+/* md_oracle_live.c */
+void orc_traj_step(float *cur, const float *next, const uint8_t *status, float *traj, int32_t *len, int P, int F, int w, int h);
+int orc_cluster_euclidean(const float *pts, int n, double distance_threshold, int32_t *labels);
+int orc_bounding_boxes(const float *pts, int n, const int32_t *labels, int nclusters, int min_size, int32_t *boxes,
+                       int32_t *sizes, int32_t *ids);
+
 #ifdef __cplusplus
 }
 #endif

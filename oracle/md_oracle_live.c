@@ -1,0 +1,108 @@
+/* md_oracle_live.c -- CPU restatement (TEST INFRASTRUCTURE ONLY) of the steps of the node's live path that follow the
+ * trajectories (MotionDetectionNode::imageCallback, ros/src/motion_detection_node.cpp:294-414):
+ *   orc_traj_step          calculateOpticalFlowTrajectory bookkeeping, common/src/optical_flow_calculator.cpp:178-241
+ *   orc_cluster_euclidean  FlowClusterer::clusterEuclidean, common/src/flow_clusterer.cpp:227-269, with
+ *                          PointCluster::getClosestDistance / getDistance, common/src/point_cluster.cpp:26-38,62-65
+ *   orc_bounding_boxes     OpticalFlowVisualizer::showBoundingBoxes, common/src/optical_flow_visualizer.cpp:223-240
+ *                          (cv::Mat(Point2f).copyTo(vector<Point>) = saturate_cast<int> = round half to even;
+ *                          cv::boundingRect of integer points: tl = min, size = max - min + 1; br = tl + size) --
+ *                          the row MotionLogger::writeBoundingBox logs (common/src/motion_logger.cpp:43-47).
+ * Written as the reference writes it (explicit cluster member lists, clusters scanned in creation order); the GPU path
+ * uses a different but equivalent formulation, which is what the parity test checks.
+ * Parity unpinned by the reference (no tests/fixtures for these functions); pinned here by construction checks in
+ * tests/test_oracle_golden.py (hand-worked cases).
+ */
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "md_oracle.h"
+
+/* One pair of calculateOpticalFlowTrajectory (cpp:178-241): a tracked point inside the 10 px margin extends its
+ * trajectory and becomes the new start point; any other point keeps its old position. */
+void orc_traj_step(float *cur, const float *next, const uint8_t *status, float *traj, int32_t *len, int P, int F, int w, int h)
+{
+    for (int i = 0; i < P; i++) {
+        if (!status[i]) continue;                                      /* cpp:219-236: temp.push_back(points_image1) */
+        const float x = next[2 * i], y = next[2 * i + 1];
+        if (x > 10.0 && y > 10.0 && x < w - 10 && y < h - 10) {      /* cpp:207-208 */
+            if (len[i] < F) { traj[((size_t)i * F + len[i]) * 2] = x; traj[((size_t)i * F + len[i]) * 2 + 1] = y; len[i]++; }
+            cur[2 * i] = x; cur[2 * i + 1] = y;                        /* cpp:210-211 */
+        }
+    }
+}
+
+typedef struct { int *member; int n, cap; } orc_cluster;
+
+static double cl_distance(const float *a, const float *b)
+{
+    /* point_cluster.cpp:62-65: float arithmetic inside, sqrt on the promoted value */
+    const float dx = a[0] - b[0], dy = a[1] - b[1];
+    const float s = dx * dx + dy * dy;
+    return sqrt((double)s);
+}
+
+/* labels[i] = id (creation order) of the cluster point i joined; returns the number of clusters founded */
+int orc_cluster_euclidean(const float *pts, int n, double distance_threshold, int32_t *labels)
+{
+    orc_cluster *cl = NULL;
+    int ncl = 0, capcl = 0;
+    for (int i = 0; i < n; i++) {
+        const float *p = pts + 2 * i;
+        double closest = DBL_MAX;                                      /* flow_clusterer.cpp:234 */
+        int index = -1;
+        for (int k = 0; k < ncl; k++) {                                /* :236-244 */
+            double md = DBL_MAX;                                       /* point_cluster.cpp:28-37 */
+            for (int m = 0; m < cl[k].n; m++) {
+                const double d = cl_distance(p, pts + 2 * cl[k].member[m]);
+                if (d < md) md = d;
+            }
+            if (md < closest) { closest = md; index = k; }
+        }
+        if (index != -1 && closest < distance_threshold) {             /* :245-248 */
+            orc_cluster *c = &cl[index];
+            if (c->n == c->cap) { c->cap *= 2; c->member = (int *)realloc(c->member, sizeof(int) * c->cap); }
+            c->member[c->n++] = i;
+            labels[i] = index;
+        } else {                                                       /* :249-254 */
+            if (ncl == capcl) { capcl = capcl ? 2 * capcl : 16; cl = (orc_cluster *)realloc(cl, sizeof(orc_cluster) * capcl); }
+            cl[ncl].cap = 8; cl[ncl].n = 1;
+            cl[ncl].member = (int *)malloc(sizeof(int) * 8);
+            cl[ncl].member[0] = i;
+            labels[i] = ncl++;
+        }
+    }
+    for (int k = 0; k < ncl; k++) free(cl[k].member);
+    free(cl);
+    return ncl;
+}
+
+/* clusters with MORE than min_size members (flow_clusterer.cpp:262-267), in creation order:
+ * boxes[k] = tl.x, tl.y, br.x, br.y; sizes[k]; ids[k]; returns their number */
+int orc_bounding_boxes(const float *pts, int n, const int32_t *labels, int nclusters, int min_size, int32_t *boxes,
+                       int32_t *sizes, int32_t *ids)
+{
+    int *cnt = (int *)calloc((size_t)(nclusters > 0 ? nclusters : 1), sizeof(int));
+    int *bb = (int *)malloc(sizeof(int) * 4 * (size_t)(nclusters > 0 ? nclusters : 1));
+    for (int k = 0; k < nclusters; k++) { bb[4 * k] = bb[4 * k + 1] = 0x7fffffff; bb[4 * k + 2] = bb[4 * k + 3] = (int)0x80000000; }
+    for (int i = 0; i < n; i++) {
+        const int k = labels[i];
+        const int x = (int)lrintf(pts[2 * i]), y = (int)lrintf(pts[2 * i + 1]);   /* saturate_cast<int>(float) */
+        cnt[k]++;
+        if (x < bb[4 * k]) bb[4 * k] = x;
+        if (y < bb[4 * k + 1]) bb[4 * k + 1] = y;
+        if (x > bb[4 * k + 2]) bb[4 * k + 2] = x;
+        if (y > bb[4 * k + 3]) bb[4 * k + 3] = y;
+    }
+    int out = 0;
+    for (int k = 0; k < nclusters; k++)
+        if (cnt[k] > min_size) {
+            boxes[4 * out] = bb[4 * k]; boxes[4 * out + 1] = bb[4 * k + 1];
+            boxes[4 * out + 2] = bb[4 * k + 2] + 1; boxes[4 * out + 3] = bb[4 * k + 3] + 1;
+            sizes[out] = cnt[k]; ids[out] = k;
+            out++;
+        }
+    free(cnt); free(bb);
+    return out;
+}

@@ -45,6 +45,8 @@ def lib():
         _LIB.orc_fit_egomotion.restype = C.c_int
         _LIB.orc_varflow.restype = C.c_int
         _LIB.orc_fit_subspace.restype = C.c_int
+        _LIB.orc_cluster_euclidean.restype = C.c_int
+        _LIB.orc_bounding_boxes.restype = C.c_int
     return _LIB
 
 
@@ -278,3 +280,61 @@ def fit_subspace(traj, num_motions=2, sigma=0.5, seed=1, forced_cols=None, iters
                                iters, res.ctypes.data_as(f32p), cols.ctypes.data_as(i32p), outl.ctypes.data_as(u8p),
                                C.byref(thr))
     return n, res, cols, outl, thr.value
+
+
+# ---- the node's live path (imageCallback, ros/src/motion_detection_node.cpp:235-414) ------------------------------
+def track_trajectories(frames, pixel_step=10):
+    """calculateOpticalFlowTrajectory (cpp:133-257) on gray frames: returns (traj [P][F][2], len [P], last_prev, last_next,
+    last_status)."""
+    frames = [np.ascontiguousarray(f, np.uint8) for f in frames]
+    F = len(frames)
+    h, w = frames[0].shape
+    pts = grid_points(w, h, pixel_step)
+    P = len(pts)
+    cur = pts.copy()
+    traj = np.zeros((P, F, 2), np.float32)
+    traj[:, 0] = pts
+    ln = np.ones(P, np.int32)
+    last = None
+    for j in range(F - 1):
+        nxt, st = lk(frames[j], frames[j + 1], cur)
+        if j == F - 2:
+            last = (cur.copy(), nxt.copy(), st.copy())
+        nxt = np.ascontiguousarray(nxt, np.float32)
+        st = np.ascontiguousarray(st, np.uint8)
+        lib().orc_traj_step(cur.ctypes.data_as(f32p), nxt.ctypes.data_as(f32p), st.ctypes.data_as(u8p), traj.ctypes.data_as(f32p),
+                            ln.ctypes.data_as(i32p), P, F, w, h)
+    return traj, ln, last
+
+
+def cluster_euclidean(pts, distance_threshold=50.0, min_size=5):
+    """FlowClusterer::clusterEuclidean + showBoundingBoxes: (labels, nclusters_all, boxes [K][4], sizes [K], ids [K])."""
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    n = len(pts)
+    labels = np.zeros(max(n, 1), np.int32)
+    ncl = lib().orc_cluster_euclidean(pts.ctypes.data_as(f32p), n, C.c_double(distance_threshold), labels.ctypes.data_as(i32p))
+    boxes = np.zeros((max(ncl, 1), 4), np.int32)
+    sizes = np.zeros(max(ncl, 1), np.int32)
+    ids = np.zeros(max(ncl, 1), np.int32)
+    k = lib().orc_bounding_boxes(pts.ctypes.data_as(f32p), n, labels.ctypes.data_as(i32p), ncl, min_size, boxes.ctypes.data_as(i32p),
+                                 sizes.ctypes.data_as(i32p), ids.ctypes.data_as(i32p))
+    return labels[:n], ncl, boxes[:k], sizes[:k], ids[:k]
+
+
+def live_detect(frames, pixel_step=10, num_motions=2, sigma=0.5, distance_threshold=50.0, seed=1, iters=50, min_size=5):
+    """The callback body over F = 2 * num_motions + 1 gray frames: trajectories -> fitSubspace -> outlier points ->
+    clusterEuclidean -> bounding boxes (node.cpp:294-395)."""
+    F = 2 * num_motions + 1
+    assert len(frames) == F
+    traj, ln, _ = track_trajectories(frames, pixel_step)
+    idx = np.nonzero(ln == F)[0].astype(np.int32)
+    tc = np.ascontiguousarray(traj[idx])
+    out = dict(traj=tc, traj_index=idx, num_trajectories=len(idx))
+    if len(idx) == 0:
+        return out
+    n, res, cols, outl, thr = fit_subspace(tc, num_motions=num_motions, sigma=sigma, seed=seed, iters=iters)
+    opts = np.ascontiguousarray(tc[outl != 0][:, F - 2])
+    labels, ncl, boxes, sizes, ids = cluster_euclidean(opts, distance_threshold, min_size)
+    out.update(subspace_inliers=n, residual=res, best_cols=cols, outlier=outl, outlier_points=opts, labels=labels,
+               num_clusters_all=ncl, boxes=boxes, cluster_sizes=sizes, cluster_ids=ids)
+    return out

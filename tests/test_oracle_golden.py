@@ -103,3 +103,42 @@ def test_glibc_rand_matches_libc(oracle):
     for seed in (1, 7, 123456789):
         libc.srand(seed)
         assert [libc.rand() for _ in range(400)] == oracle.glibc_rand(seed, 400)
+
+
+# ---- live path restatements (oracle/md_oracle_live.c): hand-worked cases ------------------------------------------------
+def test_cluster_euclidean_hand_worked():
+    from oracle import oracle as O
+    # points arrive in this order; threshold 12: (0,0) founds 0; (10,0) joins 0 (d = 10); (0,10) joins 0; (100,100) founds 1;
+    # (10,10) is 10 away from two members of cluster 0; (105,100) joins 1; (5,5) joins 0
+    pts = np.array([[0, 0], [10, 0], [0, 10], [100, 100], [10, 10], [105, 100], [5, 5]], np.float32)
+    labels, ncl, boxes, sizes, ids = O.cluster_euclidean(pts, 12.0, 1)
+    assert labels.tolist() == [0, 0, 0, 1, 0, 1, 0] and ncl == 2
+    # cv::boundingRect of the rounded points: tl = min, br = max + 1 (the CSV row of MotionLogger::writeBoundingBox)
+    assert boxes.tolist() == [[0, 0, 11, 11], [100, 100, 106, 101]] and sizes.tolist() == [5, 2] and ids.tolist() == [0, 1]
+    # only clusters with MORE than 5 members survive with the reference's constant (flow_clusterer.cpp:264)
+    assert len(O.cluster_euclidean(pts, 12.0, 5)[2]) == 0
+    # a tie between an older and a younger cluster goes to the older one (strict '<' while scanning in creation order)
+    pts = np.array([[0, 0], [20, 0], [10, 0]], np.float32)
+    assert O.cluster_euclidean(pts, 11.0, 0)[0].tolist() == [0, 1, 0]
+    # order dependence: the same points in another order chain into one cluster
+    pts = np.array([[0, 0], [10, 0], [20, 0]], np.float32)
+    assert O.cluster_euclidean(pts, 11.0, 0)[0].tolist() == [0, 0, 0]
+    # rounding is half-to-even, like saturate_cast<int>(float)
+    pts = np.array([[0.5, 1.5], [2.5, 3.5]], np.float32)
+    assert O.cluster_euclidean(pts, 10.0, 0)[2].tolist() == [[0, 2, 3, 5]]
+
+
+def test_traj_step_bookkeeping():
+    from oracle import oracle as O
+    import ctypes as C
+    P, F, w, h = 4, 3, 100, 80
+    cur = np.array([[20, 20], [30, 30], [40, 40], [50, 50]], np.float32)
+    traj = np.zeros((P, F, 2), np.float32); traj[:, 0] = cur
+    ln = np.ones(P, np.int32)
+    nxt = np.array([[21, 21], [5, 30], [41, 75], [51, 51]], np.float32)       # 2nd leaves the margin in x, 3rd in y (>= h - 10)
+    st = np.array([1, 1, 1, 0], np.uint8)
+    O.lib().orc_traj_step(cur.ctypes.data_as(O.f32p), nxt.ctypes.data_as(O.f32p), st.ctypes.data_as(O.u8p),
+                          traj.ctypes.data_as(O.f32p), ln.ctypes.data_as(O.i32p), P, F, w, h)
+    assert ln.tolist() == [2, 1, 1, 1]
+    assert cur.tolist() == [[21, 21], [30, 30], [40, 40], [50, 50]]
+    assert traj[0, 1].tolist() == [21, 21]
