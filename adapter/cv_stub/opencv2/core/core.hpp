@@ -27,6 +27,7 @@ struct Point2f { float x, y; Point2f() : x(0), y(0) {} Point2f(float a, float b)
 struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
 template <typename T, int N> struct Vec { T val[N]; T &operator[](int i) { return val[i]; } const T &operator[](int i) const { return val[i]; } };
 typedef Vec<double, 4> Vec4d;
+typedef Vec<int, 4> Vec4i;
 
 class Mat {
 public:

@@ -4,6 +4,7 @@
 #include <motion_detection/optical_flow_calculator.h>
 #include <motion_detection/outlier_detector.h>
 #include <motion_detection/VarFlow.h>
+#include <motion_detection/flow_clusterer.h>
 
 #include <cmath>
 #include <cstdio>
@@ -230,4 +231,41 @@ int VarFlow::CalcFlow(IplImage *imgA, IplImage *imgB, IplImage *imgU, IplImage *
         std::memcpy(imgV->imageData + (size_t)y * imgV->widthStep, &V[(size_t)y * width], sizeof(float) * width);
     }
     return 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+FlowClusterer::FlowClusterer() : ctx_(0), device_(0) {}
+
+FlowClusterer::~FlowClusterer() { if (ctx_) md_destroy(ctx_); }
+
+std::vector<std::vector<cv::Point2f> > FlowClusterer::clusterEuclidean(const std::vector<cv::Point2f> &points, double distance_threshold)
+{
+    std::vector<std::vector<cv::Point2f> > mat_clusters;
+    boxes_.clear();
+    const int n = (int)points.size();
+    if (n < 1) return mat_clusters;
+    if (!ctx_) {
+        md_config cfg;
+        md_config_default(&cfg);
+        cfg.width = 64; cfg.height = 64;           // geometry is irrelevant for the grouping
+        if (md_create(&cfg, device_, &ctx_) != MD_OK) { ctx_ = 0; return mat_clusters; }
+    }
+    std::vector<int32_t> labels(n), boxes(4 * (size_t)n), sizes(n), ids(n);
+    int32_t nall = 0, k = 0;
+    if (md_cluster_points(ctx_, &points[0].x, n, distance_threshold, 5, labels.data(), &nall, &k, boxes.data(), sizes.data(), ids.data(),
+                          MD_MEM_HOST) != MD_OK)
+        return mat_clusters;
+    // clusters with more than 5 points in creation order, members in arrival order (flow_clusterer.cpp:262-267)
+    std::vector<int> slot(nall > 0 ? nall : 1, -1);
+    mat_clusters.resize(k);
+    for (int c = 0; c < k; c++) {
+        slot[ids[c]] = c;
+        mat_clusters[c].reserve(sizes[c]);
+        cv::Vec4i b;
+        for (int q = 0; q < 4; q++) b[q] = boxes[4 * c + q];
+        boxes_.push_back(b);
+    }
+    for (int i = 0; i < n; i++)
+        if (slot[labels[i]] >= 0) mat_clusters[slot[labels[i]]].push_back(points[i]);
+    return mat_clusters;
 }

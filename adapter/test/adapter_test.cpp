@@ -3,6 +3,7 @@
 #include <motion_detection/optical_flow_calculator.h>
 #include <motion_detection/outlier_detector.h>
 #include <motion_detection/VarFlow.h>
+#include <motion_detection/flow_clusterer.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -50,6 +51,19 @@ int main(int argc, char **argv)
     int32_t t2[5] = {nv2, (int32_t)traj.size(), (int32_t)outliers.size(), (int32_t)basis.size(), od.lastInliers()};
     put(fo, t2, sizeof t2);
     for (size_t i = 0; i < traj.size(); i++) put(fo, traj[i].data(), sizeof(cv::Point2f) * F);
+
+    // --- clusterEuclidean on the outlier points (node.cpp:355) + the rectangles showBoundingBoxes would draw
+    FlowClusterer fc;
+    std::vector<std::vector<cv::Point2f> > clusters = fc.clusterEuclidean(outliers, 50.0);
+    int32_t nc = (int32_t)clusters.size();
+    put(fo, &nc, sizeof nc);
+    for (int c = 0; c < nc; c++) {
+        int32_t sz = (int32_t)clusters[c].size();
+        put(fo, &sz, sizeof sz);
+        put(fo, &fc.boundingBoxes()[c], 4 * sizeof(int32_t));
+        put(fo, clusters[c].data(), sizeof(cv::Point2f) * sz);
+    }
+    if (!outliers.empty()) put(fo, outliers.data(), sizeof(cv::Point2f) * outliers.size());
 
     // --- VarFlow with the parameters of varFlow() (cpp:422-429)
     VarFlow vf(w, h, 4, 0, 2, 2, 2.8f, 1400.f, 1.5f);

@@ -43,6 +43,10 @@ def parse():
     ap.add_argument("--cpu-baseline-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="pairs", choices=["pairs", "live"],
+                    help="pairs = the motion-mask chain (BASELINE metric); live = the node's imageCallback path "
+                         "(trajectory window -> fitSubspace -> clusterEuclidean -> boxes), a secondary line")
+    ap.add_argument("--num-motions", type=int, default=2)
     return ap.parse_args()
 
 
@@ -128,13 +132,164 @@ def run_reference(a, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_live(a, rank, local, world):
+    """Secondary workload: the node's live path.  A step = `--batch` imageCallbacks, each = one NEW frame pushed into the
+    ring (gray conversion + pyramid once) + md_window_detect over the newest F = 2 * num_motions + 1 frames."""
+    import torch
+    import torch.distributed as dist
+    from motion_detection_b200 import capi, streams
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    w, h, B, nm = a.width, a.height, a.batch, a.num_motions
+    F = 2 * nm + 1
+    name = "live path (imageCallback): %dx%d C2 sequence, pixel_step=%d, window F=%d, sigma=0.5, distance_threshold=50" % (
+        w, h, a.pixel_step, F)
+    ctx = capi.Context(width=w, height=h, max_batch=F - 1, pixel_step=a.pixel_step, min_vector_size=0.2, seed=1, device=local)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    clip = make_frames(a, rank, B + 1)
+    # ping-pong order keeps every pushed frame a real neighbour of the previous one
+    order = list(range(B + 1)) + list(range(B - 1, 0, -1))
+    R = max(2, int(np.ceil(300e6 / ((B + 1) * w * h))))
+    sets = torch.empty((R, B + 1, h, w), dtype=torch.uint8, device=dev)
+    for r in range(R):
+        sets[r].copy_(torch.from_numpy(clip))
+    lp = capi.MdLiveParams()
+    capi.lib().md_live_params_default(C.byref(lp))
+    lp.num_motions = nm
+    res = capi.MdLiveResult()
+    state = {"k": 0, "cb": 0, "traj": 0, "boxes": 0}
+
+    def callback(push):
+        k = state["k"]
+        state["k"] += 1
+        fill = push(order[k % len(order)], k)
+        if fill >= F:
+            lp.seed = 1 + state["cb"]
+            ctx.raw_window_detect(lp, res, capi.MD_MEM_DEVICE)
+            state["cb"] += 1
+            state["traj"] += res.num_trajectories
+            state["boxes"] += res.num_clusters
+
+    def push_dev(f, k):
+        return ctx.raw_window_push(sets[(k // len(order)) % R, f].data_ptr(), 1, w, capi.MD_MEM_DEVICE)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(push, steps):
+        for _ in range(steps * B):
+            callback(push)
+
+    run(push_dev, max(a.warmup, 1))
+    barrier()
+    l0 = ctx.stats()["kernel_launches"]
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.15)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    cb0 = state["cb"]
+    e0.record(stream)
+    run(push_dev, a.steps)
+    e1.record(stream)
+    barrier()
+    ms = streams.max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = ctx.stats()["kernel_launches"] - l0
+    ncb = state["cb"] - cb0
+    value = world * ncb / (ms * 1e-3)
+    assert state["traj"] > 0
+
+    e2e = None
+    if not a.no_e2e:
+        rgb = torch.from_numpy(np.repeat(clip[..., None], 3, axis=3)).pin_memory()       # the node hands over rgb8 (node.cpp:271)
+        P = ctx.P
+        pin = dict(boxes=torch.empty((P, 4), dtype=torch.int32).pin_memory(), sizes=torch.empty((P,), dtype=torch.int32).pin_memory(),
+                   opts=torch.empty((P, 2), dtype=torch.float32).pin_memory(), labels=torch.empty((P,), dtype=torch.int32).pin_memory())
+        hres = capi.MdLiveResult()
+        hres.boxes, hres.cluster_sizes = pin["boxes"].data_ptr(), pin["sizes"].data_ptr()
+        hres.outlier_points, hres.labels = pin["opts"].data_ptr(), pin["labels"].data_ptr()
+        ctx.window_reset()
+        st2 = {"k": 0, "cb": 0, "d2h": 0}
+
+        def hcallback():
+            k = st2["k"]
+            st2["k"] += 1
+            fill = ctx.raw_window_push(rgb[order[k % len(order)]].data_ptr(), 3, 3 * w, capi.MD_MEM_HOST)
+            if fill >= F:
+                lp.seed = 1 + st2["cb"]
+                ctx.raw_window_detect(lp, hres, capi.MD_MEM_HOST)
+                st2["cb"] += 1
+                st2["d2h"] += 20 + hres.num_outliers * 12 + hres.num_clusters * 20
+
+        for _ in range(max(a.warmup, 1) * B):
+            hcallback()
+        barrier()
+        c0, d0 = st2["cb"], st2["d2h"]
+        t0 = time.perf_counter()
+        for _ in range(a.steps * B):
+            hcallback()
+        torch.cuda.synchronize()
+        dt = streams.max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": world * (st2["cb"] - c0) / dt, "unit": "callbacks/s", "h2d_bytes_per_step": B * 3 * w * h,
+               "d2h_bytes_per_step": int((st2["d2h"] - d0) / max(a.steps, 1))}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        from oracle import cv_chain
+        n = 0
+        cv_chain.live_callback(clip[:F], pixel_step=a.pixel_step, num_motions=nm)
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < a.cpu_baseline_seconds and n < 500:
+            i = n % (B + 2 - F)
+            cv_chain.live_callback(clip[i:i + F], pixel_step=a.pixel_step, num_motions=nm, seed=1 + n)
+            n += 1
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": "callbacks/s", "cores": cv_chain.threads(), "kind": "port",
+               "sample": "%d callbacks of the same workload in %.1f s (cv2 OpenCV routines re-run over the whole window per "
+                         "callback like the reference, oracle fitSubspace + clusterEuclidean)" % (n, dt)}
+    if rank == 0:
+        N, P = w * h, ctx.P
+        alg = 1.3333 * N + (F - 1) * (2.6667 * N + 9 * P) + 8.0 * P * F      # new pyramid + F-1 LK passes + trajectories
+        peak, peak_src = peaks()
+        gbs = alg * ncb / (ms * 1e-3) / 1e9
+        line = {
+            "metric": "1080p live-path callbacks/sec (secondary workload)", "value": value, "unit": "callbacks/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8/f32/f64", "data": "synthetic",
+            "config": {"workload": name, "callbacks_per_step": B, "grid_points": P, "streams": world,
+                       "l2": "frames rotate over %d resident copies of the clip (%.0f MB > 126 MB L2)" % (R, R * (B + 1) * N / 1e6)},
+            "roofline": {"bound": "hbm", "kernel": "whole callback (k_lk_phase + 3 x k_lk_tma dominate)", "achieved": gbs, "peak": peak,
+                         "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "LK is instruction-issue bound (see DESIGN.md); algorithmic bytes per callback = %.1f MB" % (alg / 1e6)},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "live_stats": {"callbacks": ncb, "mean_trajectories": state["traj"] / max(state["cb"], 1),
+                           "mean_boxes": state["boxes"] / max(state["cb"], 1)},
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if a.impl == "reference":
+    if a.impl == "reference" and a.workload == "pairs":
         run_reference(a, rank, world)
+        return
+    if a.workload == "live":
+        if a.impl == "reference":
+            raise SystemExit("--impl reference times the BASELINE workload (pairs); the live CPU figure is the cpu_baseline of --workload live")
+        run_live(a, rank, local, world)
         return
 
     import torch

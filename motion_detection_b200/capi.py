@@ -288,6 +288,15 @@ class Context:
         self._ck(lib().md_window_push(self._h, _ptr(frame), ch, self.w * ch, C.byref(fill), MD_MEM_HOST))
         return fill.value
 
+    def raw_window_push(self, frame_ptr, channels, pitch, mem):
+        fill = C.c_int32()
+        self._ck(lib().md_window_push(self._h, C.c_void_p(frame_ptr), channels, pitch, C.byref(fill), mem))
+        return fill.value
+
+    def raw_window_detect(self, params, result, mem):
+        """params: MdLiveParams, result: MdLiveResult with device (or pinned host) pointers / NULLs; counts land in `result`."""
+        self._ck(lib().md_window_detect(self._h, C.byref(params), C.byref(result), mem))
+
     def window_detect(self, num_motions=2, sigma=0.5, distance_threshold=50.0, seed=1, iters=50, min_cluster_size=5):
         lp = MdLiveParams()
         lib().md_live_params_default(C.byref(lp))

@@ -55,6 +55,20 @@ def test_adapter_classes_end_to_end(oracle, tmp_path):
     n, res, cols, outl, thr = oracle.fit_subspace(traj, num_motions=2, sigma=0.5, seed=3)
     assert n == ninl and int(outl.sum()) == nout
 
+    # FlowClusterer::clusterEuclidean over the adapter == the oracle's literal loop on the same outlier points
+    nc = int(take(np.int32, 1)[0])
+    got_clusters = []
+    for _ in range(nc):
+        sz = int(take(np.int32, 1)[0])
+        box = take(np.int32, 4).copy()
+        got_clusters.append((sz, box, take(np.float32, 2 * sz).reshape(sz, 2).copy()))
+    opts = take(np.float32, 2 * int(nout)).reshape(int(nout), 2)
+    lab, nall, boxes, sizes, ids = oracle.cluster_euclidean(opts, 50.0, 5)
+    assert nc == len(boxes)
+    for c, (sz, box, members) in enumerate(got_clusters):
+        assert sz == sizes[c] and np.array_equal(box, boxes[c])
+        assert np.array_equal(members, opts[lab == ids[c]])
+
     vf_ok = take(np.int32, 1)[0]
     U = take(np.float32, w * h).reshape(h, w)
     V = take(np.float32, w * h).reshape(h, w)

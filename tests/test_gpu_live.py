@@ -117,3 +117,35 @@ def test_window_ring_equals_fresh_tracking(capi):
         idx = np.nonzero(ref["len"] == F)[0]
         assert np.array_equal(got["traj_index"], idx)
         assert np.array_equal(got["traj"], ref["traj"][idx])
+
+
+def test_live_node_mirrors_image_callback(capi, oracle):
+    """LiveNode = imageCallback without ROS: skip_frames, window fill, frame counters and the CSV rows of the logger."""
+    from motion_detection_b200.node import LiveNode
+    w, h, nm, skip = 320, 240, 1, 2
+    F = 2 * nm + 1
+    frames, _ = synth.sequence(w, h, 11, seed=9, blobs=2)
+    rgb = np.repeat(frames[..., None], 3, axis=3)                  # the node converts to "rgb8" (node.cpp:271)
+    node = LiveNode(w, h, num_motions=nm, skip_frames=skip, sigma=1.0, distance_threshold=50.0, seed=4)
+    kept, ncb = [], 0
+    for g in range(len(frames)):
+        res = node.on_image(rgb[g])
+        if g % skip:
+            assert res is None
+            continue
+        kept.append(g)
+        if len(kept) < F:
+            assert res is None
+            continue
+        assert res is not None and res["frame"] == g
+        win = [frames[i] for i in kept[-F:]]                       # weights sum to 2^15: gray(rgb replicated) == gray
+        ref = oracle.live_detect(win, num_motions=nm, sigma=1.0, distance_threshold=50.0, seed=4 + ncb)
+        ncb += 1
+        assert abs(res["num_trajectories"] - ref["num_trajectories"]) <= 0.005 * ref["num_trajectories"] + 1
+        n2, _, cols2, outl2, _ = oracle.fit_subspace(res["traj"], num_motions=nm, sigma=1.0, seed=3 + ncb)
+        assert np.array_equal(res["outlier"], outl2)
+    assert node.callbacks == ncb and node.frame_number == ncb and node.global_frame_count == len(frames)
+    for row in node.log_rows:
+        f = [int(v) for v in row.split(", ")]
+        assert len(f) == 6 and f[0] in kept and f[4] > f[2] and f[5] > f[3]
+    node.close()
