@@ -80,43 +80,25 @@ __device__ int sub_rand(SubRand &st)
     return (int)out;
 }
 
-// one-sided (Hestenes) Jacobi, same sweep order and formulas as the oracle's hestenes()
-__device__ void hestenes(double *A, int n, int d, double *norms)
+// ordered sum x_0 + x_1 + ... + x_{n-1} of one value per lane (the oracle's serial accumulation order), on every lane
+__device__ __forceinline__ double sub_ordered_sum(double x, int n)
 {
-    for (int sweep = 0; sweep < 60; sweep++) {
-        int rotated = 0;
-        for (int pc = 0; pc < d - 1; pc++)
-            for (int q = pc + 1; q < d; q++) {
-                double a = 0, b = 0, g = 0;
-                for (int i = 0; i < n; i++) {
-                    a = __dadd_rn(a, __dmul_rn(A[pc * n + i], A[pc * n + i]));
-                    b = __dadd_rn(b, __dmul_rn(A[q * n + i], A[q * n + i]));
-                    g = __dadd_rn(g, __dmul_rn(A[pc * n + i], A[q * n + i]));
-                }
-                if (g == 0 || fabs(g) <= __dmul_rn(1e-15, __dsqrt_rn(__dmul_rn(a, b)))) continue;
-                rotated = 1;
-                const double zeta = __ddiv_rn(__dsub_rn(b, a), __dmul_rn(2.0, g));
-                const double t = __ddiv_rn(zeta >= 0 ? 1.0 : -1.0,
-                                           __dadd_rn(fabs(zeta), __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(zeta, zeta)))));
-                const double c = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(t, t)))), s = __dmul_rn(c, t);
-                for (int i = 0; i < n; i++) {
-                    const double vp = A[pc * n + i], vq = A[q * n + i];
-                    A[pc * n + i] = __dsub_rn(__dmul_rn(c, vp), __dmul_rn(s, vq));
-                    A[q * n + i] = __dadd_rn(__dmul_rn(s, vp), __dmul_rn(c, vq));
-                }
-            }
-        if (!rotated) break;
-    }
-    for (int k = 0; k < d; k++) {
-        double a = 0;
-        for (int i = 0; i < n; i++) a = __dadd_rn(a, __dmul_rn(A[k * n + i], A[k * n + i]));
-        norms[k] = __dsqrt_rn(a);
-    }
+    double a = 0;
+    for (int i = 0; i < n; i++) a = __dadd_rn(a, __shfl_sync(0xffffffffu, x, i));
+    return a;
 }
 
-__global__ void __launch_bounds__(64) k_sub_hyp(const SubParams p)
+// One WARP per hypothesis: the sampled columns live in shared memory (A[k * n + i], lane i owns row i), the one-sided
+// (Hestenes) Jacobi runs the oracle's sweep order and formulas -- the three dot products are accumulated in the oracle's
+// serial order (products formed in parallel, summed in order through shuffles), the rotation angle is computed
+// redundantly on every lane, the rotation itself and the projector update are element-parallel.  Bit-identical to
+// oracle/md_oracle_subspace.c:hestenes(); the serial one-thread-per-hypothesis version spent 0.4 ms in local-memory latency.
+__global__ void __launch_bounds__(128) k_sub_hyp(const SubParams p)
 {
-    extern __shared__ int s_cols[];      // [iters][d]
+    extern __shared__ double s_hyp[];            // [warps][d * n] doubles, then [iters * d] ints
+    const int n = p.n, d = p.d, warps = blockDim.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int *s_cols = reinterpret_cast<int *>(s_hyp + (size_t)warps * n * d);
     if (threadIdx.x == 0) {
         SubRand st;
         sub_srand(st, p.seed);
@@ -125,27 +107,58 @@ __global__ void __launch_bounds__(64) k_sub_hyp(const SubParams p)
     }
     __syncthreads();
     const float xm = (float)p.mean[0], ym = (float)p.mean[1];
-    const int n = p.n, d = p.d;
-    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < p.iters; it += gridDim.x * blockDim.x) {
-        double A[SUB_MAXN * SUB_MAXN], norms[SUB_MAXN];
-        for (int k = 0; k < d; k++) {
+    double *A = s_hyp + (size_t)warp * n * d;
+    for (int it = blockIdx.x * warps + warp; it < p.iters; it += gridDim.x * warps) {
+        __syncwarp();
+        for (int e = lane; e < n * d; e += 32) {
+            const int k = e / n, i = e - k * n;
             int c = s_cols[it * d + k];
             c = c < 0 ? 0 : (c >= p.T ? p.T - 1 : c);
-            p.cols[it * d + k] = c;
-            for (int i = 0; i < n; i++) A[k * n + i] = sub_datum(p, i, c, xm, ym);
+            if (i == 0) p.cols[it * d + k] = c;
+            A[e] = sub_datum(p, i, c, xm, ym);
         }
-        hestenes(A, n, d, norms);
-        double smax = 0;
-        for (int k = 0; k < d; k++) if (norms[k] > smax) smax = norms[k];
-        double *P = p.P + (size_t)it * n * n;
-        for (int i = 0; i < n; i++)
-            for (int j = 0; j < n; j++) P[i * n + j] = i == j ? 1.0 : 0.0;
+        __syncwarp();
+        const bool row = lane < n;
+        for (int sweep = 0; sweep < 60; sweep++) {
+            int rotated = 0;
+            for (int pc = 0; pc < d - 1; pc++)
+                for (int q = pc + 1; q < d; q++) {
+                    const double vp = row ? A[pc * n + lane] : 0.0, vq = row ? A[q * n + lane] : 0.0;
+                    const double a = sub_ordered_sum(__dmul_rn(vp, vp), n), b = sub_ordered_sum(__dmul_rn(vq, vq), n),
+                                 g = sub_ordered_sum(__dmul_rn(vp, vq), n);
+                    if (g == 0 || fabs(g) <= __dmul_rn(1e-15, __dsqrt_rn(__dmul_rn(a, b)))) continue;      // warp-uniform
+                    rotated = 1;
+                    const double zeta = __ddiv_rn(__dsub_rn(b, a), __dmul_rn(2.0, g));
+                    const double t = __ddiv_rn(zeta >= 0 ? 1.0 : -1.0,
+                                               __dadd_rn(fabs(zeta), __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(zeta, zeta)))));
+                    const double c = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(t, t)))), sn = __dmul_rn(c, t);
+                    if (row) {
+                        A[pc * n + lane] = __dsub_rn(__dmul_rn(c, vp), __dmul_rn(sn, vq));
+                        A[q * n + lane] = __dadd_rn(__dmul_rn(sn, vp), __dmul_rn(c, vq));
+                    }
+                }
+            if (!rotated) break;
+        }
+        __syncwarp();
+        double norm_mine = 0, smax = 0;          // lane k keeps the norm of column k (d <= 32)
         for (int k = 0; k < d; k++) {
-            if (!(norms[k] > __dmul_rn(1e-12, smax)) || norms[k] == 0) continue;
-            const double inv = __ddiv_rn(1.0, norms[k]);
-            for (int i = 0; i < n; i++)
-                for (int j = 0; j < n; j++)
-                    P[i * n + j] = __dsub_rn(P[i * n + j], __dmul_rn(__dmul_rn(A[k * n + i], inv), __dmul_rn(A[k * n + j], inv)));
+            const double v = row ? A[k * n + lane] : 0.0;
+            const double nk = __dsqrt_rn(sub_ordered_sum(__dmul_rn(v, v), n));
+            if (lane == k) norm_mine = nk;
+            if (nk > smax) smax = nk;
+        }
+        double *P = p.P + (size_t)it * n * n;
+        for (int e0 = 0; e0 < n * n; e0 += 32) {
+            const int e = e0 + lane, i = e / n, jj = e - i * n;
+            const bool act = e < n * n;
+            double val = i == jj ? 1.0 : 0.0;
+            for (int k = 0; k < d; k++) {
+                const double nk = __shfl_sync(0xffffffffu, norm_mine, k);
+                if (!(nk > __dmul_rn(1e-12, smax)) || nk == 0) continue;
+                const double inv = __ddiv_rn(1.0, nk);
+                if (act) val = __dsub_rn(val, __dmul_rn(__dmul_rn(A[k * n + i], inv), __dmul_rn(A[k * n + jj], inv)));
+            }
+            if (act) P[e] = val;
         }
     }
 }
@@ -153,37 +166,50 @@ __global__ void __launch_bounds__(64) k_sub_hyp(const SubParams p)
 __device__ __forceinline__ double sub_residual(const double *P, const double *dcol, int n)
 {
     double acc = 0;
+#pragma unroll
     for (int r = 0; r < n; r++) {
         double pr = 0;
+#pragma unroll
         for (int c = 0; c < n; c++) pr = __dadd_rn(pr, __dmul_rn(P[r * n + c], dcol[c]));
         acc = __dadd_rn(acc, __dmul_rn(dcol[r], pr));
     }
     return fabs(acc);
 }
 
-// all hypotheses against all trajectories; HB hypotheses' projectors per shared-memory pass
+// all hypotheses against all trajectories: blockIdx.y = group of `hb` hypotheses (projectors in shared memory), two
+// hypotheses per inner step (two independent f64 chains per thread)
+template <int N>                        // N = 2F known at compile time (the datum column stays in registers), 0 = any
 __global__ void __launch_bounds__(256) k_sub_score(const SubParams p, int hb)
 {
     extern __shared__ double s_P[];      // [hb][n*n]
-    const int n = p.n, nn = n * n;
+    const int n = N ? N : p.n, nn = n * n;
     const float xm = (float)p.mean[0], ym = (float)p.mean[1];
     const double inl_thr = __dmul_rn(__dmul_rn((double)(n - p.d), p.sigma), p.sigma);
     const int lane = threadIdx.x & 31;
     const int Tr = (p.T + 31) & ~31;
-    for (int h0 = 0; h0 < p.iters; h0 += hb) {
-        const int nh = min(hb, p.iters - h0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < nh * nn; i += blockDim.x) s_P[i] = p.P[(size_t)h0 * nn + i];
-        __syncthreads();
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Tr; i += gridDim.x * blockDim.x) {
-            double dcol[SUB_MAXN];
-            const bool act = i < p.T;
-            if (act) for (int r = 0; r < n; r++) dcol[r] = sub_datum(p, r, i, xm, ym);
-            for (int j = 0; j < nh; j++) {
-                const bool inl = act && sub_residual(s_P + j * nn, dcol, n) < inl_thr;
-                const unsigned bal = __ballot_sync(0xffffffffu, inl);
-                if (lane == 0 && bal) atomicAdd(&p.counts[h0 + j], __popc(bal));
-            }
+    const int h0 = blockIdx.y * hb;
+    const int nh = min(hb, p.iters - h0);
+    if (nh <= 0) return;
+    for (int i = threadIdx.x; i < nh * nn; i += blockDim.x) s_P[i] = p.P[(size_t)h0 * nn + i];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Tr; i += gridDim.x * blockDim.x) {
+        double dcol[N ? N : SUB_MAXN];
+        const bool act = i < p.T;
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < n; r++) dcol[r] = sub_datum(p, r, i, xm, ym);
+        }
+        int j = 0;
+        for (; j + 1 < nh; j += 2) {
+            const double r0 = act ? sub_residual(s_P + j * nn, dcol, n) : 0.0, r1 = act ? sub_residual(s_P + (j + 1) * nn, dcol, n) : 0.0;
+            const unsigned b0 = __ballot_sync(0xffffffffu, act && r0 < inl_thr), b1 = __ballot_sync(0xffffffffu, act && r1 < inl_thr);
+            if (lane == 0 && b0) atomicAdd(&p.counts[h0 + j], __popc(b0));
+            if (lane == 0 && b1) atomicAdd(&p.counts[h0 + j + 1], __popc(b1));
+        }
+        if (j < nh) {
+            const bool inl = act && sub_residual(s_P + j * nn, dcol, n) < inl_thr;
+            const unsigned bal = __ballot_sync(0xffffffffu, inl);
+            if (lane == 0 && bal) atomicAdd(&p.counts[h0 + j], __popc(bal));
         }
     }
 }
@@ -278,17 +304,26 @@ int sub_enqueue(md_ctx *ctx, const float *d_traj, int T, int F, int num_motions,
     p.forced_cols = forced_host ? ws->forced : nullptr; p.mean = ws->mean; p.P = ws->P; p.cols = ws->cols; p.counts = ws->counts;
     p.residual = d_res; p.outlier = d_out; p.best_cols = d_best; p.num_inliers = d_ninl ? d_ninl : ws->ninl;
     k_sub_mean<<<1, 1024, 0, s>>>(p);
-    const size_t cols_smem = sizeof(int) * iters * d;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sub_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem);
-    k_sub_hyp<<<1, 64, cols_smem, s>>>(p);
-    int hb = (int)(96 * 1024 / (sizeof(double) * n * n));
+    const size_t hyp_smem = sizeof(double) * 4 * n * d + sizeof(int) * iters * d;       // 4 warps per block
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sub_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyp_smem);
+    k_sub_hyp<<<(iters + 3) / 4, 128, hyp_smem, s>>>(p);
+    int hb = 8;                                    // hypotheses per block (projectors: 8 n^2 doubles <= 64 KB)
     if (hb > iters) hb = iters;
-    if (hb < 1) hb = 1;
     const size_t psm = sizeof(double) * (size_t)hb * n * n;
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sub_score, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
     int nb = (T + 255) / 256;
     if (nb > 592) nb = 592;
-    k_sub_score<<<nb, 256, psm, s>>>(p, hb);
+    const dim3 sgrid(nb, (iters + hb - 1) / hb);
+    auto score = [&](auto kern) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm);
+        kern<<<sgrid, 256, psm, s>>>(p, hb);
+    };
+    switch (n) {                                   // F = 3, 5, 7, 9 <-> num_motions 1..4 of the launch files
+        case 6: score(k_sub_score<6>); break;
+        case 10: score(k_sub_score<10>); break;
+        case 14: score(k_sub_score<14>); break;
+        case 18: score(k_sub_score<18>); break;
+        default: score(k_sub_score<0>); break;
+    }
     k_sub_final<<<nb, 256, sizeof(double) * n * n, s>>>(p);
     MD_COUNT_LAUNCH(4);
     if (e == cudaSuccess) e = cudaGetLastError();
