@@ -173,12 +173,7 @@ std::vector<std::vector<cv::Point2f> > OutlierDetector::fitSubspace(const std::v
     const int T = (int)trajectories.size();
     if (T < 1) return basis;                       // the reference dereferences trajectories[0] unguarded (:239)
     const int F = (int)trajectories[0].size();
-    if (!ctx_) {
-        md_config cfg;
-        md_config_default(&cfg);
-        cfg.width = 64; cfg.height = 64;           // geometry is irrelevant for the subspace fit
-        if (md_create(&cfg, device_, &ctx_) != MD_OK) { ctx_ = 0; return basis; }
-    }
+    if (!ensureContext()) return basis;
     std::vector<float> traj(2 * (size_t)T * F);
     for (int i = 0; i < T; i++)
         for (int f = 0; f < F; f++) { traj[((size_t)i * F + f) * 2] = trajectories[i][f].x; traj[((size_t)i * F + f) * 2 + 1] = trajectories[i][f].y; }
@@ -231,6 +226,48 @@ int VarFlow::CalcFlow(IplImage *imgA, IplImage *imgB, IplImage *imgU, IplImage *
         std::memcpy(imgV->imageData + (size_t)y * imgV->widthStep, &V[(size_t)y * width], sizeof(float) * width);
     }
     return 1;
+}
+
+bool OutlierDetector::ensureContext()
+{
+    if (ctx_) return true;
+    md_config cfg;
+    md_config_default(&cfg);
+    cfg.width = 64; cfg.height = 64;               // geometry is irrelevant for the subspace fit and the MAD test
+    if (md_create(&cfg, device_, &ctx_) != MD_OK) { ctx_ = 0; return false; }
+    return true;
+}
+
+void OutlierDetector::findOutliers(const cv::Mat &optical_flow_vectors, cv::Mat &outlier_probabilities, bool include_zeros,
+                                   int pixel_step, bool print)
+{
+    (void)print;
+    const int rows = optical_flow_vectors.rows, cols = optical_flow_vectors.cols;
+    outlier_probabilities = cv::Mat::zeros(rows, cols, CV_64F);                              // :41
+    if (rows < 1 || cols < 1 || pixel_step < 1 || optical_flow_vectors.type() != CV_64FC4 || !ensureContext()) return;
+    std::vector<double> dxdy;
+    for (int i = 0; i < rows; i += pixel_step)                                               // the reference's traversal, :77-84
+        for (int j = 0; j < cols; j += pixel_step) {
+            const cv::Vec4d &e = optical_flow_vectors.at<cv::Vec4d>(i, j);
+            dxdy.push_back(e[2]); dxdy.push_back(e[3]);
+        }
+    const int n = (int)(dxdy.size() / 2);
+    std::vector<uint8_t> flag(n);
+    if (md_find_outliers(ctx_, dxdy.data(), n, include_zeros ? 1 : 0, flag.data(), 0, MD_MEM_HOST) != MD_OK) return;
+    int k = 0;
+    for (int i = 0; i < rows; i += pixel_step)
+        for (int j = 0; j < cols; j += pixel_step, k++)
+            if (flag[k]) outlier_probabilities.at<double>(i, j) = 1.0;
+}
+
+void OutlierDetector::getOutlierVectors(const cv::Mat &optical_flow_vectors, const cv::Mat &outlier_probabilities, cv::Mat &outlier_vectors,
+                                        int pixel_step)
+{
+    outlier_vectors = cv::Mat::zeros(optical_flow_vectors.rows, optical_flow_vectors.cols, CV_64FC4);
+    if (optical_flow_vectors.type() != CV_64FC4 || pixel_step < 1) return;
+    for (int i = 0; i < optical_flow_vectors.rows; i += pixel_step)
+        for (int j = 0; j < optical_flow_vectors.cols; j += pixel_step)
+            if (outlier_probabilities.at<double>(i, j) > 0.5) outlier_vectors.at<cv::Vec4d>(i, j) = optical_flow_vectors.at<cv::Vec4d>(i, j);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -40,6 +40,23 @@ int main(int argc, char **argv)
     for (int x = 0; x < w; x += 10)
         for (int y = 0; y < h; y += 10) put(fo, &flow.at<cv::Vec4d>(y, x), sizeof(cv::Vec4d));
 
+    // --- findOutliers on that flow field (detectOutliers, node.cpp:112-121)
+    {
+        OutlierDetector odm;
+        cv::Mat prob, outv;
+        odm.findOutliers(flow, prob, false, 10);
+        odm.getOutlierVectors(flow, prob, outv, 10);
+        int32_t nflag = 0, nvec = 0;
+        for (int y = 0; y < h; y += 10)
+            for (int x = 0; x < w; x += 10) {
+                if (prob.at<double>(y, x) > 0.5) nflag++;
+                const cv::Vec4d &e = outv.at<cv::Vec4d>(y, x);
+                if (e[2] != 0.0 || e[3] != 0.0) nvec++;
+            }
+        int32_t m[2] = {nflag, nvec};
+        put(fo, m, sizeof m);
+    }
+
     // --- calculateOpticalFlowTrajectory + fitSubspace, the live path (node.cpp:94-110, 348)
     cv::Mat flow2 = cv::Mat::zeros(h, w, CV_32FC4), comp2;
     std::vector<std::vector<cv::Point2f> > traj;

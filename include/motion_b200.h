@@ -228,6 +228,15 @@ int md_fit_subspace(md_ctx *ctx, const float *traj, int32_t T, int32_t F, int32_
                     uint32_t seed, const int32_t *forced_cols, int32_t iters, float *residual, int32_t *best_cols,
                     uint8_t *outlier, int32_t *num_inliers, int mem);
 
+/* ---- OutlierDetector::findOutliers / createMask (common/src/outlier_detector.cpp:37-186) ---------------------------- */
+/* The median / MAD test on the angles atan2(dy, dx) and magnitudes sqrt(dy^2 + dx^2) of the grid's flow vectors.
+ * flow_dxdy [n][2] f64 = components 2, 3 of the Vec4d field at the grid points (zero for filtered / failed vectors,
+ * cpp:99-115); include_zeros = 0 leaves zero vectors out of the statistics (:132-139).  outlier[n] = 1 where
+ * 0.6745 |v - median| / MAD > 3.5 for the angle or the magnitude (= outlier_probabilities > 0.5, :54-70).
+ * stats4 (nullable): median angle, MAD angle, median magnitude, MAD magnitude. */
+int md_find_outliers(md_ctx *ctx, const double *flow_dxdy, int32_t n, int32_t include_zeros, uint8_t *outlier,
+                     double *stats4, int mem);
+
 /* ---- VarFlow::CalcFlow (common/src/VarFlow.cpp:600-697) with the varFlow() parameters (cpp:422-429) ----------- */
 /* A, B gray u8; U (+x) and V (y-UP, VarFlow.cpp:103-107) f32 [h][w] dense. */
 int md_varflow(md_ctx *ctx, const uint8_t *A, const uint8_t *B, int32_t pitch, float *U, float *V, int mem);

@@ -25,7 +25,7 @@ SYMBOLS = [
     "md_pyramid_read", "md_pyramid_read_deriv", "md_lk_flow", "md_fit_egomotion", "md_motion_mask",
     "md_process_batch", "md_process_pair", "md_track_trajectories", "md_fit_subspace", "md_varflow", "md_stats_get",
     "md_stats_reset", "md_profile", "md_profile_read", "md_live_params_default", "md_window_reset", "md_window_push",
-    "md_window_detect", "md_cluster_points",
+    "md_window_detect", "md_cluster_points", "md_find_outliers",
 ]
 
 
@@ -330,6 +330,14 @@ class Context:
         self._ck(lib().md_cluster_points(self._h, _ptr(pts), n, C.c_double(distance_threshold), min_cluster_size, _ptr(labels),
                                          C.byref(nall), C.byref(k), _ptr(boxes), _ptr(sizes), _ptr(ids), MD_MEM_HOST))
         return labels[:n], nall.value, boxes[:k.value], sizes[:k.value], ids[:k.value]
+
+    def find_outliers(self, dxdy, include_zeros=False):
+        dxdy = np.ascontiguousarray(dxdy, np.float64).reshape(-1, 2)
+        n = len(dxdy)
+        out = np.zeros(n, np.uint8)
+        stats = np.zeros(4, np.float64)
+        self._ck(lib().md_find_outliers(self._h, _ptr(dxdy), n, 1 if include_zeros else 0, _ptr(out), _ptr(stats), MD_MEM_HOST))
+        return out, stats
 
     def varflow(self, A, B):
         A = np.ascontiguousarray(A, np.uint8)

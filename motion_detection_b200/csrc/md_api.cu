@@ -147,6 +147,7 @@ static void free_ctx(md_ctx *ctx)
     for (void *p : ptrs) if (p) cudaFree(p);
     vf_free_workspace(ctx->vf_ws);
     sub_free_workspace(ctx->sub_ws);
+    mad_free_workspace(ctx->mad_ws);
     live_free(ctx->live_ws);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 8; i++) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]); }

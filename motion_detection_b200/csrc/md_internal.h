@@ -182,12 +182,14 @@ struct md_ctx {
     int16_t *d_phase;     // [max_batch] pair arenas of phase planes, allocated on the first grid-mode LK call
     int phase_state;      // 0 = not tried, 1 = ready, -1 = not used (not worth it / allocation failed)
     void *sub_ws;         // fitSubspace workspace (k_subspace.cu)
+    void *mad_ws;         // findOutliers workspace (k_mad.cu)
     void *live_ws;        // live-path workspace (md_api.cu: md_window_*)
     void *vf_ws;          // VarFlow workspace (k_varflow.cu), allocated on the first md_varflow call
 };
 
 void vf_free_workspace(void *ws);
 void sub_free_workspace(void *ws);
+void mad_free_workspace(void *ws);
 int sub_enqueue(md_ctx *ctx, const float *d_traj, int T, int F, int num_motions, double sigma, uint32_t seed,
                 const int32_t *forced_host, int iters, float *d_res, uint8_t *d_out, int *d_best, int *d_ninl);
 int vf_compute_device(md_ctx *ctx, const uint8_t *dA, const uint8_t *dB, int dpitch);

@@ -106,3 +106,58 @@ int orc_bounding_boxes(const float *pts, int n, const int32_t *labels, int nclus
     free(cnt); free(bb);
     return out;
 }
+
+/* ---- OutlierDetector::findOutliers / createMask (common/src/outlier_detector.cpp:37-186), literal ------------------------ */
+static int cmp_double(const void *a, const void *b)
+{
+    const double x = *(const double *)a, y = *(const double *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+static double orc_median(const double *v, int n)            /* getMedian :99-121 (takes its vector by value and sorts it) */
+{
+    double *t = (double *)malloc(sizeof(double) * (size_t)n);
+    memcpy(t, v, sizeof(double) * (size_t)n);
+    qsort(t, (size_t)n, sizeof(double), cmp_double);
+    const double m = (n % 2 == 0) ? (t[n / 2 - 1] + t[n / 2]) / 2.0 : t[(n - 1) / 2];
+    free(t);
+    return m;
+}
+/* one createMask pass (:122-186) over `values`; mask is OR-ed; returns the number of participating vectors */
+static int orc_create_mask(const double *dxdy, const double *values, int n, int include_zeros, uint8_t *mask, double *median_out,
+                           double *mad_out)
+{
+    double *vals = (double *)malloc(sizeof(double) * (size_t)(n > 0 ? n : 1));
+    int m = 0;
+    for (int i = 0; i < n; i++)
+        if (include_zeros || fabs(dxdy[2 * i]) > 0.0 || fabs(dxdy[2 * i + 1]) > 0.0) vals[m++] = values[i];
+    if (m == 0) { free(vals); return 0; }
+    const double median = orc_median(vals, m);
+    for (int i = 0; i < m; i++) vals[i] = fabs(vals[i] - median);
+    const double mad = orc_median(vals, m);
+    int index = 0;
+    for (int i = 0; i < n; i++)
+        if (include_zeros || fabs(dxdy[2 * i]) > 0.0 || fabs(dxdy[2 * i + 1]) > 0.0) {
+            const double z = 0.6745 * vals[index] / mad;
+            if (fabs(z) > 3.5) mask[i] = 1;
+            index++;
+        }
+    *median_out = median; *mad_out = mad;
+    free(vals);
+    return m;
+}
+/* findOutliers (:37-52): angle pass, then magnitude pass into the same mask.  stats4: median/MAD angle, median/MAD magnitude */
+int orc_find_outliers(const double *dxdy, int n, int include_zeros, uint8_t *outlier, double *stats4)
+{
+    double *ang = (double *)malloc(sizeof(double) * (size_t)n), *mag = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        const double dx = dxdy[2 * i], dy = dxdy[2 * i + 1];
+        ang[i] = atan2(dy, dx);                                  /* :82 */
+        mag[i] = sqrt(dy * dy + dx * dx);                        /* :94 */
+    }
+    memset(outlier, 0, (size_t)n);
+    stats4[0] = stats4[1] = stats4[2] = stats4[3] = 0;
+    int m = orc_create_mask(dxdy, ang, n, include_zeros, outlier, &stats4[0], &stats4[1]);
+    orc_create_mask(dxdy, mag, n, include_zeros, outlier, &stats4[2], &stats4[3]);
+    free(ang); free(mag);
+    return m;
+}

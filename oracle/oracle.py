@@ -47,6 +47,7 @@ def lib():
         _LIB.orc_fit_subspace.restype = C.c_int
         _LIB.orc_cluster_euclidean.restype = C.c_int
         _LIB.orc_bounding_boxes.restype = C.c_int
+        _LIB.orc_find_outliers.restype = C.c_int
     return _LIB
 
 
@@ -338,3 +339,13 @@ def live_detect(frames, pixel_step=10, num_motions=2, sigma=0.5, distance_thresh
     out.update(subspace_inliers=n, residual=res, best_cols=cols, outlier=outl, outlier_points=opts, labels=labels,
                num_clusters_all=ncl, boxes=boxes, cluster_sizes=sizes, cluster_ids=ids)
     return out
+
+
+def find_outliers(dxdy, include_zeros=False):
+    """OutlierDetector::findOutliers (outlier_detector.cpp:37-186): (outlier u8 [n], stats [median/MAD angle, median/MAD mag])."""
+    dxdy = np.ascontiguousarray(dxdy, np.float64).reshape(-1, 2)
+    n = len(dxdy)
+    out = np.zeros(n, np.uint8)
+    stats = np.zeros(4, np.float64)
+    lib().orc_find_outliers(dxdy.ctypes.data_as(f64p), n, 1 if include_zeros else 0, out.ctypes.data_as(u8p), stats.ctypes.data_as(f64p))
+    return out, stats

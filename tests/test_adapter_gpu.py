@@ -49,6 +49,12 @@ def test_adapter_classes_end_to_end(oracle, tmp_path):
     if failed.any():
         assert (flow[failed, 0] == -1).mean() > 0.9                                   # failed points: (-1,-1,0,0), cpp:112-115
 
+    # findOutliers over the adapter == the oracle's createMask on the same (dx, dy) field (row-major grid traversal)
+    nflag, nvec = take(np.int32, 2)
+    g = flow.reshape(w // 10, h // 10, 4).transpose(1, 0, 2).reshape(-1, 4)
+    mad_ref, _ = oracle.find_outliers(g[:, 2:4], False)
+    assert abs(int(nflag) - int(mad_ref.sum())) <= 1 and nvec <= nflag
+
     nv2, ntraj, nout, nbasis, ninl = take(np.int32, 5)
     traj = take(np.float32, int(ntraj) * F * 2).reshape(int(ntraj), F, 2)
     assert ntraj > 0.7 * P and nbasis == 8 and 0 < ninl <= ntraj

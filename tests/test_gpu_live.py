@@ -149,3 +149,39 @@ def test_live_node_mirrors_image_callback(capi, oracle):
         f = [int(v) for v in row.split(", ")]
         assert len(f) == 6 and f[0] in kept and f[4] > f[2] and f[5] > f[3]
     node.close()
+
+
+@pytest.mark.parametrize("n,incl", [(20736, False), (20736, True), (3072, False), (501, True), (2, False), (1, True), (300000, False)])
+def test_find_outliers_matches_oracle(capi, oracle, n, incl):
+    """findOutliers / createMask: exact medians by radix select.  Magnitudes are bit-exact; angles go through atan2 (device
+    libm vs glibc, <= 2 ulp), so the angle statistics are compared to 1e-14 relative and the flags must agree except where a
+    z-score sits within 1e-9 of the 3.5 threshold."""
+    rng = np.random.default_rng(n)
+    d = rng.normal([1.2, -0.8], 0.15, (n, 2)).astype(np.float32).astype(np.float64)
+    d[rng.random(n) < 0.2] = 0.0
+    d[rng.random(n) < 0.03] += rng.normal(0, 2.0, 2)
+    ctx = _ctx(capi, 640, 480)
+    got, gst = ctx.find_outliers(d, incl)
+    ref, rst = oracle.find_outliers(d, incl)
+    assert gst[2] == rst[2] and gst[3] == rst[3]                       # magnitude median / MAD: bit-exact
+    assert np.allclose(gst[:2], rst[:2], rtol=1e-14, atol=1e-15)
+    diff = np.nonzero(got != ref)[0]
+    if len(diff):
+        sel = np.ones(n, bool) if incl else (np.abs(d) > 0).any(1)
+        ang = np.arctan2(d[:, 1], d[:, 0])
+        z = 0.6745 * np.abs(ang - rst[0]) / rst[1]
+        assert np.all(np.abs(z[diff] - 3.5) < 1e-9) and sel[diff].all()
+
+
+def test_find_outliers_degenerate(capi, oracle):
+    ctx = _ctx(capi, 640, 480)
+    z = np.zeros((100, 2))
+    got, st = ctx.find_outliers(z, False)                              # no participating vector
+    assert got.sum() == 0 and np.all(st == 0)
+    got, st = ctx.find_outliers(z, True)                               # MAD = 0: 0 / 0 is not > 3.5
+    ref, rst = oracle.find_outliers(z, True)
+    assert np.array_equal(got, ref) and got.sum() == 0
+    d = np.tile([[1.0, 0.0]], (50, 1)); d[7] = [5.0, 0.0]             # MAD = 0 and one mover: x / 0 = inf > 3.5
+    got, st = ctx.find_outliers(d, False)
+    ref, rst = oracle.find_outliers(d, False)
+    assert np.array_equal(got, ref) and got[7] == 1 and got.sum() == 1

@@ -142,3 +142,29 @@ def test_traj_step_bookkeeping():
     assert ln.tolist() == [2, 1, 1, 1]
     assert cur.tolist() == [[21, 21], [30, 30], [40, 40], [50, 50]]
     assert traj[0, 1].tolist() == [21, 21]
+
+
+def test_find_outliers_against_numpy_statistics():
+    """orc_find_outliers is the literal createMask loop; numpy's median / MAD give the same statistics and flags."""
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    for n, incl in [(500, False), (501, True), (64, False), (1, False)]:
+        d = rng.normal([1.2, -0.8], 0.1, (n, 2)).astype(np.float32).astype(np.float64)
+        d[rng.random(n) < 0.2] = 0.0                                   # filtered / failed vectors are stored as zeros
+        d[rng.random(n) < 0.05] += 3.0                                 # movers
+        out, st = O.find_outliers(d, incl)
+        sel = np.ones(n, bool) if incl else (np.abs(d) > 0).any(1)
+        if not sel.any():
+            assert out.sum() == 0
+            continue
+        ang, mag = np.arctan2(d[:, 1], d[:, 0]), np.sqrt(d[:, 1] ** 2 + d[:, 0] ** 2)
+        flags = np.zeros(n, bool)
+        for q, v in enumerate((ang, mag)):
+            med = np.median(v[sel]); mad = np.median(np.abs(v[sel] - med))
+            assert st[2 * q] == med and st[2 * q + 1] == mad
+            with np.errstate(divide="ignore", invalid="ignore"):
+                flags |= sel & (np.abs(0.6745 * np.abs(v - med) / mad) > 3.5)
+        assert np.array_equal(out.astype(bool), flags)
+    # no participating vector: nothing is flagged (vals.empty() return, outlier_detector.cpp:142-145)
+    out, st = O.find_outliers(np.zeros((10, 2)), False)
+    assert out.sum() == 0
