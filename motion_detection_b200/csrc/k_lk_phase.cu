@@ -273,7 +273,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_lk_phase(const LkParams p, co
     }
 }
 
-cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pairs, cudaStream_t s)
+// the phase planes of the PREVIOUS frames of `pairs` pairs (k_lk_phase reads them); may run on another stream than LK
+cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s)
 {
     PhParams q;
     q.g = p.g; q.pg = p.pg; q.img = p.img; q.der = p.der; q.ph = p.ph; q.prev_slot0 = p.prev_slot0; q.pair0 = p.ph_pair0;
@@ -285,6 +286,15 @@ cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pair
         k_phase_planes<<<grid, 256, 0, s>>>(q, l);
     }
     MD_COUNT_LAUNCH(p.g.nlev);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pairs, cudaStream_t s)
+{
+    if (!p.ph_ready) {
+        cudaError_t e0 = launch_lk_planes(p, pairs, s);
+        if (e0 != cudaSuccess) return e0;
+    }
     constexpr int WARPS = 7;
     const size_t smem = (size_t)WARPS * PhTile::WARP_BYTES + 128;
     cudaError_t e = cudaFuncSetAttribute(k_lk_phase<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

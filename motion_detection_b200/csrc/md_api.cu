@@ -151,6 +151,11 @@ static void free_ctx(md_ctx *ctx)
     live_free(ctx->live_ws);
     for (int i = 0; i < 5; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int i = 0; i < 8; i++) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_comp[i]) cudaEventDestroy(ctx->ev_comp[i]); }
+    for (int i = 0; i < 8; i++) { if (ctx->ev_k1[i]) cudaEventDestroy(ctx->ev_k1[i]); if (ctx->ev_lk[i]) cudaEventDestroy(ctx->ev_lk[i]); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux_pyr) cudaStreamDestroy(ctx->aux_pyr);
+    if (ctx->aux_post) cudaStreamDestroy(ctx->aux_post);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
     if (ctx->copy_out) cudaStreamDestroy(ctx->copy_out);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -184,9 +189,21 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
     ctx->stream = ctx->own_stream;
     bool sok = cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking) == cudaSuccess &&
                cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking) == cudaSuccess;
+    {
+        // the side streams of the kernel pipeline outrank the LK stream: their small kernels are dispatched as soon as an SM
+        // has room, instead of queueing behind LK's tens of thousands of CTAs
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        sok = sok && cudaStreamCreateWithPriority(&ctx->aux_pyr, cudaStreamNonBlocking, hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&ctx->aux_post, cudaStreamNonBlocking, hi) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    }
     for (int i = 0; i < 8 && sok; i++)
         sok = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_k1[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_lk[i], cudaEventDisableTiming) == cudaSuccess;
     if (!sok) { free_ctx(ctx); return MD_ERR_CUDA; }
 
     const int w = cfg->width, h = cfg->height, B = cfg->max_batch;
@@ -421,6 +438,7 @@ static void fill_lk(md_ctx *ctx, LkParams &p, int prev_slot0, int next_slot0, co
     p.pg = ctx->pg;
     p.ph = (!pts_in && ensure_phase(ctx)) ? ctx->d_phase : nullptr;
     p.ph_pair0 = ph_pair0;
+    p.ph_ready = 0;
     p.img = ctx->d_img; p.der = ctx->d_der;
     p.prev_slot0 = prev_slot0; p.next_slot0 = next_slot0;
     p.pts_in = pts_in;
@@ -571,11 +589,21 @@ extern "C" int md_motion_mask(md_ctx *ctx, const uint8_t *prev, const uint8_t *c
 }
 
 // ---- the chain -------------------------------------------------------------------------------------------------------
-// Runs K2 -> K3 -> K4 for pairs [p0, p1) of the current batch (pyramids of the frames involved are already built).
-static int run_pairs(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint8_t *d_status, uint8_t *d_keep, uint8_t *d_mask,
-                     int mask_pitch, long long mask_stride, bool want_mask, cudaStream_t s)
+// the sub-pixel phase planes of pairs [p0, p1) (grid-mode LK only); they depend on the pyramids of the pairs' first frames
+static int run_planes(md_ctx *ctx, int prev0, int p0, int p1, cudaStream_t s)
 {
-    const int P = ctx->P, ns = ctx->g.nslots, n = p1 - p0, it = ctx->cfg.ransac_iters;
+    if (ctx->cfg.flow_engine == MD_FLOW_VARFLOW) return MD_OK;
+    const int ns = ctx->g.nslots;
+    LkParams lp;
+    fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, ctx->P, ctx->d_next, ctx->d_status, p0);
+    if (lp.ph && ctx->ph_maps.valid && lp.win == 40) CK(launch_lk_planes(lp, p1 - p0, s));
+    return MD_OK;
+}
+
+// K2 for pairs [p0, p1) of the current batch (pyramids of the frames involved are already built) on stream s
+static int run_flow(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint8_t *d_status, cudaStream_t s, bool planes_done = false)
+{
+    const int P = ctx->P, ns = ctx->g.nslots, n = p1 - p0;
     if (ctx->cfg.flow_engine == MD_FLOW_VARFLOW) {
         // dense variational flow per pair, sampled at the grid points (the gray frames are the level-0 planes)
         for (int q = p0; q < p1; q++) {
@@ -586,9 +614,17 @@ static int run_pairs(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uin
     } else {
         LkParams lp;
         fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P, p0);
+        lp.ph_ready = planes_done ? 1 : 0;
         CK(launch_lk(lp, &ctx->lk_maps, &ctx->ph_maps, n, s));
     }
-    if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], s));
+    return MD_OK;
+}
+
+// K3 -> K4 for pairs [p0, p1) on stream s
+static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint8_t *d_status, uint8_t *d_keep, uint8_t *d_mask,
+                    int mask_pitch, long long mask_stride, bool want_mask, cudaStream_t s)
+{
+    const int P = ctx->P, ns = ctx->g.nslots, n = p1 - p0, it = ctx->cfg.ransac_iters;
     EgoParams ep;
     fill_ego(ctx, ep, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P, d_keep + (size_t)p0 * P, 0, ctx->cfg.ego_mode,
              ctx->cfg.seed + (uint32_t)ctx->pair_counter + (uint32_t)p0, nullptr, nullptr, nullptr);
@@ -613,7 +649,19 @@ static int run_pairs(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uin
     return MD_OK;
 }
 
-#define MD_PIPE_CHUNKS 5      // 1 + 3 even + 1; measured: 4 even chunks 2 032 pairs/s, 8 even 1 887 (per-chunk LK tails), unpipelined 1 918
+// The batch is cut into chunks and software-pipelined.  K2 (LK) is instruction-issue bound and fills the GPU; the pyramid
+// build (K1, bandwidth bound), the egomotion fit (K3, a chain of small latency-bound kernels) and the mask (K4) of the
+// neighbouring chunks run beside it on two higher-priority streams, so their latencies hide behind LK instead of
+// adding up per chunk.  With host buffers the H2D of chunk i+1 and the D2H of chunk i-1 overlap as well (PCIe is full
+// duplex; the results are complete on return).
+//   copy_in : H2D(c)                                (host buffers only)
+//   aux_pyr : K1(c) + phase planes(c)  after H2D(c) / after the work already queued on the context's stream
+//   stream  : LK(c)                                 after K1(c)
+//   aux_post: K3(c), K4(c)     after LK(c)
+//   copy_out: D2H(c)           after K4(c)          (host buffers only)
+// The context's stream joins aux_post at the end, so the call stays stream-ordered for the caller.
+#define MD_PIPE_CHUNKS_DEVICE 2   // device-resident frames: measured 3 445 pairs/s with 2 even chunks, 3 397 unchunked, 3 342 with 6
+#define MD_PIPE_CHUNKS 7      // host buffers: measured e2e 2 826 / 3 080 / 3 149 / 3 184 pairs/s with 2 / 4 / 5 / 7 chunks; a short first chunk (its K1 / H2D is exposed), even middle chunks, a short last chunk (its K3 / K4 / D2H is)
 
 extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outputs *out, int mem)
 {
@@ -630,78 +678,128 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
     const int w = ctx->cfg.width, h = ctx->cfg.height, P = ctx->P, ns = ctx->g.nslots;
     const int prev0 = ctx->slot_base;
     const int new0 = fr->chain ? (prev0 + 1) % ns : prev0;
+    const bool host = mem != MD_MEM_DEVICE;
+    const bool want_mask = out->mask != nullptr;
+    int r;
 
-    if (mem == MD_MEM_DEVICE) {
-        // stream-ordered, no host synchronisation: everything is enqueued on the context's stream
-        float2 *d_next = out->next_pts ? (float2 *)out->next_pts : ctx->d_next;
-        uint8_t *d_status = out->status ? out->status : ctx->d_status;
-        uint8_t *d_keep = out->keep ? out->keep : ctx->d_keep;
-        if (ctx->profile) CK(cudaEventRecord(ctx->ev[0], s));
-        CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, new0, fr->count, fr->data, fr->channels, fr->pitch, fr->frame_stride, s));
-        if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], s));
-        int r = run_pairs(ctx, prev0, 0, pairs, d_next, d_status, d_keep, out->mask ? out->mask : ctx->d_mask,
-                          out->mask ? out->mask_pitch : ctx->fpitch, out->mask ? out->mask_stride : (long long)ctx->fpitch * h,
-                          out->mask != nullptr, s);
+    // where the frames and the results live on the device
+    const uint8_t *df = fr->data;
+    int dp = fr->pitch;
+    long long ds = fr->frame_stride;
+    float2 *d_next = ctx->d_next;
+    uint8_t *d_status = ctx->d_status, *d_keep = ctx->d_keep, *d_mask = ctx->d_mask;
+    int mpitch = ctx->fpitch;
+    long long mstride = (long long)ctx->fpitch * h;
+    if (host) {
+        r = ensure_frames(ctx, fr->channels);
         if (r != MD_OK) return r;
-        if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors, ctx->d_M, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
-        if (out->H) CK(cudaMemcpyAsync(out->H, ctx->d_H, sizeof(double) * 9 * pairs, cudaMemcpyDeviceToDevice, s));
-        if (out->inliers) CK(cudaMemcpyAsync(out->inliers, ctx->d_inliers, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
+        df = ctx->d_frames; dp = ctx->fpitch * fr->channels; ds = (long long)dp * h;
     } else {
-        // Host buffers: the batch is cut into chunks and software-pipelined over three streams -- H2D of chunk i+1 and
-        // D2H of chunk i-1 overlap the kernels of chunk i (PCIe is full duplex; the results are complete on return).
-        int r = ensure_frames(ctx, fr->channels);
-        if (r != MD_OK) return r;
-        const int dp = ctx->fpitch * fr->channels;
-        const long long ds = (long long)dp * h;
-        const long long mstride = (long long)ctx->fpitch * h;
-        // chunk boundaries: a short first chunk (its H2D is exposed) and a short last chunk (its D2H is exposed) around
-        // MD_PIPE_CHUNKS - 2 even middle chunks
-        int bounds[MD_PIPE_CHUNKS + 3];
-        int nch = 0;
-        bounds[0] = 0;
-        if (ctx->profile || pairs < 2) { nch = 1; bounds[1] = pairs; }
-        else if (pairs < 8) { nch = 2; bounds[1] = pairs / 2; bounds[2] = pairs; }
-        else {
-            const int mid = MD_PIPE_CHUNKS - 2 > 0 ? MD_PIPE_CHUNKS - 2 : 1;
+        if (out->next_pts) d_next = (float2 *)out->next_pts;
+        if (out->status) d_status = out->status;
+        if (out->keep) d_keep = out->keep;
+        if (out->mask) { d_mask = out->mask; mpitch = out->mask_pitch; mstride = out->mask_stride; }
+    }
+
+    // chunk boundaries
+    int bounds[12];                   // at most 8 chunks (the per-chunk events)
+    int nch = 0;
+    bounds[0] = 0;
+    const bool serial = ctx->profile || pairs < 2 || ctx->cfg.flow_engine == MD_FLOW_VARFLOW;
+    if (serial) { nch = 1; bounds[1] = pairs; }
+    else if (pairs < 8) { nch = 2; bounds[1] = pairs / 2; bounds[2] = pairs; }
+    else {
+        static int tuned = -1;                     // MD_PIPE_CHUNKS=<2..7> in the environment overrides the default (tuning aid)
+        if (tuned < 0) { const char *e = getenv("MD_PIPE_CHUNKS"); tuned = e ? atoi(e) : 0; if (tuned < 2 || tuned > 8) tuned = 0; }
+        const int total = tuned ? tuned : (host ? MD_PIPE_CHUNKS : MD_PIPE_CHUNKS_DEVICE);
+        if (host) {
+            // a short first chunk (its H2D is exposed) and a short last chunk (its D2H is exposed) around even middle chunks
+            const int mid = total - 2 > 0 ? total - 2 : 1;
             bounds[++nch] = 1;
             for (int i = 1; i <= mid; i++) bounds[++nch] = 1 + (int)((long long)(pairs - 2) * i / mid);
             bounds[++nch] = pairs;
+        } else {
+            // device-resident frames: even chunks; only the small latency-bound kernels of K3 are worth hiding
+            for (int i = 1; i <= total; i++) bounds[++nch] = (int)((long long)pairs * i / total);
         }
-        auto d2h = [&](int p0, int p1) -> int {
-            const int n = p1 - p0;
-            cudaStream_t so = ctx->copy_out;
-            if (out->next_pts) CK(cudaMemcpyAsync(out->next_pts + (size_t)2 * p0 * P, ctx->d_next + (size_t)p0 * P, sizeof(float2) * P * n, cudaMemcpyDeviceToHost, so));
-            if (out->status) CK(cudaMemcpyAsync(out->status + (size_t)p0 * P, ctx->d_status + (size_t)p0 * P, (size_t)P * n, cudaMemcpyDeviceToHost, so));
-            if (out->keep) CK(cudaMemcpyAsync(out->keep + (size_t)p0 * P, ctx->d_keep + (size_t)p0 * P, (size_t)P * n, cudaMemcpyDeviceToHost, so));
-            if (out->H) CK(cudaMemcpyAsync(out->H + 9 * p0, ctx->d_H + 9 * p0, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, so));
-            if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors + p0, ctx->d_M + p0, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
-            if (out->inliers) CK(cudaMemcpyAsync(out->inliers + p0, ctx->d_inliers + p0, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
-            if (out->mask) {
-                if (out->mask_stride == (long long)out->mask_pitch * h)
-                    CK(cudaMemcpy2DAsync(out->mask + p0 * out->mask_stride, out->mask_pitch, ctx->d_mask + p0 * mstride, ctx->fpitch, w,
-                                         (size_t)h * n, cudaMemcpyDeviceToHost, so));
-                else
-                    for (int b = p0; b < p1; b++)
-                        CK(cudaMemcpy2DAsync(out->mask + b * out->mask_stride, out->mask_pitch, ctx->d_mask + b * mstride, ctx->fpitch, w, h,
-                                             cudaMemcpyDeviceToHost, so));
-            }
-            return MD_OK;
-        };
-        int fdone = 0, pprev0 = 0, pprev1 = 0;
-        for (int i = 0; i < nch; i++) {
-            const int p0 = bounds[i], p1 = bounds[i + 1];
-            const int fa = fdone, fb = fr->chain ? p1 : p1 + 1;
+    }
+    cudaStream_t s_pyr = serial ? s : ctx->aux_pyr, s_post = serial ? s : ctx->aux_post;
+
+    auto d2h = [&](int p0, int p1) -> int {
+        const int n = p1 - p0;
+        cudaStream_t so = ctx->copy_out;
+        if (out->next_pts) CK(cudaMemcpyAsync(out->next_pts + (size_t)2 * p0 * P, ctx->d_next + (size_t)p0 * P, sizeof(float2) * P * n, cudaMemcpyDeviceToHost, so));
+        if (out->status) CK(cudaMemcpyAsync(out->status + (size_t)p0 * P, ctx->d_status + (size_t)p0 * P, (size_t)P * n, cudaMemcpyDeviceToHost, so));
+        if (out->keep) CK(cudaMemcpyAsync(out->keep + (size_t)p0 * P, ctx->d_keep + (size_t)p0 * P, (size_t)P * n, cudaMemcpyDeviceToHost, so));
+        if (out->H) CK(cudaMemcpyAsync(out->H + 9 * p0, ctx->d_H + 9 * p0, sizeof(double) * 9 * n, cudaMemcpyDeviceToHost, so));
+        if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors + p0, ctx->d_M + p0, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
+        if (out->inliers) CK(cudaMemcpyAsync(out->inliers + p0, ctx->d_inliers + p0, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
+        if (out->mask) {
+            if (out->mask_stride == (long long)out->mask_pitch * h)
+                CK(cudaMemcpy2DAsync(out->mask + p0 * out->mask_stride, out->mask_pitch, ctx->d_mask + p0 * mstride, ctx->fpitch, w,
+                                     (size_t)h * n, cudaMemcpyDeviceToHost, so));
+            else
+                for (int b = p0; b < p1; b++)
+                    CK(cudaMemcpy2DAsync(out->mask + b * out->mask_stride, out->mask_pitch, ctx->d_mask + b * mstride, ctx->fpitch, w, h,
+                                         cudaMemcpyDeviceToHost, so));
+        }
+        return MD_OK;
+    };
+
+    static int trace_env = -1;
+    if (trace_env < 0) { const char *e = getenv("MD_TRACE"); trace_env = e ? atoi(e) : 0; }
+    const bool trace = trace_env > 0 && !serial;
+    cudaEvent_t tev[8][6];            // per chunk: K1 begin, K1+planes end, LK begin, LK end, post begin, post end
+    cudaEvent_t tev0 = nullptr;
+    if (trace) {
+        cudaEventCreate(&tev0);
+        for (int i = 0; i < nch; i++) for (int k = 0; k < 6; k++) cudaEventCreate(&tev[i][k]);
+    }
+    if (!serial) {
+        if (trace) cudaEventRecord(tev0, s);
+        // fork: the side streams start after whatever the caller already queued on the context's stream
+        CK(cudaEventRecord(ctx->ev_fork, s));
+        CK(cudaStreamWaitEvent(s_pyr, ctx->ev_fork, 0));
+        CK(cudaStreamWaitEvent(s_post, ctx->ev_fork, 0));
+    }
+    int fdone = 0, pprev0 = 0, pprev1 = 0;
+    for (int i = 0; i < nch; i++) {
+        const int p0 = bounds[i], p1 = bounds[i + 1];
+        const int fa = fdone, fb = fr->chain ? p1 : p1 + 1;          // new frames this chunk needs
+        if (host) {
             for (int f = fa; f < fb; f++)
                 CK(cudaMemcpy2DAsync(ctx->d_frames + f * ds, dp, fr->data + f * fr->frame_stride, fr->pitch, (size_t)w * fr->channels, h,
                                      cudaMemcpyHostToDevice, ctx->copy_in));
             CK(cudaEventRecord(ctx->ev_in[i], ctx->copy_in));
-            CK(cudaStreamWaitEvent(s, ctx->ev_in[i], 0));
-            if (ctx->profile) CK(cudaEventRecord(ctx->ev[0], s));
-            CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, (new0 + fa) % ns, fb - fa, ctx->d_frames + fa * ds, fr->channels, dp, ds, s));
-            if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], s));
-            r = run_pairs(ctx, prev0, p0, p1, ctx->d_next, ctx->d_status, ctx->d_keep, ctx->d_mask, ctx->fpitch, mstride, out->mask != nullptr, s);
+            CK(cudaStreamWaitEvent(s_pyr, ctx->ev_in[i], 0));
+        }
+        if (ctx->profile) CK(cudaEventRecord(ctx->ev[0], s));
+        if (trace) cudaEventRecord(tev[i][0], s_pyr);
+        if (fb > fa) CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, (new0 + fa) % ns, fb - fa, df + fa * ds, fr->channels, dp, ds, s_pyr));
+        if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], s));
+        if (!serial) {
+            // the phase planes ride with the pyramids on the side stream: the context's stream runs LK kernels back to back
+            r = run_planes(ctx, prev0, p0, p1, s_pyr);
             if (r != MD_OK) return r;
-            CK(cudaEventRecord(ctx->ev_comp[i], s));
+            if (trace) cudaEventRecord(tev[i][1], s_pyr);
+            CK(cudaEventRecord(ctx->ev_k1[i], s_pyr));
+            CK(cudaStreamWaitEvent(s, ctx->ev_k1[i], 0));
+        }
+        if (trace) cudaEventRecord(tev[i][2], s);
+        r = run_flow(ctx, prev0, p0, p1, d_next, d_status, s, !serial);
+        if (r != MD_OK) return r;
+        if (trace) cudaEventRecord(tev[i][3], s);
+        if (ctx->profile) CK(cudaEventRecord(ctx->ev[2], s));
+        if (!serial) {
+            CK(cudaEventRecord(ctx->ev_lk[i], s));
+            CK(cudaStreamWaitEvent(s_post, ctx->ev_lk[i], 0));
+        }
+        if (trace) cudaEventRecord(tev[i][4], s_post);
+        r = run_post(ctx, prev0, p0, p1, d_next, d_status, d_keep, d_mask, mpitch, mstride, want_mask, s_post);
+        if (r != MD_OK) return r;
+        if (trace) cudaEventRecord(tev[i][5], s_post);
+        if (host) {
+            CK(cudaEventRecord(ctx->ev_comp[i], s_post));
             // results of the PREVIOUS chunk are copied out only now, so that (with pageable host memory, where the copy call
             // blocks) this chunk's kernels are already queued behind it
             if (i > 0) {
@@ -709,13 +807,36 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
                 r = d2h(pprev0, pprev1);
                 if (r != MD_OK) return r;
             }
-            fdone = fb; pprev0 = p0; pprev1 = p1;
         }
+        fdone = fb; pprev0 = p0; pprev1 = p1;
+    }
+    if (!serial) {
+        // join: everything of this call is ordered before later work on the context's stream
+        CK(cudaEventRecord(ctx->ev_join, s_post));
+        CK(cudaStreamWaitEvent(s, ctx->ev_join, 0));
+    }
+    if (trace) {
+        cudaStreamSynchronize(s);
+        for (int i = 0; i < nch; i++) {
+            float t[6];
+            for (int k = 0; k < 6; k++) cudaEventElapsedTime(&t[k], tev0, tev[i][k]);
+            fprintf(stderr, "[md trace] chunk %d pairs %2d..%2d  K1+planes %.3f-%.3f  LK %.3f-%.3f  K3+K4 %.3f-%.3f ms\n", i, bounds[i],
+                    bounds[i + 1], t[0], t[1], t[2], t[3], t[4], t[5]);
+            for (int k = 0; k < 6; k++) cudaEventDestroy(tev[i][k]);
+        }
+        cudaEventDestroy(tev0);
+        trace_env--;                  // MD_TRACE=n traces the next n calls
+    }
+    if (host) {
         CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[nch - 1], 0));
         r = d2h(pprev0, pprev1);
         if (r != MD_OK) return r;
         CK(cudaStreamSynchronize(ctx->copy_out));
         CK(cudaStreamSynchronize(s));
+    } else {
+        if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors, ctx->d_M, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
+        if (out->H) CK(cudaMemcpyAsync(out->H, ctx->d_H, sizeof(double) * 9 * pairs, cudaMemcpyDeviceToDevice, s));
+        if (out->inliers) CK(cudaMemcpyAsync(out->inliers, ctx->d_inliers, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
     }
     ctx->slot_base = (prev0 + pairs) % ns;
     ctx->have_cached = 1;

@@ -90,6 +90,7 @@ struct LkParams {
     PhaseGeom pg;
     int16_t *ph;
     int ph_pair0;            // pair b of this launch uses arena ph_pair0 + b
+    int ph_ready;            // 1 = the planes were already computed (launch_lk_planes on another stream)
 };
 
 struct EgoParams {
@@ -143,6 +144,8 @@ struct md_ctx {
     cudaStream_t own_stream, stream;
     cudaStream_t copy_in, copy_out;     // H2D / D2H streams of the pipelined host-memory path
     cudaEvent_t ev_in[8], ev_comp[8];
+    cudaStream_t aux_pyr, aux_post;     // side streams of the kernel pipeline (K1 / K3+K4 beside LK), higher priority
+    cudaEvent_t ev_k1[8], ev_lk[8], ev_fork, ev_join;
     std::string err;
     int sm_count;
 
@@ -212,6 +215,7 @@ cudaError_t launch_compact_outliers(const float2 *traj_c, const uint8_t *outlier
 cudaError_t launch_cluster(const float2 *pts, const int *n_ptr, int n_max, double thr, int min_size, float *m2, int *cand, int *ncand,
                            int *label, int *nclusters, int *sizes, int *box, int *nout, int32_t *out_box, int32_t *out_size,
                            int32_t *out_id, cudaStream_t s);
+cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s);
 cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pairs, cudaStream_t s);
 cudaError_t launch_traj_step(float2 *pts_cur, const float2 *next, const uint8_t *status, float2 *traj, int32_t *len,
                              int P, int F, int w, int h, cudaStream_t s);
