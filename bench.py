@@ -399,6 +399,20 @@ def main():
                 "note": "LK with a 40x40 window is ALU/shared-memory bound by construction (1600 taps x levels x iterations "
                         "per point); its HBM fraction is small by design, see stages[] for the HBM-bound kernels (K1, K4)"}
 
+    # LK is bound by instruction issue, not by bytes: report that roofline beside the HBM one.  Instructions per tracked point
+    # come from the committed ncu capture (profiles/traffic.json "k_lk_warp_instr_per_point"); the time is measured here.
+    try:
+        ipp = json.load(open(tp)).get("k_lk_warp_instr_per_point")
+    except Exception:
+        ipp = None
+    if ipp and a.pixel_step == 10 and (w, h) == (1920, 1080):
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        peak_issue = 148 * 4 * sm_mhz * 1e6                       # one warp instruction per scheduler per clock
+        ach = ipp * P * B / (stage_ms[1] * 1e-3)
+        roofline["issue"] = {"bound": "instruction issue (148 SMs x 4 schedulers x SM clock)", "achieved": ach / 1e9, "peak": peak_issue / 1e9,
+                             "unit": "G warp-instr/s", "frac": ach / peak_issue, "warp_instr_per_point": ipp,
+                             "source": "ncu smsp__inst_executed.sum of k_lk_phase / tracked points (profiles/r01_lk_phase_ncu_full.txt)"}
+
     # ---- e2e: C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
     e2e = None
     if not a.no_e2e:
