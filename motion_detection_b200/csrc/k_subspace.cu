@@ -88,78 +88,87 @@ __device__ __forceinline__ double sub_ordered_sum(double x, int n)
     return a;
 }
 
-// One WARP per hypothesis: the sampled columns live in shared memory (A[k * n + i], lane i owns row i), the one-sided
-// (Hestenes) Jacobi runs the oracle's sweep order and formulas -- the three dot products are accumulated in the oracle's
-// serial order (products formed in parallel, summed in order through shuffles), the rotation angle is computed
-// redundantly on every lane, the rotation itself and the projector update are element-parallel.  Bit-identical to
-// oracle/md_oracle_subspace.c:hestenes(); the serial one-thread-per-hypothesis version spent 0.4 ms in local-memory latency.
-__global__ void __launch_bounds__(128) k_sub_hyp(const SubParams p)
+// One BLOCK per hypothesis, one warp per column pair.  The sampled columns live in shared memory (A[k * n + i], lane i
+// owns row i).  The one-sided (Hestenes) Jacobi runs the oracle's ROUND-ROBIN sweep order: a round is d/2 disjoint column
+// pairs whose rotations commute exactly, so the warps of the block rotate them concurrently and the result is
+// bit-identical to the oracle's sequential loop (oracle/md_oracle_subspace.c:hestenes).  Inside a pair the three dot
+// products are accumulated in the oracle's serial order (products in parallel, ordered sum through shuffles), the
+// rotation angle is computed redundantly on every lane, the rotation itself is element-parallel.
+__global__ void __launch_bounds__(512) k_sub_hyp(const SubParams p)
 {
-    extern __shared__ double s_hyp[];            // [warps][d * n] doubles, then [iters * d] ints
-    const int n = p.n, d = p.d, warps = blockDim.x >> 5;
+    extern __shared__ double s_hyp[];            // [d * n] doubles, [32] norms, then [d] ints
+    const int n = p.n, d = p.d, nwarps = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int *s_cols = reinterpret_cast<int *>(s_hyp + (size_t)warps * n * d);
+    double *A = s_hyp, *s_norm = s_hyp + (size_t)n * d;
+    int *s_cols = reinterpret_cast<int *>(s_norm + 32);
+    const int it = blockIdx.x;
     if (threadIdx.x == 0) {
-        SubRand st;
-        sub_srand(st, p.seed);
-        for (int i = 0; i < 310; i++) (void)sub_rand(st);
-        for (int i = 0; i < p.iters * p.d; i++) s_cols[i] = p.forced_cols ? p.forced_cols[i] : sub_rand(st) % p.T;
+        // fillSubset (:223-234): the draws of hypothesis `it` are draws it*d .. it*d+d-1 of the stream
+        if (p.forced_cols) {
+            for (int k = 0; k < d; k++) s_cols[k] = p.forced_cols[it * d + k];
+        } else {
+            SubRand st;
+            sub_srand(st, p.seed);
+            for (int i = 0; i < 310 + it * d; i++) (void)sub_rand(st);
+            for (int k = 0; k < d; k++) s_cols[k] = sub_rand(st) % p.T;
+        }
     }
     __syncthreads();
     const float xm = (float)p.mean[0], ym = (float)p.mean[1];
-    double *A = s_hyp + (size_t)warp * n * d;
-    for (int it = blockIdx.x * warps + warp; it < p.iters; it += gridDim.x * warps) {
-        __syncwarp();
-        for (int e = lane; e < n * d; e += 32) {
-            const int k = e / n, i = e - k * n;
-            int c = s_cols[it * d + k];
-            c = c < 0 ? 0 : (c >= p.T ? p.T - 1 : c);
-            if (i == 0) p.cols[it * d + k] = c;
-            A[e] = sub_datum(p, i, c, xm, ym);
-        }
-        __syncwarp();
-        const bool row = lane < n;
-        for (int sweep = 0; sweep < 60; sweep++) {
-            int rotated = 0;
-            for (int pc = 0; pc < d - 1; pc++)
-                for (int q = pc + 1; q < d; q++) {
-                    const double vp = row ? A[pc * n + lane] : 0.0, vq = row ? A[q * n + lane] : 0.0;
-                    const double a = sub_ordered_sum(__dmul_rn(vp, vp), n), b = sub_ordered_sum(__dmul_rn(vq, vq), n),
-                                 g = sub_ordered_sum(__dmul_rn(vp, vq), n);
-                    if (g == 0 || fabs(g) <= __dmul_rn(1e-15, __dsqrt_rn(__dmul_rn(a, b)))) continue;      // warp-uniform
-                    rotated = 1;
-                    const double zeta = __ddiv_rn(__dsub_rn(b, a), __dmul_rn(2.0, g));
-                    const double t = __ddiv_rn(zeta >= 0 ? 1.0 : -1.0,
-                                               __dadd_rn(fabs(zeta), __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(zeta, zeta)))));
-                    const double c = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(t, t)))), sn = __dmul_rn(c, t);
-                    if (row) {
-                        A[pc * n + lane] = __dsub_rn(__dmul_rn(c, vp), __dmul_rn(sn, vq));
-                        A[q * n + lane] = __dadd_rn(__dmul_rn(sn, vp), __dmul_rn(c, vq));
-                    }
+    for (int e = threadIdx.x; e < n * d; e += blockDim.x) {
+        const int k = e / n, i = e - k * n;
+        int c = s_cols[k];
+        c = c < 0 ? 0 : (c >= p.T ? p.T - 1 : c);
+        if (i == 0) p.cols[it * d + k] = c;
+        A[e] = sub_datum(p, i, c, xm, ym);
+    }
+    __syncthreads();
+    const bool row = lane < n;
+    const int de = d + (d & 1), m = de - 1;
+    for (int sweep = 0; sweep < 60; sweep++) {
+        int rotated = 0;
+        for (int r = 0; r < m; r++) {
+            for (int i = warp; i < de / 2; i += nwarps) {
+                int pc = i == 0 ? r : (r + i) % m, q = i == 0 ? m : (r - i + m) % m;
+                if (pc > q) { const int t = pc; pc = q; q = t; }
+                if (q >= d || pc == q) continue;
+                const double vp = row ? A[pc * n + lane] : 0.0, vq = row ? A[q * n + lane] : 0.0;
+                const double a = sub_ordered_sum(__dmul_rn(vp, vp), n), b = sub_ordered_sum(__dmul_rn(vq, vq), n),
+                             g = sub_ordered_sum(__dmul_rn(vp, vq), n);
+                if (g == 0 || fabs(g) <= __dmul_rn(1e-15, __dsqrt_rn(__dmul_rn(a, b)))) continue;          // warp-uniform
+                rotated = 1;
+                const double zeta = __ddiv_rn(__dsub_rn(b, a), __dmul_rn(2.0, g));
+                const double t = __ddiv_rn(zeta >= 0 ? 1.0 : -1.0,
+                                           __dadd_rn(fabs(zeta), __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(zeta, zeta)))));
+                const double c = __ddiv_rn(1.0, __dsqrt_rn(__dadd_rn(1.0, __dmul_rn(t, t)))), sn = __dmul_rn(c, t);
+                if (row) {
+                    A[pc * n + lane] = __dsub_rn(__dmul_rn(c, vp), __dmul_rn(sn, vq));
+                    A[q * n + lane] = __dadd_rn(__dmul_rn(sn, vp), __dmul_rn(c, vq));
                 }
-            if (!rotated) break;
-        }
-        __syncwarp();
-        double norm_mine = 0, smax = 0;          // lane k keeps the norm of column k (d <= 32)
-        for (int k = 0; k < d; k++) {
-            const double v = row ? A[k * n + lane] : 0.0;
-            const double nk = __dsqrt_rn(sub_ordered_sum(__dmul_rn(v, v), n));
-            if (lane == k) norm_mine = nk;
-            if (nk > smax) smax = nk;
-        }
-        double *P = p.P + (size_t)it * n * n;
-        for (int e0 = 0; e0 < n * n; e0 += 32) {
-            const int e = e0 + lane, i = e / n, jj = e - i * n;
-            const bool act = e < n * n;
-            double val = i == jj ? 1.0 : 0.0;
-            for (int k = 0; k < d; k++) {
-                const double nk = __shfl_sync(0xffffffffu, norm_mine, k);
-                if (!(nk > __dmul_rn(1e-12, smax)) || nk == 0) continue;
-                const double inv = __ddiv_rn(1.0, nk);
-                if (act) val = __dsub_rn(val, __dmul_rn(__dmul_rn(A[k * n + i], inv), __dmul_rn(A[k * n + jj], inv)));
             }
-            if (act) P[e] = val;
+            __syncthreads();                     // the next round pairs the columns differently
         }
+        if (!__syncthreads_or(rotated)) break;
+    }
+    for (int k = warp; k < d; k += nwarps) {
+        const double v = row ? A[k * n + lane] : 0.0;
+        const double nk = __dsqrt_rn(sub_ordered_sum(__dmul_rn(v, v), n));
+        if (lane == 0) s_norm[k] = nk;
+    }
+    __syncthreads();
+    double smax = 0;
+    for (int k = 0; k < d; k++) if (s_norm[k] > smax) smax = s_norm[k];
+    double *P = p.P + (size_t)it * n * n;
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, jj = e - i * n;
+        double val = i == jj ? 1.0 : 0.0;
+        for (int k = 0; k < d; k++) {
+            const double nk = s_norm[k];
+            if (!(nk > __dmul_rn(1e-12, smax)) || nk == 0) continue;
+            const double inv = __ddiv_rn(1.0, nk);
+            val = __dsub_rn(val, __dmul_rn(__dmul_rn(A[k * n + i], inv), __dmul_rn(A[k * n + jj], inv)));
+        }
+        P[e] = val;
     }
 }
 
@@ -304,9 +313,9 @@ int sub_enqueue(md_ctx *ctx, const float *d_traj, int T, int F, int num_motions,
     p.forced_cols = forced_host ? ws->forced : nullptr; p.mean = ws->mean; p.P = ws->P; p.cols = ws->cols; p.counts = ws->counts;
     p.residual = d_res; p.outlier = d_out; p.best_cols = d_best; p.num_inliers = d_ninl ? d_ninl : ws->ninl;
     k_sub_mean<<<1, 1024, 0, s>>>(p);
-    const size_t hyp_smem = sizeof(double) * 4 * n * d + sizeof(int) * iters * d;       // 4 warps per block
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sub_hyp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hyp_smem);
-    k_sub_hyp<<<(iters + 3) / 4, 128, hyp_smem, s>>>(p);
+    const size_t hyp_smem = sizeof(double) * ((size_t)n * d + 32) + sizeof(int) * d;
+    const int hyp_warps = (d + 1) / 2 < 1 ? 1 : (d + 1) / 2;                              // one warp per column pair of a round
+    k_sub_hyp<<<iters, 32 * hyp_warps, hyp_smem, s>>>(p);
     int hb = 8;                                    // hypotheses per block (projectors: 8 n^2 doubles <= 64 KB)
     if (hb > iters) hb = iters;
     const size_t psm = sizeof(double) * (size_t)hb * n * n;

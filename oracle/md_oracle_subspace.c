@@ -25,30 +25,44 @@
 /* chi_square_table p99, outlier_detector.cpp:19-30 */
 static const double CHI2_P99[10] = {0.0, 0.020, 0.115, 0.297, 0.554, 0.872, 1.239, 1.646, 2.088, 2.558};
 
-/* Orthonormal basis of span(A[:, 0..d)) by one-sided Jacobi; A is n x d column-major in f64 (destroyed).
- * On return column k of A is sigma_k * u_k; norms[k] = sigma_k. Fixed sweep order -> deterministic. */
+/* Orthonormal basis of span(A[:, 0..d)) by one-sided (Hestenes) Jacobi; A is n x d column-major in f64 (destroyed).
+ * On return column k of A is sigma_k * u_k; norms[k] = sigma_k.
+ * Sweep order: ROUND-ROBIN.  A sweep is d' - 1 rounds (d' = d rounded up to even) of d'/2 disjoint column pairs -- the
+ * chess-tournament schedule: round r pairs (r, d'-1) and ((r + i) mod (d'-1), (r - i) mod (d'-1)), i = 1 .. d'/2 - 1.
+ * The pairs of a round touch different columns, so their rotations commute EXACTLY: any order (or all at once, as the
+ * device does) gives the same bits.  (The reference uses Eigen's JacobiSVD in f32; any convergent Jacobi order spans the
+ * same subspace -- tests/test_oracle_vs_cv2.py pins the projector against numpy's SVD.) */
+static int jacobi_pair(double *A, int n, int p, int q)
+{
+    double a = 0, b = 0, g = 0;
+    for (int i = 0; i < n; i++) {
+        a += A[p * n + i] * A[p * n + i];
+        b += A[q * n + i] * A[q * n + i];
+        g += A[p * n + i] * A[q * n + i];
+    }
+    if (g == 0 || fabs(g) <= 1e-15 * sqrt(a * b)) return 0;
+    double zeta = (b - a) / (2 * g);
+    double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
+    double c = 1 / sqrt(1 + t * t), s = c * t;
+    for (int i = 0; i < n; i++) {
+        double vp = A[p * n + i], vq = A[q * n + i];
+        A[p * n + i] = c * vp - s * vq;
+        A[q * n + i] = s * vp + c * vq;
+    }
+    return 1;
+}
+
 static void hestenes(double *A, int n, int d, double *norms)
 {
+    const int de = d + (d & 1), m = de - 1;          /* an odd d gets a bye (the pair with the phantom column is skipped) */
     for (int sweep = 0; sweep < 60; sweep++) {
         int rotated = 0;
-        for (int p = 0; p < d - 1; p++)
-            for (int q = p + 1; q < d; q++) {
-                double a = 0, b = 0, g = 0;
-                for (int i = 0; i < n; i++) {
-                    a += A[p * n + i] * A[p * n + i];
-                    b += A[q * n + i] * A[q * n + i];
-                    g += A[p * n + i] * A[q * n + i];
-                }
-                if (g == 0 || fabs(g) <= 1e-15 * sqrt(a * b)) continue;
-                rotated = 1;
-                double zeta = (b - a) / (2 * g);
-                double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1 + zeta * zeta));
-                double c = 1 / sqrt(1 + t * t), s = c * t;
-                for (int i = 0; i < n; i++) {
-                    double vp = A[p * n + i], vq = A[q * n + i];
-                    A[p * n + i] = c * vp - s * vq;
-                    A[q * n + i] = s * vp + c * vq;
-                }
+        for (int r = 0; r < m; r++)
+            for (int i = 0; i < de / 2; i++) {
+                int p = i == 0 ? r : (r + i) % m, q = i == 0 ? m : (r - i + m) % m;
+                if (p > q) { int t = p; p = q; q = t; }
+                if (q >= d || p == q) continue;
+                rotated |= jacobi_pair(A, n, p, q);
             }
         if (!rotated) break;
     }
