@@ -399,7 +399,8 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src, "peak_spec": 8000.0,
+                "frac_of_spec": stages[dom]["gbs"] / 8000.0,
                 "share_of_step": float(stage_ms[dom] / stage_ms.sum()),
                 "note": "LK with a 40x40 window is ALU/shared-memory bound by construction (1600 taps x levels x iterations "
                         "per point); its HBM fraction is small by design, see stages[] for the HBM-bound kernels (K1, K4)"}
@@ -493,6 +494,16 @@ def main():
         dt = time.perf_counter() - t0
         cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d pairs of the same workload in %.1f s (%s)" % (n, dt, how)}
+        if a.flow_engine != "varflow" and cv_chain.have_cv2() and cores > 1:
+            # the same chain on ONE host thread beside the all-threads figure (short sample)
+            import cv2
+            cv2.setNumThreads(1)
+            n1, t1 = 0, time.perf_counter()
+            while time.perf_counter() - t1 < min(4.0, a.cpu_baseline_seconds) and n1 < 200:
+                cpu_pair(n1 % B)
+                n1 += 1
+            cpu["value_1_thread"] = n1 / (time.perf_counter() - t1)
+            cv2.setNumThreads(cores)
 
     if rank == 0:
         line = {
