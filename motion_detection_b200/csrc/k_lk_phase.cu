@@ -13,6 +13,8 @@
 //    (48 % of its instructions) becomes one TMA box load + the integer sums A11, A12, A22, sum I*Ix, sum I*Iy.
 //  * The iteration loop (J tile staged by TMA, dp2a bilinear samples, dp2a mismatch accumulation on packed tap pairs,
 //    REDUX reductions) is the one of k_lk_tma.cu.
+#include <stdlib.h>
+
 #include "lk_tile.cuh"
 #include "tma.h"
 
@@ -116,7 +118,7 @@ struct PhTile {
 };
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) k_lk_phase(const LkParams p, const __grid_constant__ LkPhaseMaps maps)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 14 : WARPS == 2 ? 7 : (WARPS <= 4 ? 3 : (WARPS <= 7 ? 2 : 1))) k_lk_phase(const LkParams p, const __grid_constant__ LkPhaseMaps maps)
 {
     using T = PhTile;
     constexpr int WIN = T::WIN, TW = T::TW, TH = T::TH, NP = T::NP;
@@ -295,12 +297,21 @@ cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pair
         cudaError_t e0 = launch_lk_planes(p, pairs, s);
         if (e0 != cudaSuccess) return e0;
     }
-    constexpr int WARPS = 7;
-    const size_t smem = (size_t)WARPS * PhTile::WARP_BYTES + 128;
-    cudaError_t e = cudaFuncSetAttribute(k_lk_phase<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid((p.P + WARPS - 1) / WARPS, pairs);
-    k_lk_phase<WARPS><<<grid, WARPS * 32, smem, s>>>(p, *maps);
-    MD_COUNT_LAUNCH(1);
-    return cudaGetLastError();
+    static int warps_env = -1;
+    if (warps_env < 0) { const char *e = getenv("MD_LK_WARPS"); warps_env = e ? atoi(e) : 0; }
+    auto go = [&](auto kern, int WARPS) {
+        const size_t smem = (size_t)WARPS * PhTile::WARP_BYTES + 128;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        dim3 grid((p.P + WARPS - 1) / WARPS, pairs);
+        kern<<<grid, WARPS * 32, smem, s>>>(p, *maps);
+        MD_COUNT_LAUNCH(1);
+        return cudaGetLastError();
+    };
+    // One warp per CTA (14 CTAs per SM): a CTA's shared memory is released as soon as its point is done instead of when the
+    // slowest of several points is.  Measured on the default bench (LK ms per 16 pairs): 14 warps per CTA 4.59, 7: 3.92,
+    // 4: 3.94, 2: 3.74, 1: 3.54.  MD_LK_WARPS=2|7 selects the other builds (tuning aid).
+    if (warps_env == 7) return go(k_lk_phase<7>, 7);
+    if (warps_env == 2) return go(k_lk_phase<2>, 2);
+    return go(k_lk_phase<1>, 1);
 }

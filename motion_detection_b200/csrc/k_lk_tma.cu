@@ -16,6 +16,8 @@
 //    registers (an aligned and a one-byte-shifted copy): no byte is ever extracted;
 //  * structure-tensor / mismatch sums: exact int32 per lane, f64 warp-shuffle butterfly, one rounding to f32.
 // Arithmetic is identical to k_lk (k_lk.cu); tap order differs only inside exact integer sums.
+#include <stdlib.h>
+
 #include "lk_tile.cuh"
 #include "tma.h"
 
@@ -38,7 +40,7 @@ struct LkTile {
 };
 
 template <int WIN, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) k_lk_tma(const LkParams p, const __grid_constant__ LkTmaMaps maps)
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) k_lk_tma(const LkParams p, const __grid_constant__ LkTmaMaps maps)
 {
     using T = LkTile<WIN>;
     constexpr int TW = T::TW, TH = T::TH, NP = T::NP;
@@ -199,12 +201,18 @@ __global__ void __launch_bounds__(WARPS * 32, 2) k_lk_tma(const LkParams p, cons
 
 cudaError_t launch_lk_tma(const LkParams &p, const void *maps, int pairs, cudaStream_t s)
 {
-    constexpr int WARPS = 8;
-    const size_t smem = (size_t)WARPS * LkTile<40>::WARP_BYTES + 128;
-    cudaError_t e = cudaFuncSetAttribute(k_lk_tma<40, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    dim3 grid((p.P + WARPS - 1) / WARPS, pairs);
-    k_lk_tma<40, WARPS><<<grid, WARPS * 32, smem, s>>>(p, *reinterpret_cast<const LkTmaMaps *>(maps));
-    MD_COUNT_LAUNCH(1);
-    return cudaGetLastError();
+    static int warps_env = -1;
+    if (warps_env < 0) { const char *e = getenv("MD_LKT_WARPS"); warps_env = e ? atoi(e) : 0; }
+    auto go = [&](auto kern, int WARPS) {
+        const size_t smem = (size_t)WARPS * LkTile<40>::WARP_BYTES + 128;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        dim3 grid((p.P + WARPS - 1) / WARPS, pairs);
+        kern<<<grid, WARPS * 32, smem, s>>>(p, *reinterpret_cast<const LkTmaMaps *>(maps));
+        MD_COUNT_LAUNCH(1);
+        return cudaGetLastError();
+    };
+    // one warp per CTA, like k_lk_phase (live path: 552 callbacks/s with 8 warps per CTA, 578 with 1); MD_LKT_WARPS=8: tuning aid
+    if (warps_env == 8) return go(k_lk_tma<40, 8>, 8);
+    return go(k_lk_tma<40, 1>, 1);
 }
