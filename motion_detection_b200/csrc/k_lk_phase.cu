@@ -10,7 +10,10 @@
 //    on that fraction only, so the window samples I (5 extra bits), Ix, Iy of ALL points of a class are the same
 //    function of the integer origin.  k_phase_planes evaluates them once per pixel and class (2 N pixel evaluations
 //    per frame at pixel_step 10 instead of 80 N per-point tap evaluations); the per-point window build of k_lk_tma
-//    (48 % of its instructions) becomes one TMA box load + the integer sums A11, A12, A22, sum I*Ix, sum I*Iy.
+//    (48 % of its instructions) becomes one TMA box load of the Ix, Iy planes.
+//  * The five integer window sums A11, A12, A22, sum I*Ix, sum I*Iy of a point are box sums over its class planes; points
+//    of one grid row and class share their 40 window rows, so k_window_sums forms the column sums once per (row, class)
+//    and every point adds up 40 of them: 28 M pixel visits per 1080p pair instead of 166 M per-point taps, exact int64.
 //  * The iteration loop (J tile staged by TMA, dp2a bilinear samples, dp2a mismatch accumulation on packed tap pairs,
 //    REDUX reductions) is the one of k_lk_tma.cu.
 #include <stdlib.h>
@@ -25,7 +28,9 @@ struct PhParams {
     const uint8_t *img;
     const short2 *der;
     int16_t *ph;
+    long long *wsum;
     int prev_slot0, pair0;
+    int P, ps, gx, gy;
     float half;
 };
 
@@ -101,6 +106,59 @@ __global__ void __launch_bounds__(256) k_phase_planes(const PhParams q, int leve
     }
 }
 
+// ---- per-point window sums -----------------------------------------------------------------------------------------------
+// One CTA = the grid points of one grid row ky that fall into x-class cx at `level` (they share class plane and window rows).
+// Phase 1: every plane column gets the sums over the 40 window rows of x^2, x*y, y^2, i*x, i*y (int32: 40 * 8160 * 4080 fits).
+// Phase 2: a point's sums are 40 consecutive column sums (int64).  Same integers as the per-point loops of k_lk_tma.
+__global__ void __launch_bounds__(256) k_window_sums(const PhParams q, int level)
+{
+    extern __shared__ int ws_col[];          // [5][pitch]
+    const PhaseLevel PL = q.pg.lv[level];
+    const int ky = blockIdx.x, cx = blockIdx.y, b = blockIdx.z;
+    const int msk = (1 << level) - 1;
+    const int gyi = q.ps * ky;
+    const int cy = (gyi & msk) >> PL.shift;
+    const float scale = 1.f / (float)(1 << level);
+    const int oy = __float2int_rd(__fsub_rn((float)gyi * scale, q.half)) + MD_PH_MARGIN;
+    const size_t plane = (size_t)PL.pitch * PL.h;
+    const int16_t *base = q.ph + (size_t)(q.pair0 + b) * q.pg.pair_elems + PL.off + (size_t)(cy * PL.ncx + cx) * 3 * plane +
+                          (size_t)oy * PL.pitch;
+    const uint32_t *pI = reinterpret_cast<const uint32_t *>(base), *pX = reinterpret_cast<const uint32_t *>(base + plane),
+                   *pY = reinterpret_cast<const uint32_t *>(base + 2 * plane);
+    const int wp = PL.pitch >> 1;            // words per plane row; a thread sums two adjacent columns
+    for (int c2 = threadIdx.x; c2 < wp; c2 += blockDim.x) {
+        int s[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+#pragma unroll 4
+        for (int r = 0; r < 40; r++) {
+            const uint32_t wi = pI[r * wp + c2], wx = pX[r * wp + c2], wy = pY[r * wp + c2];
+            const int i0 = (int)(wi & 0xffffu), i1 = (int)(wi >> 16);
+            const int x0 = (int)(short)wx, x1 = (int)wx >> 16, y0 = (int)(short)wy, y1 = (int)wy >> 16;
+            s[0][0] += x0 * x0; s[0][1] += x0 * y0; s[0][2] += y0 * y0; s[0][3] += i0 * x0; s[0][4] += i0 * y0;
+            s[1][0] += x1 * x1; s[1][1] += x1 * y1; s[1][2] += y1 * y1; s[1][3] += i1 * x1; s[1][4] += i1 * y1;
+        }
+#pragma unroll
+        for (int t = 0; t < 5; t++) { ws_col[t * PL.pitch + 2 * c2] = s[0][t]; ws_col[t * PL.pitch + 2 * c2 + 1] = s[1][t]; }
+    }
+    __syncthreads();
+    // the points of this row and class: kx with ((ps * kx) & msk) >> shift == cx, i.e. every ncx-th kx from the first match
+    const int ncx = PL.ncx;
+    int kx0 = -1;
+    for (int t = 0; t < ncx && t < q.gx; t++)
+        if ((((q.ps * t) & msk) >> PL.shift) == cx) { kx0 = t; break; }
+    if (kx0 < 0) return;
+    const int npts = (q.gx - kx0 + ncx - 1) / ncx;
+    for (int e = threadIdx.x; e < npts * 5; e += blockDim.x) {
+        const int pi = e / 5, t = e - pi * 5;
+        const int kx = kx0 + pi * ncx;
+        const int ox = __float2int_rd(__fsub_rn((float)(q.ps * kx) * scale, q.half)) + MD_PH_MARGIN;
+        const int *v = ws_col + t * PL.pitch + ox;
+        long long acc = 0;
+#pragma unroll 8
+        for (int c = 0; c < 40; c++) acc += v[c];
+        q.wsum[((((size_t)(q.pair0 + b) * q.g.nlev + level) * q.P) + (size_t)kx * q.gy + ky) * 5 + t] = acc;
+    }
+}
+
 // ---- LK on phase planes ------------------------------------------------------------------------------------------------
 struct PhTile {
     static constexpr int WIN = 40, LXN = 4, LYN = 8;
@@ -109,7 +167,7 @@ struct PhTile {
     static constexpr int PLANE_WORDS = PW * WIN;      // 960
     static constexpr int JP = MD_LK_J_BOX_W / 4;      // J tile pitch in words (20)
     static constexpr int JROWS = WIN + 1 + 2 * MD_LK_J_MARGIN_Y;
-    static constexpr int P_BYTES = 3 * PLANE_WORDS * 4, J_BYTES = MD_LK_J_BOX_W * JROWS;
+    static constexpr int P_BYTES = 2 * PLANE_WORDS * 4, J_BYTES = MD_LK_J_BOX_W * JROWS;      // Ix, Iy planes
     static constexpr int P_OFF = 0;
     static constexpr int J_OFF = (P_BYTES + 127) / 128 * 128;
     static constexpr int BAR_OFF = J_OFF + (J_BYTES + 127) / 128 * 128;
@@ -118,7 +176,7 @@ struct PhTile {
 };
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 14 : WARPS == 2 ? 7 : (WARPS <= 4 ? 3 : (WARPS <= 7 ? 2 : 1))) k_lk_phase(const LkParams p, const __grid_constant__ LkPhaseMaps maps)
+__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 : (WARPS <= 4 ? 3 : (WARPS <= 7 ? 2 : 1))) k_lk_phase(const LkParams p, const __grid_constant__ LkPhaseMaps maps)
 {
     using T = PhTile;
     constexpr int WIN = T::WIN, TW = T::TW, TH = T::TH, NP = T::NP;
@@ -158,7 +216,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 14 : WARPS == 2 ? 7 :
             const int msk = (1 << level) - 1, sh = p.pg.lv[level].shift;
             const int cls = ((gyi & msk) >> sh) * p.pg.lv[level].ncx + ((gxi & msk) >> sh);
             mbar_expect_tx(barP, T::P_BYTES);
-            tma_load_5d(tP, &maps.ph[level], (ipx + MD_PH_MARGIN) & ~7, ipy + MD_PH_MARGIN, 0, cls, p.ph_pair0 + b, barP);
+            tma_load_5d(tP, &maps.ph[level], (ipx + MD_PH_MARGIN) & ~7, ipy + MD_PH_MARGIN, 1, cls, p.ph_pair0 + b, barP);
         }
     };
     issue_P(p.g.nlev - 1);
@@ -195,38 +253,34 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 14 : WARPS == 2 ? 7 :
             }
         }
 
-        // ---- window samples from the phase planes into registers, structure tensor, constant part of the mismatch ----
+        // ---- derivative window from the phase planes into registers; the window sums come precomputed ---------------
         mbar_wait(barP, phP); phP ^= 1;
         int Xpk[TH][NP], Ypk[TH][NP];
-        int a11 = 0, a12 = 0, a22 = 0, c1 = 0, c2 = 0;
         {
             const int e0 = ((ipx + MD_PH_MARGIN) & 7) + TW * lx;       // first tap column of this lane inside the box
             const int sh = (e0 & 1) * 16;
-            const uint32_t *pI = tP + (TH * ly) * T::PW + (e0 >> 1), *pX = pI + T::PLANE_WORDS, *pY = pX + T::PLANE_WORDS;
+            const uint32_t *pX = tP + (TH * ly) * T::PW + (e0 >> 1), *pY = pX + T::PLANE_WORDS;
 #pragma unroll
             for (int r = 0; r < TH; r++) {
-                uint32_t wi[NP + 1], wx[NP + 1], wy[NP + 1];
+                uint32_t wx[NP + 1], wy[NP + 1];
 #pragma unroll
-                for (int i = 0; i <= NP; i++) { wi[i] = pI[r * T::PW + i]; wx[i] = pX[r * T::PW + i]; wy[i] = pY[r * T::PW + i]; }
+                for (int i = 0; i <= NP; i++) { wx[i] = pX[r * T::PW + i]; wy[i] = pY[r * T::PW + i]; }
 #pragma unroll
                 for (int i = 0; i < NP; i++) {
-                    const uint32_t qi = __funnelshift_r(wi[i], wi[i + 1], sh);
-                    const int X = (int)__funnelshift_r(wx[i], wx[i + 1], sh), Y = (int)__funnelshift_r(wy[i], wy[i + 1], sh);
-                    const int x0 = (int)(short)X, x1 = X >> 16, y0 = (int)(short)Y, y1 = Y >> 16;
-                    const int i0 = (int)(qi & 0xffffu), i1 = (int)(qi >> 16);
-                    a11 += x0 * x0 + x1 * x1; a12 += x0 * y0 + x1 * y1; a22 += y0 * y0 + y1 * y1;
-                    c1 += i0 * x0 + i1 * x1; c2 += i0 * y0 + i1 * y1;
-                    Xpk[r][i] = X; Ypk[r][i] = Y;
+                    Xpk[r][i] = (int)__funnelshift_r(wx[i], wx[i + 1], sh);
+                    Ypk[r][i] = (int)__funnelshift_r(wy[i], wy[i + 1], sh);
                 }
             }
         }
+        const long long *ws = p.wsum + ((((size_t)(p.ph_pair0 + b) * p.g.nlev + level) * p.P) + k) * 5;
+        const long long s11 = __ldg(ws), s12 = __ldg(ws + 1), s22 = __ldg(ws + 2), C1 = __ldg(ws + 3), C2 = __ldg(ws + 4);
         __syncwarp();                       // the phase tile is consumed: prefetch the next level's
         if (level > 0) issue_P(level - 1);
         if (j_ok) { mbar_wait(barJ, phJ); phJ ^= 1; }
 
-        const float A11 = warp_sum_exact_f32(a11) * FLT_SCALE;
-        const float A12 = warp_sum_exact_f32(a12) * FLT_SCALE;
-        const float A22 = warp_sum_exact_f32(a22) * FLT_SCALE;
+        const float A11 = (float)s11 * FLT_SCALE;
+        const float A12 = (float)s12 * FLT_SCALE;
+        const float A22 = (float)s22 * FLT_SCALE;
         float D;
         if (!lk_min_eig_ok(A11, A12, A22, WIN, p.min_eig, D)) {
             if (level == 0) st = 0;
@@ -255,7 +309,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 14 : WARPS == 2 ? 7 :
             const uint32_t *rowp = tJ + ((iny - ty0) + TH * ly) * T::JP;
             const int wtop = (int)__byte_perm((uint32_t)w00, (uint32_t)w01, 0x5410);
             const int wbot = (int)__byte_perm((uint32_t)w10, (uint32_t)w11, 0x5410);
-            int b1lo = -c1, b1hi = 0, b2lo = -c2, b2hi = 0;
+            int b1lo = 0, b1hi = 0, b2lo = 0, b2hi = 0;
             RowWords r0 = load_row(rowp, wb, sh);
 #pragma unroll
             for (int r = 0; r < TH; r++) {
@@ -264,8 +318,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 14 : WARPS == 2 ? 7 :
                 r0 = r1;
             }
             const int b1 = b1hi * 256 + b1lo, b2 = b2hi * 256 + b2lo;
-            const float fb1 = warp_sum_exact_f32(b1) * FLT_SCALE;
-            const float fb2 = warp_sum_exact_f32(b2) * FLT_SCALE;
+            // sum (J - I) Ix = sum J Ix - sum I Ix, exactly, in 64-bit integers; one rounding to f32
+            const float fb1 = (float)(warp_sum_exact_i64(b1) - C1) * FLT_SCALE;
+            const float fb2 = (float)(warp_sum_exact_i64(b2) - C2) * FLT_SCALE;
             if (lk_update(A11, A12, A22, D, fb1, fb2, half, j, p.eps2, s, nxt)) break;
         }
     }
@@ -280,6 +335,7 @@ cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s)
 {
     PhParams q;
     q.g = p.g; q.pg = p.pg; q.img = p.img; q.der = p.der; q.ph = p.ph; q.prev_slot0 = p.prev_slot0; q.pair0 = p.ph_pair0;
+    q.wsum = p.wsum; q.P = p.P; q.ps = p.ps; q.gy = p.gy; q.gx = p.P / p.gy;
     q.half = (p.win - 1) * 0.5f;
     for (int l = 0; l < p.g.nlev; l++) {
         const PhaseLevel &PL = p.pg.lv[l];
@@ -287,7 +343,15 @@ cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s)
         dim3 grid((threads + 255) / 256, PL.ncx * PL.ncx, pairs);
         k_phase_planes<<<grid, 256, 0, s>>>(q, l);
     }
-    MD_COUNT_LAUNCH(p.g.nlev);
+    size_t max_smem = 0;
+    for (int l = 0; l < p.g.nlev; l++) max_smem = max_smem > (size_t)p.pg.lv[l].pitch * 20 ? max_smem : (size_t)p.pg.lv[l].pitch * 20;
+    cudaError_t e = cudaFuncSetAttribute(k_window_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
+    if (e != cudaSuccess) return e;
+    for (int l = 0; l < p.g.nlev; l++) {
+        const PhaseLevel &PL = p.pg.lv[l];
+        k_window_sums<<<dim3(q.gy, PL.ncx, pairs), 256, (size_t)PL.pitch * 20, s>>>(q, l);
+    }
+    MD_COUNT_LAUNCH(2 * p.g.nlev);
     return cudaGetLastError();
 }
 

@@ -108,10 +108,11 @@ struct RowStore {
 };
 
 // exact warp sum of per-lane int32 partial sums (|v| < 2^31): two REDUX adds on the 16-bit halves, one rounding to f32
-__device__ __forceinline__ float warp_sum_exact_f32(int v)
+__device__ __forceinline__ long long warp_sum_exact_i64(int v)
 {
     const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
     const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xffffu);
-    return (float)((long long)hi * 65536 + (long long)lo);
+    return (long long)hi * 65536 + (long long)lo;
 }
+__device__ __forceinline__ float warp_sum_exact_f32(int v) { return (float)warp_sum_exact_i64(v); }
 

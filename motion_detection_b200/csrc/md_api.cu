@@ -119,14 +119,21 @@ static bool ensure_phase(md_ctx *ctx)
     if ((double)ctx->P * ctx->g.nlev * 1600.0 < 4.0 * (double)pg.px_per_pair) return false;
     const size_t bytes = pg.pair_elems * sizeof(int16_t) * ctx->cfg.max_batch;
     if (bytes > ((size_t)24 << 30)) return false;
+    for (int l = 0; l < ctx->g.nlev; l++)
+        if ((size_t)pg.lv[l].pitch * 5 * sizeof(int) > 200 * 1024) return false;      // k_window_sums keeps 5 column sums per plane column
     if (cudaMalloc((void **)&ctx->d_phase, bytes) != cudaSuccess) { cudaGetLastError(); ctx->d_phase = nullptr; return false; }
+    if (cudaMalloc((void **)&ctx->d_wsum, sizeof(long long) * 5 * (size_t)ctx->P * ctx->g.nlev * ctx->cfg.max_batch) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(ctx->d_phase); ctx->d_phase = nullptr; ctx->d_wsum = nullptr;
+        return false;
+    }
     for (int l = 0; l < ctx->g.nlev; l++) {
         const PhaseLevel &PL = pg.lv[l];
         const uint64_t plane = (uint64_t)PL.pitch * PL.h * 2;
         const uint64_t dims[5] = {(uint64_t)PL.pitch, (uint64_t)PL.h, 3, (uint64_t)PL.ncx * PL.ncx, (uint64_t)ctx->cfg.max_batch};
         const uint64_t str[4] = {(uint64_t)PL.pitch * 2, plane, 3 * plane, (uint64_t)pg.pair_elems * 2};
-        if (!tma_encode_5d_u16(&ctx->ph_maps.ph[l], ctx->d_phase + PL.off, dims, str, MD_PH_BOX_W, 40, 3)) {
-            cudaFree(ctx->d_phase); ctx->d_phase = nullptr;
+        if (!tma_encode_5d_u16(&ctx->ph_maps.ph[l], ctx->d_phase + PL.off, dims, str, MD_PH_BOX_W, 40, 2)) {
+            cudaFree(ctx->d_phase); ctx->d_phase = nullptr; cudaFree(ctx->d_wsum); ctx->d_wsum = nullptr;
             return false;
         }
         ctx->ph_maps.imgJ[l] = ctx->lk_maps.imgJ[l];
@@ -143,7 +150,7 @@ static void free_ctx(md_ctx *ctx)
     void *ptrs[] = {ctx->d_img, ctx->d_der, ctx->d_frames, ctx->d_mask, ctx->d_pts_in, ctx->d_next, ctx->d_status, ctx->d_keep,
                     ctx->d_inlier_mask, ctx->d_blockcnt, ctx->d_kept_idx, ctx->d_M, ctx->d_hyp_valid, ctx->d_counts,
                     ctx->d_inliers, ctx->d_valid, ctx->d_hyp, ctx->d_partial, ctx->d_H, ctx->d_Hinv, ctx->d_stats,
-                    ctx->d_traj, ctx->d_traj_len, ctx->d_phase};
+                    ctx->d_traj, ctx->d_traj_len, ctx->d_phase, ctx->d_wsum};
     for (void *p : ptrs) if (p) cudaFree(p);
     vf_free_workspace(ctx->vf_ws);
     sub_free_workspace(ctx->sub_ws);
@@ -437,6 +444,7 @@ static void fill_lk(md_ctx *ctx, LkParams &p, int prev_slot0, int next_slot0, co
     p.g = ctx->g;
     p.pg = ctx->pg;
     p.ph = (!pts_in && ensure_phase(ctx)) ? ctx->d_phase : nullptr;
+    p.wsum = ctx->d_wsum;
     p.ph_pair0 = ph_pair0;
     p.ph_ready = 0;
     p.img = ctx->d_img; p.der = ctx->d_der;

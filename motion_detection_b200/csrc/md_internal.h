@@ -69,7 +69,7 @@ struct PhaseGeom {
 };
 struct alignas(64) LkPhaseMaps {
     CUtensorMap imgJ[MD_MAX_LEVELS];   // u8, box 80 x 47 (same as LkTmaMaps::imgJ)
-    CUtensorMap ph[MD_MAX_LEVELS];     // s16, dims (x, y, plane, class, pair), box 48 x 40 x 3
+    CUtensorMap ph[MD_MAX_LEVELS];     // s16, dims (x, y, plane, class, pair), box 48 x 40 x 2 (the Ix, Iy planes)
     int valid;
 };
 
@@ -89,6 +89,7 @@ struct LkParams {
     // grid mode with phase planes (pts_in == nullptr): pair b uses arena ph + b * pg.pair_elems
     PhaseGeom pg;
     int16_t *ph;
+    long long *wsum;         // [max_batch][nlev][P][5] window sums A11, A12, A22, sum I*Ix, sum I*Iy (k_window_sums)
     int ph_pair0;            // pair b of this launch uses arena ph_pair0 + b
     int ph_ready;            // 1 = the planes were already computed (launch_lk_planes on another stream)
 };
@@ -183,6 +184,7 @@ struct md_ctx {
     LkPhaseMaps ph_maps;
     PhaseGeom pg;
     int16_t *d_phase;     // [max_batch] pair arenas of phase planes, allocated on the first grid-mode LK call
+    long long *d_wsum;    // [max_batch][nlev][P][5] per-point window sums
     int phase_state;      // 0 = not tried, 1 = ready, -1 = not used (not worth it / allocation failed)
     void *sub_ws;         // fitSubspace workspace (k_subspace.cu)
     void *mad_ws;         // findOutliers workspace (k_mad.cu)
