@@ -107,55 +107,88 @@ __global__ void __launch_bounds__(256) k_phase_planes(const PhParams q, int leve
 }
 
 // ---- per-point window sums -----------------------------------------------------------------------------------------------
-// One CTA = the grid points of one grid row ky that fall into x-class cx at `level` (they share class plane and window rows).
-// Phase 1: every plane column gets the sums over the 40 window rows of x^2, x*y, y^2, i*x, i*y (int32: 40 * 8160 * 4080 fits).
-// Phase 2: a point's sums are 40 consecutive column sums (int64).  Same integers as the per-point loops of k_lk_tma.
-__global__ void __launch_bounds__(256) k_window_sums(const PhParams q, int level)
+// The window origins of one phase class form a lattice with step s = ps / gcd(ps, 2^level) in both directions, and the
+// windows of neighbouring lattice rows share 40 - s of their 40 rows.  One CTA owns a block of the lattice (<= WS_SEG origin
+// rows x the origin columns that fit 512 plane columns) of one (class, pair); a thread keeps the five column sums
+// (x^2, x*y, y^2, i*x, i*y over the window's 40 rows; int32: 40 * 8160 * 4080 fits) of two adjacent plane columns and
+// SLIDES them from one origin row to the next (subtract s rows, add s rows); after every origin row the points of that row
+// add up 40 consecutive column sums from shared memory (int64).  Same integers as the per-point loops of k_lk_tma.
+#define WS_COLS 512
+#define WS_SEG 16
+__device__ __forceinline__ void ws_accumulate(int (&acc)[2][5], uint32_t wi, uint32_t wx, uint32_t wy, int sign)
 {
-    extern __shared__ int ws_col[];          // [5][pitch]
+    const int i0 = (int)(wi & 0xffffu), i1 = (int)(wi >> 16);
+    const int x0 = (int)(short)wx * sign, x1 = ((int)wx >> 16) * sign, y0 = (int)(short)wy, y1 = (int)wy >> 16;
+    const int xs0 = (int)(short)wx, xs1 = (int)wx >> 16;
+    acc[0][0] += x0 * xs0; acc[0][1] += x0 * y0; acc[0][2] += y0 * y0 * sign; acc[0][3] += i0 * x0; acc[0][4] += i0 * y0 * sign;
+    acc[1][0] += x1 * xs1; acc[1][1] += x1 * y1; acc[1][2] += y1 * y1 * sign; acc[1][3] += i1 * x1; acc[1][4] += i1 * y1 * sign;
+}
+
+__global__ void __launch_bounds__(256) k_window_sums(const PhParams q, int level, int cp, int nchunk_x)
+{
+    __shared__ int ws_col[5][WS_COLS + 8];
     const PhaseLevel PL = q.pg.lv[level];
-    const int ky = blockIdx.x, cx = blockIdx.y, b = blockIdx.z;
+    const int ncx = PL.ncx, cls = blockIdx.y, cx = cls % ncx, cy = cls / ncx, b = blockIdx.z;
+    const int chunk = blockIdx.x % nchunk_x, seg = blockIdx.x / nchunk_x;
     const int msk = (1 << level) - 1;
-    const int gyi = q.ps * ky;
-    const int cy = (gyi & msk) >> PL.shift;
+    const int step = q.ps >> PL.shift;                          // lattice step in plane pixels: ps / gcd(ps, 2^level)
     const float scale = 1.f / (float)(1 << level);
-    const int oy = __float2int_rd(__fsub_rn((float)gyi * scale, q.half)) + MD_PH_MARGIN;
+    // first grid index of each axis that falls into this class; the class members are every ncx-th index from there
+    int kx0 = -1, ky0 = -1;
+    for (int t = 0; t < ncx; t++) {
+        if (kx0 < 0 && t < q.gx && (((q.ps * t) & msk) >> PL.shift) == cx) kx0 = t;
+        if (ky0 < 0 && t < q.gy && (((q.ps * t) & msk) >> PL.shift) == cy) ky0 = t;
+    }
+    if (kx0 < 0 || ky0 < 0) return;
+    const int nx = (q.gx - kx0 + ncx - 1) / ncx, ny = (q.gy - ky0 + ncx - 1) / ncx;
+    const int i0 = chunk * cp, i1 = min(nx, i0 + cp);           // lattice columns of this CTA
+    const int j0 = seg * WS_SEG, j1 = min(ny, j0 + WS_SEG);     // lattice rows of this CTA
+    if (i0 >= i1 || j0 >= j1) return;
+    const int ox0 = __float2int_rd(__fsub_rn((float)(q.ps * (kx0 + i0 * ncx)) * scale, q.half)) + MD_PH_MARGIN;
+    const int oy0 = __float2int_rd(__fsub_rn((float)(q.ps * (ky0 + j0 * ncx)) * scale, q.half)) + MD_PH_MARGIN;
+    const int c_lo = ox0 & ~1;                                   // word aligned first column
+    const int ncols = ox0 + (i1 - i0 - 1) * step + 40 - c_lo;    // <= WS_COLS by the choice of cp
     const size_t plane = (size_t)PL.pitch * PL.h;
-    const int16_t *base = q.ph + (size_t)(q.pair0 + b) * q.pg.pair_elems + PL.off + (size_t)(cy * PL.ncx + cx) * 3 * plane +
-                          (size_t)oy * PL.pitch;
-    const uint32_t *pI = reinterpret_cast<const uint32_t *>(base), *pX = reinterpret_cast<const uint32_t *>(base + plane),
-                   *pY = reinterpret_cast<const uint32_t *>(base + 2 * plane);
-    const int wp = PL.pitch >> 1;            // words per plane row; a thread sums two adjacent columns
-    for (int c2 = threadIdx.x; c2 < wp; c2 += blockDim.x) {
-        int s[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    const int16_t *base = q.ph + (size_t)(q.pair0 + b) * q.pg.pair_elems + PL.off + (size_t)cls * 3 * plane + c_lo;
+    const int wp = PL.pitch >> 1;
+    const uint32_t *pI = reinterpret_cast<const uint32_t *>(base) + threadIdx.x, *pX = pI + (plane >> 1), *pY = pX + (plane >> 1);
+    const bool col_on = 2 * (int)threadIdx.x < ncols;
+    int acc[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    if (col_on) {
 #pragma unroll 4
         for (int r = 0; r < 40; r++) {
-            const uint32_t wi = pI[r * wp + c2], wx = pX[r * wp + c2], wy = pY[r * wp + c2];
-            const int i0 = (int)(wi & 0xffffu), i1 = (int)(wi >> 16);
-            const int x0 = (int)(short)wx, x1 = (int)wx >> 16, y0 = (int)(short)wy, y1 = (int)wy >> 16;
-            s[0][0] += x0 * x0; s[0][1] += x0 * y0; s[0][2] += y0 * y0; s[0][3] += i0 * x0; s[0][4] += i0 * y0;
-            s[1][0] += x1 * x1; s[1][1] += x1 * y1; s[1][2] += y1 * y1; s[1][3] += i1 * x1; s[1][4] += i1 * y1;
+            const size_t o = (size_t)(oy0 + r) * wp;
+            ws_accumulate(acc, __ldg(pI + o), __ldg(pX + o), __ldg(pY + o), 1);
         }
-#pragma unroll
-        for (int t = 0; t < 5; t++) { ws_col[t * PL.pitch + 2 * c2] = s[0][t]; ws_col[t * PL.pitch + 2 * c2 + 1] = s[1][t]; }
     }
-    __syncthreads();
-    // the points of this row and class: kx with ((ps * kx) & msk) >> shift == cx, i.e. every ncx-th kx from the first match
-    const int ncx = PL.ncx;
-    int kx0 = -1;
-    for (int t = 0; t < ncx && t < q.gx; t++)
-        if ((((q.ps * t) & msk) >> PL.shift) == cx) { kx0 = t; break; }
-    if (kx0 < 0) return;
-    const int npts = (q.gx - kx0 + ncx - 1) / ncx;
-    for (int e = threadIdx.x; e < npts * 5; e += blockDim.x) {
-        const int pi = e / 5, t = e - pi * 5;
-        const int kx = kx0 + pi * ncx;
-        const int ox = __float2int_rd(__fsub_rn((float)(q.ps * kx) * scale, q.half)) + MD_PH_MARGIN;
-        const int *v = ws_col + t * PL.pitch + ox;
-        long long acc = 0;
+    for (int j = j0; j < j1; j++) {
+        if (j > j0 && col_on) {
+            const int top = oy0 + (j - 1 - j0) * step;          // previous origin row
+#pragma unroll 5
+            for (int r = 0; r < step; r++) {
+                const size_t om = (size_t)(top + r) * wp, op = (size_t)(top + 40 + r) * wp;
+                const uint32_t mi = __ldg(pI + om), mx = __ldg(pX + om), my = __ldg(pY + om);
+                const uint32_t ai = __ldg(pI + op), ax = __ldg(pX + op), ay = __ldg(pY + op);
+                ws_accumulate(acc, mi, mx, my, -1);
+                ws_accumulate(acc, ai, ax, ay, 1);
+            }
+        }
+        __syncthreads();                                         // the previous row's readers are done
+        if (col_on) {
+#pragma unroll
+            for (int t = 0; t < 5; t++) { ws_col[t][2 * threadIdx.x] = acc[0][t]; ws_col[t][2 * threadIdx.x + 1] = acc[1][t]; }
+        }
+        __syncthreads();
+        const int ky = ky0 + j * ncx;
+        for (int e = threadIdx.x; e < (i1 - i0) * 5; e += blockDim.x) {
+            const int pi = e / 5, t = e - pi * 5;
+            const int *v = &ws_col[t][ox0 + pi * step - c_lo];
+            long long sum = 0;
 #pragma unroll 8
-        for (int c = 0; c < 40; c++) acc += v[c];
-        q.wsum[((((size_t)(q.pair0 + b) * q.g.nlev + level) * q.P) + (size_t)kx * q.gy + ky) * 5 + t] = acc;
+            for (int c = 0; c < 40; c++) sum += v[c];
+            const int kx = kx0 + (i0 + pi) * ncx;
+            q.wsum[((((size_t)(q.pair0 + b) * q.g.nlev + level) * q.P) + (size_t)kx * q.gy + ky) * 5 + t] = sum;
+        }
     }
 }
 
@@ -343,13 +376,14 @@ cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s)
         dim3 grid((threads + 255) / 256, PL.ncx * PL.ncx, pairs);
         k_phase_planes<<<grid, 256, 0, s>>>(q, l);
     }
-    size_t max_smem = 0;
-    for (int l = 0; l < p.g.nlev; l++) max_smem = max_smem > (size_t)p.pg.lv[l].pitch * 20 ? max_smem : (size_t)p.pg.lv[l].pitch * 20;
-    cudaError_t e = cudaFuncSetAttribute(k_window_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem);
-    if (e != cudaSuccess) return e;
     for (int l = 0; l < p.g.nlev; l++) {
         const PhaseLevel &PL = p.pg.lv[l];
-        k_window_sums<<<dim3(q.gy, PL.ncx, pairs), 256, (size_t)PL.pitch * 20, s>>>(q, l);
+        const int step = p.ps >> PL.shift;
+        if (step > WS_COLS - 42) return cudaErrorInvalidConfiguration;          // one point per chunk must fit (pixel_step <= 470)
+        const int cp = (WS_COLS - 42) / step + 1;                                // lattice columns per CTA
+        const int nx = (q.gx + PL.ncx - 1) / PL.ncx, ny = (q.gy + PL.ncx - 1) / PL.ncx;   // upper bounds per class
+        const int nchunk_x = (nx + cp - 1) / cp, nseg = (ny + WS_SEG - 1) / WS_SEG;
+        k_window_sums<<<dim3(nchunk_x * nseg, PL.ncx * PL.ncx, pairs), 256, 0, s>>>(q, l, cp, nchunk_x);
     }
     MD_COUNT_LAUNCH(2 * p.g.nlev);
     return cudaGetLastError();
