@@ -290,6 +290,19 @@ def test_process_batch_1080p(capi, oracle):
         _check_pair(res, b, ref)
 
 
+@pytest.mark.parametrize("size,ps", [((640, 480), 7), ((640, 480), 16), ((320, 240), 3), ((160, 120), 1), ((1280, 720), 12)])
+def test_process_batch_other_grid_steps(capi, oracle, size, ps):
+    """The chain at other pixel_step values: other phase-class layouts and lattice steps (7, 3: steps that do not divide the
+    40-row window; 16: a single class on every level; 1: dense) through planes + window sums + LK + fit + mask."""
+    w, h = size
+    frames, _ = synth.sequence(w, h, 3, seed=31 + ps, blobs=2)
+    ctx = _ctx(capi, w, h, max_batch=2, seed=5, pixel_step=ps)
+    res = ctx.process_batch(frames)
+    for b in range(2):
+        ref = oracle.process_pair(frames[b], frames[b + 1], pixel_step=ps, min_vector_size=0.2, seed=5 + b)
+        _check_pair(res, b, ref)
+
+
 def test_affine_mode_chain(capi, oracle, seq640):
     frames, _ = seq640
     ctx = _ctx(capi, 640, 480, max_batch=1, seed=2, ego_mode=2)
