@@ -35,7 +35,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=16, help="frame pairs per step")
+    ap.add_argument("--batch", type=int, default=32, help="frame pairs per step (16: 4 202 pairs/s, 32: 4 440, 64: 4 551)")
     ap.add_argument("--pixel-step", type=int, default=10, help="grid step (launch-file default 10; 1 = dense)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)

@@ -727,8 +727,13 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
             for (int i = 1; i <= mid; i++) bounds[++nch] = 1 + (int)((long long)(pairs - 2) * i / mid);
             bounds[++nch] = pairs;
         } else {
-            // device-resident frames: even chunks; only the small latency-bound kernels of K3 are worth hiding
-            for (int i = 1; i <= total; i++) bounds[++nch] = (int)((long long)pairs * i / total);
+            // device-resident frames: a short first chunk (its pyramids, planes and sums are exposed), then even chunks
+            static int first_env = -1;
+            if (first_env < 0) { const char *e = getenv("MD_PIPE_FIRST"); first_env = e ? atoi(e) : 0; }
+            const int first = first_env > 0 && first_env < pairs ? first_env : 0;
+            if (first) bounds[++nch] = first;
+            const int rest = pairs - first, nrest = first ? total - 1 : total;
+            for (int i = 1; i <= nrest; i++) bounds[++nch] = first + (int)((long long)rest * i / nrest);
         }
     }
     cudaStream_t s_pyr = serial ? s : ctx->aux_pyr, s_post = serial ? s : ctx->aux_post;
