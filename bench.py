@@ -347,7 +347,8 @@ def main():
     for i in range(a.warmup):
         step(i)
     barrier()
-    l0 = ctx.stats()["kernel_launches"]
+    st0 = ctx.stats()
+    l0 = st0["kernel_launches"]
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.15)
@@ -360,7 +361,9 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
-    launches = ctx.stats()["kernel_launches"] - l0
+    st1 = ctx.stats()
+    launches = st1["kernel_launches"] - l0
+    lk_work = (st1["lk_iterations"] - st0["lk_iterations"], st1["lk_levels"] - st0["lk_levels"])
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -398,6 +401,13 @@ def main():
             traffic = per_pair * B if per_pair is not None else None     # ncu dram bytes per pair x pairs per launch
         except Exception:
             traffic = None
+    # K2's work in window-tap evaluations (1600 taps per iteration, counted on the device in the timed region)
+    lk_taps = None
+    if lk_work[0] > 0:
+        per_point = lk_work[0] / (P * B * a.steps)
+        lk_taps = {"iterations_per_point": per_point, "levels_iterated_per_point": lk_work[1] / (P * B * a.steps),
+                   "tap_evaluations_per_pair": 1600.0 * lk_work[0] / (B * a.steps),
+                   "tap_evaluations_per_s_device_resident": 1600.0 * lk_work[0] * world / (ms_max * 1e-3)}
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src, "peak_spec": 8000.0,
                 "frac_of_spec": stages[dom]["gbs"] / 8000.0,
@@ -417,7 +427,7 @@ def main():
         ach = ipp * P * B / (stage_ms[1] * 1e-3)
         roofline["issue"] = {"bound": "instruction issue (148 SMs x 4 schedulers x SM clock)", "achieved": ach / 1e9, "peak": peak_issue / 1e9,
                              "unit": "G warp-instr/s", "frac": ach / peak_issue, "warp_instr_per_point": ipp,
-                             "source": "ncu smsp__inst_executed.sum of k_lk_phase / tracked points (profiles/r01_lk_phase_ncu_full.txt)"}
+                             "source": "ncu smsp__inst_executed.sum of k_lk_phase / tracked points (profiles/r01_lk_phase_ncu_full_v2.txt); the time is the whole K2 stage (planes + window sums + LK), so this is a lower bound of the LK kernel's own 80 %"}
 
     # ---- e2e: C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
     e2e = None
@@ -514,7 +524,7 @@ def main():
                        "l2": "inputs rotate over %d resident copies (%.0f MB > 126 MB L2)" % (R, R * (B + 1) * frame_bytes / 1e6),
                        "parallelism": "independent camera streams, one per GPU, no frame-path collective"},
             "mpx_per_s": value * N / 1e6,
-            "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "lk_work": lk_taps, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "stream_stats": gathered,
         }
         print(json.dumps(line), flush=True)

@@ -110,7 +110,9 @@ typedef struct md_stats {
     double  last_H[9];
     int64_t kernel_launches;    /* CUDA kernels launched by this library in this process (all contexts) */
     int32_t device;
-    int32_t reserved[5];
+    int32_t reserved0;
+    int64_t lk_iterations;      /* sum over tracked points and pyramid levels of the LK iterations executed (each = 1600 taps) */
+    int64_t lk_levels;          /* sum over tracked points of the pyramid levels whose window was evaluated */
 } md_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------------------- */

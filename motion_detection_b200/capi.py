@@ -56,7 +56,8 @@ class MdOutputs(C.Structure):
 
 class MdStats(C.Structure):
     _fields_ = [("pairs", C.c_int64), ("mask_pixels", C.c_int64), ("tracked", C.c_int64), ("inliers", C.c_int64),
-                ("last_H", C.c_double * 9), ("kernel_launches", C.c_int64), ("device", C.c_int32), ("reserved", C.c_int32 * 5)]
+                ("last_H", C.c_double * 9), ("kernel_launches", C.c_int64), ("device", C.c_int32), ("reserved0", C.c_int32),
+                ("lk_iterations", C.c_int64), ("lk_levels", C.c_int64)]
 
 
 class MdLiveParams(C.Structure):
@@ -351,7 +352,8 @@ class Context:
         st = MdStats()
         self._ck(lib().md_stats_get(self._h, C.byref(st)))
         return dict(pairs=st.pairs, mask_pixels=st.mask_pixels, tracked=st.tracked, inliers=st.inliers,
-                    last_H=np.array(st.last_H[:]).reshape(3, 3), device=st.device, kernel_launches=st.kernel_launches)
+                    last_H=np.array(st.last_H[:]).reshape(3, 3), device=st.device, kernel_launches=st.kernel_launches,
+                    lk_iterations=st.lk_iterations, lk_levels=st.lk_levels)
 
     def profile(self, enable=True):
         self._ck(lib().md_profile(self._h, 1 if enable else 0))

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 :
     const float FLT_SCALE = 1.f / (1 << 20);
     float2 nxt = make_float2(0.f, 0.f);
     int st = 1;
+    int n_iters = 0, n_levels = 0;              // measurement: work actually done for this point
 
     // request the window (I, Ix, Iy planes of the point's phase class) of `level`
     auto issue_P = [&](int level) {
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 :
             continue;
         }
         s.pdx = 0.f; s.pdy = 0.f;
+        n_levels++;
         for (int j = 0; j < p.max_iters; j++) {
             const int inx = __float2int_rd(s.npx), iny = __float2int_rd(s.npy);
             if (inx < -WIN || inx >= Lw || iny < -WIN || iny >= Lh) {
@@ -328,6 +330,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 :
             }
             int w00, w01, w10, w11;
             lk_weights(__fsub_rn(s.npx, (float)inx), __fsub_rn(s.npy, (float)iny), w00, w01, w10, w11);
+            n_iters++;
             // ---- restage the J tile when the window drifts out of it (warp-uniform, rare) -----------------------------
             if (inx < tx0 || inx - tx0 > T::JX_MAX || iny < ty0 || iny - ty0 > 2 * MD_LK_J_MARGIN_Y) {
                 tx0 = ((inx - MD_LK_J_MARGIN_X + p.g.padx) & ~15) - p.g.padx; ty0 = iny - MD_LK_J_MARGIN_Y;
@@ -360,6 +363,8 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 :
     if (lane == 0) {
         p.next[(size_t)b * p.P + k] = nxt;
         p.status[(size_t)b * p.P + k] = (uint8_t)st;
+        // 64 striped counter pairs: one hot address would serialise the atomics of every finishing warp
+        if (p.stat_iters) { unsigned long long *c = p.stat_iters + 2 * (k & 63); atomicAdd(c, (unsigned long long)n_iters); atomicAdd(c + 1, (unsigned long long)n_levels); }
     }
 }
 

@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) k_lk_tma(const LkParam
     const float FLT_SCALE = 1.f / (1 << 20);
     float2 nxt = make_float2(0.f, 0.f);
     int st = 1;
+    int n_iters = 0, n_levels = 0;              // measurement: work actually done for this point
 
     // request the previous-frame patch + Scharr planes of `level` (no-op when the window is out of range there)
     auto issue_I = [&](int level) {
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) k_lk_tma(const LkParam
             continue;
         }
         s.pdx = 0.f; s.pdy = 0.f;
+        n_levels++;
         for (int j = 0; j < p.max_iters; j++) {
             const int inx = __float2int_rd(s.npx), iny = __float2int_rd(s.npy);
             if (inx < -WIN || inx >= Lw || iny < -WIN || iny >= Lh) {
@@ -165,6 +167,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) k_lk_tma(const LkParam
                 break;
             }
             lk_weights(__fsub_rn(s.npx, (float)inx), __fsub_rn(s.npy, (float)iny), w00, w01, w10, w11);
+            n_iters++;
             // ---- restage the J tile when the window drifts out of it (warp-uniform, rare) -----------------------------
             if (inx < tx0 || inx - tx0 > T::JX_MAX || iny < ty0 || iny - ty0 > 2 * MD_LK_J_MARGIN_Y) {
                 tx0 = ((inx - MD_LK_J_MARGIN_X + p.g.padx) & ~15) - p.g.padx; ty0 = iny - MD_LK_J_MARGIN_Y;
@@ -196,6 +199,8 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) k_lk_tma(const LkParam
     if (lane == 0) {
         p.next[(size_t)b * p.P + k] = nxt;
         p.status[(size_t)b * p.P + k] = (uint8_t)st;
+        // 64 striped counter pairs: one hot address would serialise the atomics of every finishing warp
+        if (p.stat_iters) { unsigned long long *c = p.stat_iters + 2 * (k & 63); atomicAdd(c, (unsigned long long)n_iters); atomicAdd(c + 1, (unsigned long long)n_levels); }
     }
 }
 

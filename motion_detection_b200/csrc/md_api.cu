@@ -265,11 +265,11 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
     A((void **)&ctx->d_partial, sizeof(double) * 24 * ctx->nblk_acc * B);
     A((void **)&ctx->d_H, sizeof(double) * 9 * B);
     A((void **)&ctx->d_Hinv, sizeof(double) * 9 * B);
-    A((void **)&ctx->d_stats, sizeof(unsigned long long) * 4);
+    A((void **)&ctx->d_stats, sizeof(unsigned long long) * 136);
     if (ok) {
         // derivative planes keep a ZERO frame forever (derivBorder = BORDER_CONSTANT); image frames are rewritten per build
         ok = cudaMemsetAsync(ctx->d_der, 0, g.slot_der_elems * sizeof(short2) * g.nslots, ctx->stream) == cudaSuccess &&
-             cudaMemsetAsync(ctx->d_stats, 0, sizeof(unsigned long long) * 4, ctx->stream) == cudaSuccess &&
+             cudaMemsetAsync(ctx->d_stats, 0, sizeof(unsigned long long) * 136, ctx->stream) == cudaSuccess &&
              cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     }
     if (!ok) { free_ctx(ctx); return MD_ERR_NOMEM; }
@@ -447,6 +447,7 @@ static void fill_lk(md_ctx *ctx, LkParams &p, int prev_slot0, int next_slot0, co
     p.wsum = ctx->d_wsum;
     p.ph_pair0 = ph_pair0;
     p.ph_ready = 0;
+    p.stat_iters = ctx->d_stats + 8;
     p.img = ctx->d_img; p.der = ctx->d_der;
     p.prev_slot0 = prev_slot0; p.next_slot0 = next_slot0;
     p.pts_in = pts_in;
@@ -1116,13 +1117,15 @@ extern "C" int md_stats_get(md_ctx *ctx, md_stats *out)
 {
     if (!ctx || !out) return MD_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    unsigned long long v[4];
+    unsigned long long v[136];
     CK(cudaMemcpyAsync(v, ctx->d_stats, sizeof v, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->stats.last_H, ctx->d_H, sizeof(double) * 9, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stats.mask_pixels = (int64_t)v[0];
     ctx->stats.tracked = (int64_t)v[1];
     ctx->stats.inliers = (int64_t)v[2];
+    ctx->stats.lk_iterations = 0; ctx->stats.lk_levels = 0;
+    for (int i = 0; i < 64; i++) { ctx->stats.lk_iterations += (int64_t)v[8 + 2 * i]; ctx->stats.lk_levels += (int64_t)v[9 + 2 * i]; }
     ctx->stats.kernel_launches = g_md_launches;
     *out = ctx->stats;
     return MD_OK;
@@ -1132,7 +1135,7 @@ extern "C" int md_stats_reset(md_ctx *ctx)
 {
     if (!ctx) return MD_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(unsigned long long) * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_stats, 0, sizeof(unsigned long long) * 136, ctx->stream));
     int dev = ctx->stats.device;
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.device = dev;

@@ -92,6 +92,7 @@ struct LkParams {
     long long *wsum;         // [max_batch][nlev][P][5] window sums A11, A12, A22, sum I*Ix, sum I*Iy (k_window_sums)
     int ph_pair0;            // pair b of this launch uses arena ph_pair0 + b
     int ph_ready;            // 1 = the planes were already computed (launch_lk_planes on another stream)
+    unsigned long long *stat_iters;   // [64][2] nullable, striped: iterations executed, levels iterated (summed over points)
 };
 
 struct EgoParams {
@@ -172,7 +173,7 @@ struct md_ctx {
     int nblk_scan, nblk_acc;
     int *d_blockcnt, *d_kept_idx, *d_M, *d_hyp_valid, *d_counts, *d_inliers, *d_valid;
     double *d_hyp, *d_partial, *d_H, *d_Hinv;
-    unsigned long long *d_stats;   // [0] mask px, [1] tracked, [2] inliers
+    unsigned long long *d_stats;   // [0] mask px, [1] tracked, [2] inliers, [3] spare, [8 .. 136) 64 striped (LK iterations, LK levels) pairs
     float2 *d_traj;       // [P][F] trajectory staging (host-memory calls)
     int32_t *d_traj_len;
     int traj_F;
