@@ -120,7 +120,7 @@ static bool ensure_phase(md_ctx *ctx)
     const size_t bytes = pg.pair_elems * sizeof(int16_t) * ctx->cfg.max_batch;
     if (bytes > ((size_t)24 << 30)) return false;
     for (int l = 0; l < ctx->g.nlev; l++)
-        if ((size_t)pg.lv[l].pitch * 5 * sizeof(int) > 200 * 1024) return false;      // k_window_sums keeps 5 column sums per plane column
+        if ((ctx->cfg.pixel_step >> pg.lv[l].shift) > 470) return false;              // k_window_sums: one lattice step must fit its 512-column block
     if (cudaMalloc((void **)&ctx->d_phase, bytes) != cudaSuccess) { cudaGetLastError(); ctx->d_phase = nullptr; return false; }
     if (cudaMalloc((void **)&ctx->d_wsum, sizeof(long long) * 5 * (size_t)ctx->P * ctx->g.nlev * ctx->cfg.max_batch) != cudaSuccess) {
         cudaGetLastError();

@@ -112,3 +112,18 @@ def test_static_scene_min_vector_filter(capi, oracle):
     assert abs(int(res["num_vectors"][0]) - ref["num_vectors"]) <= 3
     assert np.array_equal(res["keep"][0] != 0, ref["keep"] != 0) or (res["keep"][0] != ref["keep"]).mean() < 0.002
     assert (res["mask"][0] == ref["mask"]).mean() >= 0.999
+
+
+def test_huge_pixel_step_falls_back_to_point_kernel(capi, oracle):
+    """pixel_step larger than the window-sums block: the grid mode must quietly use the per-point kernel (not fail)."""
+    import numpy as np
+    from motion_detection_b200 import synth
+    w, h = 1280, 720
+    frames, _ = synth.sequence(w, h, 2, seed=4, blobs=1)
+    ctx = capi.Context(width=w, height=h, max_batch=1, pixel_step=500, min_vector_size=0.2)
+    ctx.pyramid(frames[0], 0)
+    ctx.pyramid(frames[1], 1)
+    nxt, st = ctx.lk_flow(0, 1)
+    ref, rst = oracle.lk(frames[0], frames[1], ctx.grid_points())
+    assert np.array_equal(st, rst)
+    assert np.abs(nxt[st == 1] - ref[rst == 1]).max() < 1e-2
