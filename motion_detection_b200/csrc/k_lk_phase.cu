@@ -115,6 +115,7 @@ __global__ void __launch_bounds__(256) k_phase_planes(const PhParams q, int leve
 // add up 40 consecutive column sums from shared memory (int64).  Same integers as the per-point loops of k_lk_tma.
 #define WS_COLS 512
 #define WS_SEG 16
+#define WS_GRP 4
 __device__ __forceinline__ void ws_accumulate(int (&acc)[2][5], uint32_t wi, uint32_t wx, uint32_t wy, int sign)
 {
     const int i0 = (int)(wi & 0xffffu), i1 = (int)(wi >> 16);
@@ -126,7 +127,7 @@ __device__ __forceinline__ void ws_accumulate(int (&acc)[2][5], uint32_t wi, uin
 
 __global__ void __launch_bounds__(256) k_window_sums(const PhParams q, int level, int cp, int nchunk_x)
 {
-    __shared__ int ws_col[5][WS_COLS + 8];
+    __shared__ int ws_col[WS_GRP][5][WS_COLS + 8];
     const PhaseLevel PL = q.pg.lv[level];
     const int ncx = PL.ncx, cls = blockIdx.y, cx = cls % ncx, cy = cls / ncx, b = blockIdx.z;
     const int chunk = blockIdx.x % nchunk_x, seg = blockIdx.x / nchunk_x;
@@ -161,32 +162,39 @@ __global__ void __launch_bounds__(256) k_window_sums(const PhParams q, int level
             ws_accumulate(acc, __ldg(pI + o), __ldg(pX + o), __ldg(pY + o), 1);
         }
     }
-    for (int j = j0; j < j1; j++) {
-        if (j > j0 && col_on) {
-            const int top = oy0 + (j - 1 - j0) * step;          // previous origin row
+    // WS_GRP origin rows per barrier pair: the sliding column sums of a group are parked in shared memory, then all the points
+    // of the group's rows add up their 40 columns together (the horizontal phase of a single row keeps only 240 threads busy)
+    for (int jg = j0; jg < j1; jg += WS_GRP) {
+        const int gn = min(WS_GRP, j1 - jg);
+        __syncthreads();                                         // the previous group's readers are done
+        for (int g = 0; g < gn; g++) {
+            const int j = jg + g;
+            if (j > j0 && col_on) {
+                const int top = oy0 + (j - 1 - j0) * step;      // previous origin row
 #pragma unroll 5
-            for (int r = 0; r < step; r++) {
-                const size_t om = (size_t)(top + r) * wp, op = (size_t)(top + 40 + r) * wp;
-                const uint32_t mi = __ldg(pI + om), mx = __ldg(pX + om), my = __ldg(pY + om);
-                const uint32_t ai = __ldg(pI + op), ax = __ldg(pX + op), ay = __ldg(pY + op);
-                ws_accumulate(acc, mi, mx, my, -1);
-                ws_accumulate(acc, ai, ax, ay, 1);
+                for (int r = 0; r < step; r++) {
+                    const size_t om = (size_t)(top + r) * wp, op = (size_t)(top + 40 + r) * wp;
+                    const uint32_t mi = __ldg(pI + om), mx = __ldg(pX + om), my = __ldg(pY + om);
+                    const uint32_t ai = __ldg(pI + op), ax = __ldg(pX + op), ay = __ldg(pY + op);
+                    ws_accumulate(acc, mi, mx, my, -1);
+                    ws_accumulate(acc, ai, ax, ay, 1);
+                }
+            }
+            if (col_on) {
+#pragma unroll
+                for (int t = 0; t < 5; t++) { ws_col[g][t][2 * threadIdx.x] = acc[0][t]; ws_col[g][t][2 * threadIdx.x + 1] = acc[1][t]; }
             }
         }
-        __syncthreads();                                         // the previous row's readers are done
-        if (col_on) {
-#pragma unroll
-            for (int t = 0; t < 5; t++) { ws_col[t][2 * threadIdx.x] = acc[0][t]; ws_col[t][2 * threadIdx.x + 1] = acc[1][t]; }
-        }
         __syncthreads();
-        const int ky = ky0 + j * ncx;
-        for (int e = threadIdx.x; e < (i1 - i0) * 5; e += blockDim.x) {
-            const int pi = e / 5, t = e - pi * 5;
-            const int *v = &ws_col[t][ox0 + pi * step - c_lo];
+        const int per_row = (i1 - i0) * 5;
+        for (int e = threadIdx.x; e < gn * per_row; e += blockDim.x) {
+            const int g = e / per_row, e2 = e - g * per_row;
+            const int pi = e2 / 5, t = e2 - pi * 5;
+            const int *v = &ws_col[g][t][ox0 + pi * step - c_lo];
             long long sum = 0;
 #pragma unroll 8
             for (int c = 0; c < 40; c++) sum += v[c];
-            const int kx = kx0 + (i0 + pi) * ncx;
+            const int kx = kx0 + (i0 + pi) * ncx, ky = ky0 + (jg + g) * ncx;
             q.wsum[((((size_t)(q.pair0 + b) * q.g.nlev + level) * q.P) + (size_t)kx * q.gy + ky) * 5 + t] = sum;
         }
     }
