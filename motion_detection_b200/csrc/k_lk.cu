@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_lk(const LkParams p)
 
     for (int level = p.g.nlev - 1; level >= 0; level--) {
         const LevelGeom L = p.g.lv[level];
-        const float scale = 1.f / (float)(1 << level);
+        const float scale = lk_level_scale(level);
         float ppx = pt.x * scale, ppy = pt.y * scale;
         LkIterState s;
         if (level == p.g.nlev - 1) { s.npx = ppx; s.npy = ppy; }

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(256) k_phase_planes(const PhParams q, int leve
     int w00, w01, w10, w11;
     {
         // the fraction of a class representative's window origin, computed exactly like the LK kernels compute a point's
-        const float scale = 1.f / (float)(1 << level);
+        const float scale = lk_level_scale(level);
         const float ppx = __fsub_rn((float)(cx << PL.shift) * scale, q.half), ppy = __fsub_rn((float)(cy << PL.shift) * scale, q.half);
         lk_weights(__fsub_rn(ppx, floorf(ppx)), __fsub_rn(ppy, floorf(ppy)), w00, w01, w10, w11);
     }
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(256) k_window_sums(const PhParams q, int level
     const int chunk = blockIdx.x % nchunk_x, seg = blockIdx.x / nchunk_x;
     const int msk = (1 << level) - 1;
     const int step = q.ps >> PL.shift;                          // lattice step in plane pixels: ps / gcd(ps, 2^level)
-    const float scale = 1.f / (float)(1 << level);
+    const float scale = lk_level_scale(level);
     // first grid index of each axis that falls into this class; the class members are every ncx-th index from there
     int kx0 = -1, ky0 = -1;
     for (int t = 0; t < ncx; t++) {
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 :
 
     // request the window (I, Ix, Iy planes of the point's phase class) of `level`
     auto issue_P = [&](int level) {
-        const float scale = 1.f / (float)(1 << level);
+        const float scale = lk_level_scale(level);
         const float ppx = __fsub_rn(pt.x * scale, half), ppy = __fsub_rn(pt.y * scale, half);
         const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
         if (ipx < -WIN || ipx >= p.g.lv[level].w || ipy < -WIN || ipy >= p.g.lv[level].h) return;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 :
 
     for (int level = p.g.nlev - 1; level >= 0; level--) {
         const int Lw = p.g.lv[level].w, Lh = p.g.lv[level].h;
-        const float scale = 1.f / (float)(1 << level);
+        const float scale = lk_level_scale(level);
         float ppx = pt.x * scale, ppy = pt.y * scale;
         LkIterState s;
         if (level == p.g.nlev - 1) { s.npx = ppx; s.npy = ppy; }

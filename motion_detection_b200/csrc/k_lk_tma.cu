@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) k_lk_tma(const LkParam
 
     // request the previous-frame patch + Scharr planes of `level` (no-op when the window is out of range there)
     auto issue_I = [&](int level) {
-        const float scale = 1.f / (float)(1 << level);
+        const float scale = lk_level_scale(level);
         const float ppx = __fsub_rn(pt.x * scale, half), ppy = __fsub_rn(pt.y * scale, half);
         const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
         if (ipx < -WIN || ipx >= p.g.lv[level].w || ipy < -WIN || ipy >= p.g.lv[level].h) return;
@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) k_lk_tma(const LkParam
 
     for (int level = p.g.nlev - 1; level >= 0; level--) {
         const int Lw = p.g.lv[level].w, Lh = p.g.lv[level].h;
-        const float scale = 1.f / (float)(1 << level);
+        const float scale = lk_level_scale(level);
         float ppx = pt.x * scale, ppy = pt.y * scale;
         LkIterState s;
         if (level == p.g.nlev - 1) { s.npx = ppx; s.npy = ppy; }

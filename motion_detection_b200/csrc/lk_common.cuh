@@ -18,6 +18,9 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// 2^-level exactly (what 1.f / (float)(1 << level) evaluates to), without the division routine
+__device__ __forceinline__ float lk_level_scale(int level) { return __int_as_float((127 - level) << 23); }
+
 __device__ __forceinline__ void lk_weights(float a, float b, int &w00, int &w01, int &w10, int &w11)
 {
     float na = __fsub_rn(1.f, a), nb = __fsub_rn(1.f, b);
