@@ -127,3 +127,25 @@ def test_huge_pixel_step_falls_back_to_point_kernel(capi, oracle):
     ref, rst = oracle.lk(frames[0], frames[1], ctx.grid_points())
     assert np.array_equal(st, rst)
     assert np.abs(nxt[st == 1] - ref[rst == 1]).max() < 1e-2
+
+
+def test_lk_large_displacement_restages_the_next_frame_tile(capi, oracle):
+    """A field moving 13 x 9 px per frame: at every pyramid level the window drifts out of the staged next-frame tile
+    (margins 8 x 3 px), so the TMA restage path runs in both LK kernels; results must still be the oracle's."""
+    import numpy as np
+    from motion_detection_b200 import synth
+    w, h = 640, 480
+    frames, _ = synth.sequence(w, h, 2, seed=8, camera=False, blobs=0, whole_field=(13.0, -9.0))
+    ctx = capi.Context(width=w, height=h, max_batch=1, pixel_step=10, min_vector_size=0.2)
+    ctx.pyramid(frames[0], 0)
+    ctx.pyramid(frames[1], 1)
+    pts = ctx.grid_points()
+    a, sa = ctx.lk_flow(0, 1)                    # phase-plane kernel
+    b, sb = ctx.lk_flow(0, 1, pts)               # per-point kernel
+    assert np.array_equal(sa, sb) and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    ref, rst = oracle.lk(frames[0], frames[1], pts)
+    assert (sa != rst).mean() < 0.005
+    ok = (sa == 1) & (rst == 1)
+    assert np.linalg.norm(a[ok] - ref[ok], axis=1).mean() < 0.01
+    inner = ok & (pts[:, 0] > 80) & (pts[:, 0] < w - 80) & (pts[:, 1] > 80) & (pts[:, 1] < h - 80)
+    assert np.abs(np.median(a[inner] - pts[inner], axis=0) - np.array([13.0, -9.0])).max() < 0.1
