@@ -44,3 +44,30 @@ def test_skip_frames_like_the_node(capi, oracle):
         ref = oracle.process_pair(kept[p], kept[p + 1], min_vector_size=0.4, seed=1 + p)
         assert np.linalg.norm(res["H"][p] - ref["H"]) / np.linalg.norm(ref["H"]) < 1e-4
         assert (res["mask"][p] == ref["mask"]).mean() >= 0.999
+
+
+def test_two_contexts_interleaved_on_one_gpu(capi):
+    """Several camera streams per GPU (streams.shard_streams with more streams than GPUs): contexts share nothing -- calls
+    interleaved between two contexts give exactly what each context gives alone."""
+    w, h = 320, 240
+    fa, _ = synth.sequence(w, h, 9, seed=11, blobs=2)
+    fb, _ = synth.sequence(w, h, 9, seed=12, blobs=1)
+
+    def alone(frames, seed):
+        ctx = capi.Context(width=w, height=h, max_batch=4, pixel_step=10, min_vector_size=0.2, seed=seed)
+        r1 = ctx.process_batch(frames[:5])
+        r2 = ctx.process_batch(frames[5:], chain=True)
+        ctx.close()
+        return r1, r2
+
+    a1, a2 = alone(fa, 3)
+    b1, b2 = alone(fb, 4)
+    ca = capi.Context(width=w, height=h, max_batch=4, pixel_step=10, min_vector_size=0.2, seed=3)
+    cb = capi.Context(width=w, height=h, max_batch=4, pixel_step=10, min_vector_size=0.2, seed=4)
+    x1 = ca.process_batch(fa[:5])
+    y1 = cb.process_batch(fb[:5])
+    x2 = ca.process_batch(fa[5:], chain=True)
+    y2 = cb.process_batch(fb[5:], chain=True)
+    for got, ref in ((x1, a1), (x2, a2), (y1, b1), (y2, b2)):
+        for k in ("next", "status", "keep", "H", "num_vectors", "inliers", "mask"):
+            assert np.array_equal(got[k], ref[k]), k
