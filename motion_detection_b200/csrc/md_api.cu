@@ -161,6 +161,8 @@ static void free_ctx(md_ctx *ctx)
     for (int i = 0; i < 8; i++) { if (ctx->ev_k1[i]) cudaEventDestroy(ctx->ev_k1[i]); if (ctx->ev_lk[i]) cudaEventDestroy(ctx->ev_lk[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    for (int i = 0; i < 3; i++) if (ctx->ev_lv[i]) cudaEventDestroy(ctx->ev_lv[i]);
+    for (int i = 0; i < 2; i++) if (ctx->aux_lv[i]) cudaStreamDestroy(ctx->aux_lv[i]);
     if (ctx->aux_pyr) cudaStreamDestroy(ctx->aux_pyr);
     if (ctx->aux_post) cudaStreamDestroy(ctx->aux_post);
     if (ctx->copy_in) cudaStreamDestroy(ctx->copy_in);
@@ -201,6 +203,9 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
         // has room, instead of queueing behind LK's tens of thousands of CTAs
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        sok = sok && cudaStreamCreateWithPriority(&ctx->aux_lv[0], cudaStreamNonBlocking, hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&ctx->aux_lv[1], cudaStreamNonBlocking, hi) == cudaSuccess;
+        for (int i = 0; i < 3 && sok; i++) sok = cudaEventCreateWithFlags(&ctx->ev_lv[i], cudaEventDisableTiming) == cudaSuccess;
         sok = sok && cudaStreamCreateWithPriority(&ctx->aux_pyr, cudaStreamNonBlocking, hi) == cudaSuccess &&
               cudaStreamCreateWithPriority(&ctx->aux_post, cudaStreamNonBlocking, hi) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
@@ -605,7 +610,12 @@ static int run_planes(md_ctx *ctx, int prev0, int p0, int p1, cudaStream_t s)
     const int ns = ctx->g.nslots;
     LkParams lp;
     fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, ctx->P, ctx->d_next, ctx->d_status, p0);
-    if (lp.ph && ctx->ph_maps.valid && lp.win == 40) CK(launch_lk_planes(lp, p1 - p0, s));
+    if (lp.ph && ctx->ph_maps.valid && lp.win == 40) {
+        LkSideStreams side;
+        side.s[0] = ctx->aux_lv[0]; side.s[1] = ctx->aux_lv[1];
+        for (int i = 0; i < 3; i++) side.ev[i] = ctx->ev_lv[i];
+        CK(launch_lk_planes(lp, p1 - p0, s, &side));
+    }
     return MD_OK;
 }
 
