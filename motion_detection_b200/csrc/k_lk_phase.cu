@@ -377,49 +377,35 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 :
 }
 
 // the phase planes of the PREVIOUS frames of `pairs` pairs (k_lk_phase reads them); may run on another stream than LK
-// `side` (nullable): two more streams + three events.  The planes and sums of different pyramid levels are independent, and
-// when a batch starts nothing else runs yet: level 0 / levels 1-2 / levels 3+ then run on three streams at once (forked
-// from and joined back into `s`), so the exposed head of the batch is the longest level group instead of the sum of all.
-cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s, const LkSideStreams *side)
+// planes + window sums of pyramid levels l0..l1 (the levels are independent of each other)
+cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1, cudaStream_t s)
 {
     PhParams q;
     q.g = p.g; q.pg = p.pg; q.img = p.img; q.der = p.der; q.ph = p.ph; q.prev_slot0 = p.prev_slot0; q.pair0 = p.ph_pair0;
     q.wsum = p.wsum; q.P = p.P; q.ps = p.ps; q.gy = p.gy; q.gx = p.P / p.gy;
     q.half = (p.win - 1) * 0.5f;
-    for (int l = 0; l < p.g.nlev; l++)
-        if ((p.ps >> p.pg.lv[l].shift) > WS_COLS - 42) return cudaErrorInvalidConfiguration;   // one point per chunk must fit
-    auto level = [&](int l, cudaStream_t st) {
+    for (int l = l0; l <= l1 && l < p.g.nlev; l++) {
         const PhaseLevel &PL = p.pg.lv[l];
+        const int step = p.ps >> PL.shift;
+        if (step > WS_COLS - 42) return cudaErrorInvalidConfiguration;          // one point per chunk must fit (pixel_step <= 470)
         const int threads = (PL.pitch / 8) * ((PL.h + 3) / 4);
         dim3 grid((threads + 255) / 256, PL.ncx * PL.ncx, pairs);
-        k_phase_planes<<<grid, 256, 0, st>>>(q, l);
-        const int step = p.ps >> PL.shift;
+        k_phase_planes<<<grid, 256, 0, s>>>(q, l);
         const int cp = (WS_COLS - 42) / step + 1;                                // lattice columns per CTA
         const int nx = (q.gx + PL.ncx - 1) / PL.ncx, ny = (q.gy + PL.ncx - 1) / PL.ncx;   // upper bounds per class
         const int nchunk_x = (nx + cp - 1) / cp, nseg = (ny + WS_SEG - 1) / WS_SEG;
-        k_window_sums<<<dim3(nchunk_x * nseg, PL.ncx * PL.ncx, pairs), 256, 0, st>>>(q, l, cp, nchunk_x);
-    };
-    const bool fan = side && side->s[0] && side->s[1] && p.g.nlev >= 3;
-    if (fan) {
-        cudaEventRecord(side->ev[0], s);
-        cudaStreamWaitEvent(side->s[0], side->ev[0], 0);
-        cudaStreamWaitEvent(side->s[1], side->ev[0], 0);
+        k_window_sums<<<dim3(nchunk_x * nseg, PL.ncx * PL.ncx, pairs), 256, 0, s>>>(q, l, cp, nchunk_x);
+        MD_COUNT_LAUNCH(2);
     }
-    for (int l = 0; l < p.g.nlev; l++) level(l, !fan || l == 0 ? s : (l <= 2 ? side->s[0] : side->s[1]));
-    if (fan) {
-        cudaEventRecord(side->ev[1], side->s[0]);
-        cudaEventRecord(side->ev[2], side->s[1]);
-        cudaStreamWaitEvent(s, side->ev[1], 0);
-        cudaStreamWaitEvent(s, side->ev[2], 0);
-    }
-    MD_COUNT_LAUNCH(2 * p.g.nlev);
     return cudaGetLastError();
 }
+
+cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s) { return launch_lk_planes_levels(p, pairs, 0, p.g.nlev - 1, s); }
 
 cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pairs, cudaStream_t s)
 {
     if (!p.ph_ready) {
-        cudaError_t e0 = launch_lk_planes(p, pairs, s, nullptr);
+        cudaError_t e0 = launch_lk_planes(p, pairs, s);
         if (e0 != cudaSuccess) return e0;
     }
     static int warps_env = -1;

@@ -158,27 +158,48 @@ __global__ void __launch_bounds__(256) k_scharr(const uint8_t *__restrict__ img,
         for (int i = 0; i < 4 && x + i < L.w; i++) reinterpret_cast<uint32_t *>(dst)[i] = o[i];
 }
 
-cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot0, int nframes, const uint8_t *frames,
-                           int channels, int fpitch, long long fstride, cudaStream_t s)
+// The three parts of the build, separately launchable (md_process_batch spreads the levels over several streams):
+// level-0 image (gray conversion + padding), pyrDown for levels l0..l1 (needs level l0-1), Scharr planes for levels l0..l1.
+cudaError_t launch_pyramid_level0(const PyrGeom &g, uint8_t *img, int slot0, int nframes, const uint8_t *frames, int channels,
+                                  int fpitch, long long fstride, cudaStream_t s)
 {
-    {
-        const LevelGeom &L = g.lv[0];
-        dim3 grid((L.pitch / 4 + 255) / 256, L.rows, nframes);
-        if (channels == 1)
-            k_level0<1><<<grid, 256, 0, s>>>(frames, fpitch, fstride, img, g.slot_img_bytes, slot0, g.nslots, L, g.padx, g.pady);
-        else
-            k_level0<3><<<grid, 256, 0, s>>>(frames, fpitch, fstride, img, g.slot_img_bytes, slot0, g.nslots, L, g.padx, g.pady);
-    }
-    for (int l = 1; l < g.nlev; l++) {
+    const LevelGeom &L = g.lv[0];
+    dim3 grid((L.pitch / 4 + 255) / 256, L.rows, nframes);
+    if (channels == 1)
+        k_level0<1><<<grid, 256, 0, s>>>(frames, fpitch, fstride, img, g.slot_img_bytes, slot0, g.nslots, L, g.padx, g.pady);
+    else
+        k_level0<3><<<grid, 256, 0, s>>>(frames, fpitch, fstride, img, g.slot_img_bytes, slot0, g.nslots, L, g.padx, g.pady);
+    MD_COUNT_LAUNCH(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pyramid_down(const PyrGeom &g, uint8_t *img, int slot0, int nframes, int l0, int l1, cudaStream_t s)
+{
+    for (int l = l0 < 1 ? 1 : l0; l <= l1 && l < g.nlev; l++) {
         const LevelGeom &D = g.lv[l];
         dim3 grid((D.pitch / 4 + 255) / 256, D.rows, nframes);
         k_pyrdown<<<grid, 256, 0, s>>>(img, g.slot_img_bytes, slot0, g.nslots, g.lv[l - 1], D, g.padx, g.pady);
+        MD_COUNT_LAUNCH(1);
     }
-    MD_COUNT_LAUNCH(2 * g.nlev);
-    for (int l = 0; l < g.nlev; l++) {
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pyramid_scharr(const PyrGeom &g, uint8_t *img, short2 *der, int slot0, int nframes, int l0, int l1, cudaStream_t s)
+{
+    for (int l = l0; l <= l1 && l < g.nlev; l++) {
         const LevelGeom &L = g.lv[l];
         dim3 grid(((L.w + 3) / 4 + 127) / 128, L.h, nframes);
         k_scharr<<<grid, 128, 0, s>>>(img, der, g.slot_img_bytes, g.slot_der_elems, slot0, g.nslots, L, g.padx, g.pady);
+        MD_COUNT_LAUNCH(1);
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot0, int nframes, const uint8_t *frames,
+                           int channels, int fpitch, long long fstride, cudaStream_t s)
+{
+    cudaError_t e = launch_pyramid_level0(g, img, slot0, nframes, frames, channels, fpitch, fstride, s);
+    if (e == cudaSuccess) e = launch_pyramid_down(g, img, slot0, nframes, 1, g.nlev - 1, s);
+    if (e == cudaSuccess) e = launch_pyramid_scharr(g, img, der, slot0, nframes, 0, g.nlev - 1, s);
+    return e;
 }

@@ -161,7 +161,7 @@ static void free_ctx(md_ctx *ctx)
     for (int i = 0; i < 8; i++) { if (ctx->ev_k1[i]) cudaEventDestroy(ctx->ev_k1[i]); if (ctx->ev_lk[i]) cudaEventDestroy(ctx->ev_lk[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    for (int i = 0; i < 3; i++) if (ctx->ev_lv[i]) cudaEventDestroy(ctx->ev_lv[i]);
+    for (int i = 0; i < 4; i++) if (ctx->ev_lv[i]) cudaEventDestroy(ctx->ev_lv[i]);
     for (int i = 0; i < 2; i++) if (ctx->aux_lv[i]) cudaStreamDestroy(ctx->aux_lv[i]);
     if (ctx->aux_pyr) cudaStreamDestroy(ctx->aux_pyr);
     if (ctx->aux_post) cudaStreamDestroy(ctx->aux_post);
@@ -205,7 +205,7 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         sok = sok && cudaStreamCreateWithPriority(&ctx->aux_lv[0], cudaStreamNonBlocking, hi) == cudaSuccess &&
               cudaStreamCreateWithPriority(&ctx->aux_lv[1], cudaStreamNonBlocking, hi) == cudaSuccess;
-        for (int i = 0; i < 3 && sok; i++) sok = cudaEventCreateWithFlags(&ctx->ev_lv[i], cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; i < 4 && sok; i++) sok = cudaEventCreateWithFlags(&ctx->ev_lv[i], cudaEventDisableTiming) == cudaSuccess;
         sok = sok && cudaStreamCreateWithPriority(&ctx->aux_pyr, cudaStreamNonBlocking, hi) == cudaSuccess &&
               cudaStreamCreateWithPriority(&ctx->aux_post, cudaStreamNonBlocking, hi) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
@@ -603,19 +603,49 @@ extern "C" int md_motion_mask(md_ctx *ctx, const uint8_t *prev, const uint8_t *c
 }
 
 // ---- the chain -------------------------------------------------------------------------------------------------------
-// the sub-pixel phase planes of pairs [p0, p1) (grid-mode LK only); they depend on the pyramids of the pairs' first frames
-static int run_planes(md_ctx *ctx, int prev0, int p0, int p1, cudaStream_t s)
+// Everything LK of pairs [p0, p1) needs: the pyramids of the chunk's `nframes` new frames (slots slot0 ...) and the phase
+// planes + window sums of the pairs' first frames, spread over three streams by pyramid level -- level 0 on `s`, levels 1-2
+// and levels 3+ on the two level streams (forked from / joined into `s`).  The levels only meet in the pyrDown chain, so
+// when a batch starts and nothing else runs yet, the exposed head is the longest level group instead of the sum of all.
+static int run_prep(md_ctx *ctx, int prev0, int p0, int p1, int slot0, int nframes, const uint8_t *frames, int channels, int fpitch,
+                    long long fstride, cudaStream_t s)
 {
-    if (ctx->cfg.flow_engine == MD_FLOW_VARFLOW) return MD_OK;
-    const int ns = ctx->g.nslots;
+    const PyrGeom &g = ctx->g;
+    const int ns = g.nslots, nl = g.nlev;
     LkParams lp;
-    fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, ctx->P, ctx->d_next, ctx->d_status, p0);
-    if (lp.ph && ctx->ph_maps.valid && lp.win == 40) {
-        LkSideStreams side;
-        side.s[0] = ctx->aux_lv[0]; side.s[1] = ctx->aux_lv[1];
-        for (int i = 0; i < 3; i++) side.ev[i] = ctx->ev_lv[i];
-        CK(launch_lk_planes(lp, p1 - p0, s, &side));
+    bool planes = false;
+    if (ctx->cfg.flow_engine != MD_FLOW_VARFLOW) {
+        fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, ctx->P, ctx->d_next, ctx->d_status, p0);
+        planes = lp.ph && ctx->ph_maps.valid && lp.win == 40;
     }
+    if (nl < 3) {
+        if (nframes > 0) CK(launch_pyramid(g, ctx->d_img, ctx->d_der, slot0, nframes, frames, channels, fpitch, fstride, s));
+        if (planes) CK(launch_lk_planes(lp, p1 - p0, s));
+        return MD_OK;
+    }
+    cudaStream_t s1 = ctx->aux_lv[0], s2 = ctx->aux_lv[1];
+    const int lmid = 2;                                          // levels 1..2 on s1, 3.. on s2
+    if (nframes > 0) CK(launch_pyramid_level0(g, ctx->d_img, slot0, nframes, frames, channels, fpitch, fstride, s));
+    CK(cudaEventRecord(ctx->ev_lv[0], s));
+    CK(cudaStreamWaitEvent(s1, ctx->ev_lv[0], 0));
+    if (nframes > 0) CK(launch_pyramid_down(g, ctx->d_img, slot0, nframes, 1, lmid, s1));
+    CK(cudaEventRecord(ctx->ev_lv[1], s1));
+    CK(cudaStreamWaitEvent(s2, ctx->ev_lv[1], 0));
+    if (nframes > 0) {
+        CK(launch_pyramid_down(g, ctx->d_img, slot0, nframes, lmid + 1, nl - 1, s2));
+        CK(launch_pyramid_scharr(g, ctx->d_img, ctx->d_der, slot0, nframes, 0, 0, s));
+        CK(launch_pyramid_scharr(g, ctx->d_img, ctx->d_der, slot0, nframes, 1, lmid, s1));
+        CK(launch_pyramid_scharr(g, ctx->d_img, ctx->d_der, slot0, nframes, lmid + 1, nl - 1, s2));
+    }
+    if (planes) {
+        CK(launch_lk_planes_levels(lp, p1 - p0, 0, 0, s));
+        CK(launch_lk_planes_levels(lp, p1 - p0, 1, lmid, s1));
+        CK(launch_lk_planes_levels(lp, p1 - p0, lmid + 1, nl - 1, s2));
+    }
+    CK(cudaEventRecord(ctx->ev_lv[2], s1));
+    CK(cudaEventRecord(ctx->ev_lv[3], s2));
+    CK(cudaStreamWaitEvent(s, ctx->ev_lv[2], 0));
+    CK(cudaStreamWaitEvent(s, ctx->ev_lv[3], 0));
     return MD_OK;
 }
 
@@ -674,7 +704,7 @@ static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
 // adding up per chunk.  With host buffers the H2D of chunk i+1 and the D2H of chunk i-1 overlap as well (PCIe is full
 // duplex; the results are complete on return).
 //   copy_in : H2D(c)                                (host buffers only)
-//   aux_pyr : K1(c) + phase planes(c)  after H2D(c) / after the work already queued on the context's stream
+//   aux_pyr (+ two level streams): K1(c) + phase planes(c) + window sums(c)  after H2D(c) / after the work already queued on the context's stream
 //   stream  : LK(c)                                 after K1(c)
 //   aux_post: K3(c), K4(c)     after LK(c)
 //   copy_out: D2H(c)           after K4(c)          (host buffers only)
@@ -799,11 +829,13 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
         }
         if (ctx->profile) CK(cudaEventRecord(ctx->ev[0], s));
         if (trace) cudaEventRecord(tev[i][0], s_pyr);
-        if (fb > fa) CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, (new0 + fa) % ns, fb - fa, df + fa * ds, fr->channels, dp, ds, s_pyr));
+        if (serial) {
+            if (fb > fa) CK(launch_pyramid(ctx->g, ctx->d_img, ctx->d_der, (new0 + fa) % ns, fb - fa, df + fa * ds, fr->channels, dp, ds, s_pyr));
+        }
         if (ctx->profile) CK(cudaEventRecord(ctx->ev[1], s));
         if (!serial) {
-            // the phase planes ride with the pyramids on the side stream: the context's stream runs LK kernels back to back
-            r = run_planes(ctx, prev0, p0, p1, s_pyr);
+            // pyramids, phase planes and window sums ride on the side streams: the context's stream runs LK kernels back to back
+            r = run_prep(ctx, prev0, p0, p1, (new0 + fa) % ns, fb - fa, df + fa * ds, fr->channels, dp, ds, s_pyr);
             if (r != MD_OK) return r;
             if (trace) cudaEventRecord(tev[i][1], s_pyr);
             CK(cudaEventRecord(ctx->ev_k1[i], s_pyr));

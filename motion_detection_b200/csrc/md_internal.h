@@ -149,7 +149,7 @@ struct md_ctx {
     cudaStream_t aux_pyr, aux_post;     // side streams of the kernel pipeline (K1 / K3+K4 beside LK), higher priority
     cudaEvent_t ev_k1[8], ev_lk[8], ev_fork, ev_join;
     cudaStream_t aux_lv[2];             // level groups of the phase planes / window sums (launch_lk_planes)
-    cudaEvent_t ev_lv[3];
+    cudaEvent_t ev_lv[4];
     std::string err;
     int sm_count;
 
@@ -220,8 +220,12 @@ cudaError_t launch_compact_outliers(const float2 *traj_c, const uint8_t *outlier
 cudaError_t launch_cluster(const float2 *pts, const int *n_ptr, int n_max, double thr, int min_size, float *m2, int *cand, int *ncand,
                            int *label, int *nclusters, int *sizes, int *box, int *nout, int32_t *out_box, int32_t *out_size,
                            int32_t *out_id, cudaStream_t s);
-struct LkSideStreams { cudaStream_t s[2]; cudaEvent_t ev[3]; };
-cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s, const LkSideStreams *side);
+cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1, cudaStream_t s);
+cudaError_t launch_pyramid_level0(const PyrGeom &g, uint8_t *img, int slot0, int nframes, const uint8_t *frames, int channels,
+                                  int fpitch, long long fstride, cudaStream_t s);
+cudaError_t launch_pyramid_down(const PyrGeom &g, uint8_t *img, int slot0, int nframes, int l0, int l1, cudaStream_t s);
+cudaError_t launch_pyramid_scharr(const PyrGeom &g, uint8_t *img, short2 *der, int slot0, int nframes, int l0, int l1, cudaStream_t s);
 cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pairs, cudaStream_t s);
 cudaError_t launch_traj_step(float2 *pts_cur, const float2 *next, const uint8_t *status, float2 *traj, int32_t *len,
                              int P, int F, int w, int h, cudaStream_t s);
