@@ -476,6 +476,41 @@ def main():
         assert int(pin["inl"].min()) > 0
         ctx2.close()
 
+    # ---- two camera streams on this GPU (two contexts, two CUDA streams): the head and tail of one stream's batch are filled by
+    # the other stream's LK.  An extra figure; `value` above stays the single-stream number.
+    multi = None
+    if not a.no_e2e:
+        ctxs, strs, outs2 = [ctx], [stream], [outs]
+        cB = capi.Context(width=w, height=h, max_batch=B, pixel_step=a.pixel_step, min_vector_size=0.2, seed=2, device=local,
+                          flow_engine=engine)
+        sB = torch.cuda.Stream(device=dev)
+        cB.set_stream(sB.cuda_stream)
+        bufs = [torch.empty_like(t_) for t_ in (d_next, d_status, d_keep, d_H, d_nv, d_inl, d_mask)]
+        oB = capi.MdOutputs(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), bufs[4].data_ptr(),
+                            bufs[5].data_ptr(), bufs[6].data_ptr(), w, w * h)
+        ctxs.append(cB); strs.append(sB); outs2.append(oB)
+
+        def step2(i):
+            for c_, o_ in zip(ctxs, outs2):
+                c_.raw_process_batch(sets[i % R].data_ptr(), 1, w, frame_bytes, B + 1, False, o_, capi.MD_MEM_DEVICE)
+
+        for i in range(max(a.warmup, 1)):
+            step2(i)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in strs]
+        for (e0_, _), s_ in zip(ev, strs):
+            e0_.record(s_)
+        n2 = max(3, a.steps // 2)
+        for i in range(n2):
+            step2(i)
+        for (_, e1_), s_ in zip(ev, strs):
+            e1_.record(s_)
+        barrier()
+        # both streams start together; the job ends when the slower one does
+        ms2 = streams.max_over_ranks(max(ev[0][0].elapsed_time(ev[0][1]), ev[0][0].elapsed_time(ev[1][1])))
+        multi = {"streams_per_gpu": 2, "value": world * 2 * B * n2 / (ms2 * 1e-3), "unit": UNIT}
+        cB.close()
+
     # ---- per-stream statistics gathered over NCCL (the only collective; off the frame path)
     st = ctx.stats()
     gathered = streams.gather_stats({k: st[k] for k in ("pairs", "mask_pixels", "tracked", "inliers")})
@@ -525,7 +560,7 @@ def main():
                        "parallelism": "independent camera streams, one per GPU, no frame-path collective"},
             "mpx_per_s": value * N / 1e6,
             "roofline": roofline, "lk_work": lk_taps, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "stream_stats": gathered,
+            "clocks": clocks, "stream_stats": gathered, "two_streams_per_gpu": multi,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
