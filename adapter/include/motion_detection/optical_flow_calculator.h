@@ -1,7 +1,7 @@
 /* optical_flow_calculator.h -- drop-in replacement of common/include/motion_detection/optical_flow_calculator.h:13-33.
  * Same class name and public signatures; the bodies forward to libmotion_b200.so (include/motion_b200.h).
- * Viz / file-IO members of the reference (drawMotionField, writeFlow, writeTrajectories, superPixelFlow,
- * calculateCompensatedFlow) are outside the accelerated path and stay with the reference's own sources. */
+ * Viz / file-IO members of the reference (drawMotionField, writeFlow, writeTrajectories) and superPixelFlow (SLIC, uncalled)
+ * are outside the accelerated path and stay with the reference's own sources. */
 #ifndef OPTICAL_FLOW_CALCULATOR_H_
 #define OPTICAL_FLOW_CALCULATOR_H_
 
@@ -22,6 +22,9 @@ class OpticalFlowCalculator
         /* common/src/optical_flow_calculator.cpp:133-257 */
         int calculateOpticalFlowTrajectory(const std::vector<cv::Mat> &images, cv::Mat &optical_flow_vectors, std::vector<std::vector<cv::Point2f> > &trajectories, int pixel_step, cv::Mat &comp, double min_vector_size);
 
+        /* common/src/optical_flow_calculator.cpp:259-330: the grid LK alone, 2 pyramid levels above the image, vectors over 1 px */
+        int calculateCompensatedFlow(const cv::Mat &image1, const cv::Mat &image2, cv::Mat &optical_flow_vectors, int pixel_step);
+
         /* common/src/optical_flow_calculator.cpp:417-464 (the dense flow itself; the reference only draws it) */
         void varFlow(const cv::Mat &image1, const cv::Mat &image2, cv::Mat &optical_flow, cv::Mat &optical_flow_vectors);
 
@@ -40,6 +43,8 @@ class OpticalFlowCalculator
         void release();
         static void ensureFlowMat(cv::Mat &m, int rows, int cols);
         md_ctx *ctx_;
+        md_ctx *ctx2_;                 /* calculateCompensatedFlow: MAX_LEVEL = 2 */
+        int w2_, h2_, ps2_;
         int w_, h_, ps_, batch_, device_, ego_mode_;
         bool morph_;
         unsigned seed_;

@@ -15,7 +15,7 @@
 
 // ---------------------------------------------------------------------------------------------------------------
 OpticalFlowCalculator::OpticalFlowCalculator()
-    : ctx_(0), w_(0), h_(0), ps_(0), batch_(0), device_(0), ego_mode_(MD_EGO_RANSAC_HOMOGRAPHY), morph_(true), seed_(1), minvec_(0)
+    : ctx_(0), ctx2_(0), w2_(0), h2_(0), ps2_(0), w_(0), h_(0), ps_(0), batch_(0), device_(0), ego_mode_(MD_EGO_RANSAC_HOMOGRAPHY), morph_(true), seed_(1), minvec_(0)
 {
     for (int i = 0; i < 9; i++) last_H_[i] = (i % 4 == 0) ? 1.0 : 0.0;
 }
@@ -25,7 +25,8 @@ OpticalFlowCalculator::~OpticalFlowCalculator() { release(); }
 void OpticalFlowCalculator::release()
 {
     if (ctx_) md_destroy(ctx_);
-    ctx_ = 0;
+    if (ctx2_) md_destroy(ctx2_);
+    ctx_ = 0; ctx2_ = 0;
 }
 
 const char *OpticalFlowCalculator::lastError() const { return md_last_error(ctx_); }
@@ -141,6 +142,50 @@ int OpticalFlowCalculator::calculateOpticalFlowTrajectory(const std::vector<cv::
         for (int f = 0; f < F; f++) t[f] = cv::Point2f(traj[((size_t)i * F + f) * 2], traj[((size_t)i * F + f) * 2 + 1]);
         trajectories.push_back(t);
     }
+    return num_vectors;
+}
+
+// The grid LK alone (cpp:259-330): MAX_LEVEL = 2, vectors kept when |dx| or |dy| exceeds 1 px.  (The reference falls off the
+// end of this non-void function; the count it computes is returned here.)
+int OpticalFlowCalculator::calculateCompensatedFlow(const cv::Mat &image1, const cv::Mat &image2, cv::Mat &optical_flow_vectors, int pixel_step)
+{
+    const int w = image1.cols, h = image1.rows, ch = image1.channels();
+    if (image1.empty() || image2.empty() || image2.cols != w || image2.rows != h || image2.channels() != ch || (ch != 1 && ch != 3) || pixel_step < 1)
+        return 0;
+    if (!ctx2_ || w != w2_ || h != h2_ || pixel_step != ps2_) {
+        if (ctx2_) md_destroy(ctx2_);
+        ctx2_ = 0;
+        md_config cfg;
+        md_config_default(&cfg);
+        cfg.width = w; cfg.height = h; cfg.pixel_step = pixel_step; cfg.max_batch = 1;
+        cfg.lk_max_level = 2;                                   // cpp:261
+        cfg.min_vector_size = 1.0;                              // cpp:301
+        if (md_create(&cfg, device_, &ctx2_) != MD_OK) { ctx2_ = 0; return 0; }
+        w2_ = w; h2_ = h; ps2_ = pixel_step;
+    }
+    std::vector<uint8_t> g1((size_t)w * h), g2((size_t)w * h);
+    const cv::Mat *im[2] = {&image1, &image2};
+    uint8_t *g[2] = {g1.data(), g2.data()};
+    for (int k = 0; k < 2; k++) {
+        if (ch == 3) {
+            if (md_gray_u8(ctx2_, im[k]->data, (int32_t)im[k]->step, w, h, g[k], w, MD_MEM_HOST) != MD_OK) return 0;   // cpp:270-271
+        } else {
+            for (int y = 0; y < h; y++) std::memcpy(g[k] + (size_t)y * w, im[k]->data + (size_t)y * im[k]->step, (size_t)w);
+        }
+        if (md_pyramid_u8(ctx2_, g[k], w, k, MD_MEM_HOST) != MD_OK) return 0;
+    }
+    const int P = md_grid_size(ctx2_);
+    std::vector<float> p1(2 * (size_t)P), p2(2 * (size_t)P);
+    std::vector<uint8_t> st(P), keep(P);
+    md_grid_points(ctx2_, p1.data());
+    if (md_lk_flow(ctx2_, 0, 1, 0, P, p2.data(), st.data(), MD_MEM_HOST) != MD_OK) return 0;
+    for (int i = 0; i < P; i++) {
+        const float xd = p2[2 * i] - p1[2 * i], yd = p2[2 * i + 1] - p1[2 * i + 1];
+        keep[i] = st[i] && (std::abs(xd) > 1.0 || std::abs(yd) > 1.0);
+    }
+    ensureFlowMat(optical_flow_vectors, h, w);
+    int num_vectors = 0;
+    write_flow(optical_flow_vectors, p1.data(), p2.data(), st.data(), keep.data(), P, num_vectors);
     return num_vectors;
 }
 

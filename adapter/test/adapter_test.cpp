@@ -40,6 +40,15 @@ int main(int argc, char **argv)
     for (int x = 0; x < w; x += 10)
         for (int y = 0; y < h; y += 10) put(fo, &flow.at<cv::Vec4d>(y, x), sizeof(cv::Vec4d));
 
+    // --- calculateCompensatedFlow: the grid LK alone with 2 levels above the image (cpp:259-330)
+    {
+        cv::Mat flowc = cv::Mat::zeros(h, w, CV_32FC4);
+        int32_t nvc = ofc.calculateCompensatedFlow(rgb[0], rgb[1], flowc, 10);
+        put(fo, &nvc, sizeof nvc);
+        for (int x = 0; x < w; x += 10)
+            for (int y = 0; y < h; y += 10) put(fo, &flowc.at<cv::Vec4d>(y, x), sizeof(cv::Vec4d));
+    }
+
     // --- findOutliers on that flow field (detectOutliers, node.cpp:112-121)
     {
         OutlierDetector odm;

@@ -49,6 +49,16 @@ def test_adapter_classes_end_to_end(oracle, tmp_path):
     if failed.any():
         assert (flow[failed, 0] == -1).mean() > 0.9                                   # failed points: (-1,-1,0,0), cpp:112-115
 
+    # calculateCompensatedFlow: LK with maxLevel 2, vectors over 1 px
+    nvc = int(take(np.int32, 1)[0])
+    flowc = take(np.float64, 4 * P).reshape(P, 4)
+    refc, stc = oracle.lk(frames[0], frames[1], ref["pts"], max_level=2)
+    dc = refc - ref["pts"]
+    keepc = (stc == 1) & ((np.abs(dc[:, 0]) > 1.0) | (np.abs(dc[:, 1]) > 1.0))
+    assert abs(nvc - int(keepc.sum())) <= 2
+    okc = keepc & (flowc[:, 0] >= 0) & ((flowc[:, 2] != 0) | (flowc[:, 3] != 0))
+    assert okc.sum() >= keepc.sum() - 2 and np.abs(flowc[okc, 2:] - dc[okc]).mean() < 0.01
+
     # findOutliers over the adapter == the oracle's createMask on the same (dx, dy) field (row-major grid traversal)
     nflag, nvec = take(np.int32, 2)
     g = flow.reshape(w // 10, h // 10, 4).transpose(1, 0, 2).reshape(-1, 4)
