@@ -27,14 +27,17 @@ def test_library_exports_every_declared_symbol(capi):
 
 def test_struct_layouts_match_c(capi, tmp_path):
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "motion_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "motion_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(md_config),sizeof(md_frames),sizeof(md_outputs),sizeof(md_stats),offsetof(md_config,lk_eps),'
-                   'offsetof(md_config,ransac_thresh),offsetof(md_config,vf_rho));return 0;}\n')
+                   'offsetof(md_config,ransac_thresh),offsetof(md_config,vf_rho),sizeof(md_live_params),sizeof(md_live_result),'
+                   'offsetof(md_live_params,distance_threshold),offsetof(md_live_result,traj),offsetof(md_stats,lk_iterations));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(capi.MdConfig), C.sizeof(capi.MdFrames), C.sizeof(capi.MdOutputs), C.sizeof(capi.MdStats),
-            capi.MdConfig.lk_eps.offset, capi.MdConfig.ransac_thresh.offset, capi.MdConfig.vf_rho.offset]
+            capi.MdConfig.lk_eps.offset, capi.MdConfig.ransac_thresh.offset, capi.MdConfig.vf_rho.offset,
+            C.sizeof(capi.MdLiveParams), C.sizeof(capi.MdLiveResult), capi.MdLiveParams.distance_threshold.offset,
+            capi.MdLiveResult.traj.offset, capi.MdStats.lk_iterations.offset]
     assert got == want
 
 
