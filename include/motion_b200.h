@@ -74,7 +74,9 @@ typedef struct md_config {
     float   vf_rho, vf_alpha, vf_sigma; /* 2.8, 1400, 1.5 */
     int32_t vf_literal;         /* 1 = literal multigrid schedule incl. the (numerically inert) coarse corrections */
     int32_t flow_engine;        /* md_flow_engine: which flow feeds the egomotion fit in md_process_batch */
-    int32_t reserved[7];
+    int32_t vf_grid_barrier;    /* test hook: 1 = run every Gauss-Seidel launch of md_varflow as the cooperative grid with the
+                                   counting barrier (the path large levels take by themselves) instead of one cluster */
+    int32_t reserved[6];
 } md_config;
 
 typedef struct md_ctx md_ctx;

@@ -39,7 +39,7 @@ class MdConfig(C.Structure):
         ("ransac_thresh", C.c_double), ("seed", C.c_uint32),
         ("vf_max_level", C.c_int32), ("vf_start_level", C.c_int32), ("vf_n1", C.c_int32), ("vf_n2", C.c_int32),
         ("vf_rho", C.c_float), ("vf_alpha", C.c_float), ("vf_sigma", C.c_float), ("vf_literal", C.c_int32),
-        ("flow_engine", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("flow_engine", C.c_int32), ("vf_grid_barrier", C.c_int32), ("reserved", C.c_int32 * 6),
     ]
 
 
