@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <string>
 #include <vector>
 
 #define CV_8U 0
@@ -28,6 +29,8 @@ struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int
 template <typename T, int N> struct Vec { T val[N]; T &operator[](int i) { return val[i]; } const T &operator[](int i) const { return val[i]; } };
 typedef Vec<double, 4> Vec4d;
 typedef Vec<int, 4> Vec4i;
+struct Scalar { double val[4]; Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; } };
+struct Rect { int x, y, width, height; };
 
 class Mat {
 public:
@@ -59,6 +62,27 @@ private:
 };
 }  // namespace cv
 
-// legacy C image header used by VarFlow's interface (VarFlow.h:33-36)
+// legacy C types used by VarFlow's interface (VarFlow.h:33-36) and drawMotionField (optical_flow_calculator.h:29)
 struct IplImage { int nChannels, depth, width, height, widthStep; char *imageData; };
+struct CvScalar { double val[4]; };
+struct CvPoint { int x, y; };
+inline CvPoint cvPoint(int x, int y) { CvPoint p = {x, y}; return p; }
+inline CvScalar cvScalar(double a, double b = 0, double c = 0, double d = 0) { CvScalar s = {{a, b, c, d}}; return s; }
+#define CV_RGB(r, g, b) cv::Scalar((b), (g), (r), 0)
+#define CV_AA 16
+// plain 8-connected line into an 8-bit IplImage (stand-in for cvLine; real OpenCV draws the anti-aliased one)
+inline void cvLine(IplImage *img, CvPoint a, CvPoint b, CvScalar color, int = 1, int = 8, int = 0)
+{
+    int dx = b.x > a.x ? b.x - a.x : a.x - b.x, dy = b.y > a.y ? b.y - a.y : a.y - b.y;
+    const int sx = a.x < b.x ? 1 : -1, sy = a.y < b.y ? 1 : -1;
+    int err = dx - dy, x = a.x, y = a.y;
+    for (;;) {
+        if (x >= 0 && y >= 0 && x < img->width && y < img->height)
+            for (int c = 0; c < img->nChannels; c++) img->imageData[(size_t)y * img->widthStep + (size_t)x * img->nChannels + c] = (char)(unsigned char)color.val[c];
+        if (x == b.x && y == b.y) break;
+        const int e2 = 2 * err;
+        if (e2 > -dy) { err -= dy; x += sx; }
+        if (e2 < dx) { err += dx; y += sy; }
+    }
+}
 #endif

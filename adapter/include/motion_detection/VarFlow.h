@@ -17,7 +17,11 @@ class VarFlow{
         /* common/src/VarFlow.cpp:600-697; imgA/imgB 8-bit 1-channel, imgU/imgV IPL_DEPTH_32F; returns 1 on success, 0 otherwise */
         int CalcFlow(IplImage* imgA, IplImage* imgB, IplImage* imgU, IplImage* imgV, bool saved_data);
 
+        /* the GPU the next VarFlow objects are created on (the reference's constructor has no such argument) */
+        static void setDefaultDevice(int device) { default_device_ = device; }
+
     private:
+        static int default_device_;
         VarFlow(const VarFlow &);
         VarFlow &operator=(const VarFlow &);
         md_ctx *ctx_;

@@ -19,7 +19,7 @@ class OutlierDetector
 
         /* common/src/outlier_detector.cpp:37-52: outlier_probabilities (CV_64F) = 1.0 at grid vectors whose angle or magnitude
          * fails the median / MAD test */
-        void findOutliers(const cv::Mat &optical_flow_vectors, cv::Mat &outlier_probabilities, bool include_zeros, int pixel_step, bool print = false);
+        void findOutliers(const cv::Mat &optical_flow_vectors, cv::Mat &outlier_probabilities, bool include_zeros, int pixel_step, bool print);
         /* :54-73 (the reference allocates CV_32FC4 and writes Vec4d; here the field is CV_64FC4) */
         void getOutlierVectors(const cv::Mat &optical_flow_vectors, const cv::Mat &outlier_probabilities, cv::Mat &outlier_vectors, int pixel_step);
 

@@ -7,15 +7,18 @@
 #include <motion_detection/flow_clusterer.h>
 
 #include <cmath>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <ctime>
+#include <fstream>
+#include <limits>
 
 #include "motion_b200.h"
 
 // ---------------------------------------------------------------------------------------------------------------
 OpticalFlowCalculator::OpticalFlowCalculator()
-    : ctx_(0), ctx2_(0), w2_(0), h2_(0), ps2_(0), w_(0), h_(0), ps_(0), batch_(0), device_(0), ego_mode_(MD_EGO_RANSAC_HOMOGRAPHY), morph_(true), seed_(1), minvec_(0)
+    : ctx_(0), ctx2_(0), w2_(0), h2_(0), ps2_(0), w_(0), h_(0), ps_(0), batch_(0), device_(0), ego_mode_(MD_EGO_RANSAC_HOMOGRAPHY), morph_(false), seed_(1), minvec_(0)
 {
     for (int i = 0; i < 9; i++) last_H_[i] = (i % 4 == 0) ? 1.0 : 0.0;
 }
@@ -206,6 +209,69 @@ void OpticalFlowCalculator::varFlow(const cv::Mat &image1, const cv::Mat &image2
     md_varflow(ctx_, a.data(), b.data(), w, reinterpret_cast<float *>(optical_flow.data), reinterpret_cast<float *>(optical_flow_vectors.data), MD_MEM_HOST);
 }
 
+#ifndef MD_ADAPTER_EXTERNAL_SUPERPIXELFLOW
+// cpp:337-416 -- SLIC superpixels + LK per superpixel centre.  Nothing in the reference calls it and it depends on the
+// vendored slic.cpp; not on the accelerated path: no vectors, outputs untouched (see the header note).
+int OpticalFlowCalculator::superPixelFlow(const cv::Mat &, const cv::Mat &, cv::Mat &, cv::Mat &) { return 0; }
+#endif
+
+// cpp:467-507: for every (xSpace, ySpace) grid node an arrow along (U, -V) scaled by `multiplier`, when longer than `cutoff`;
+// shaft plus two 3-pixel barbs at +-45 degrees from the reversed direction.
+void OpticalFlowCalculator::drawMotionField(IplImage *imgU, IplImage *imgV, IplImage *imgMotion, int xSpace, int ySpace, float cutoff,
+                                            int multiplier, CvScalar color)
+{
+    if (!imgU || !imgV || !imgMotion || xSpace < 1 || ySpace < 1) return;
+    const double pi = 3.14159265358979323846;
+    for (int y = ySpace; y < imgU->height; y += ySpace) {
+        const float *urow = reinterpret_cast<const float *>(imgU->imageData + (size_t)y * imgU->widthStep);
+        const float *vrow = reinterpret_cast<const float *>(imgV->imageData + (size_t)y * imgV->widthStep);
+        for (int x = xSpace; x < imgU->width; x += xSpace) {
+            const float du = urow[x], dv = -vrow[x];                      // V is y-up
+            const float len = std::sqrt(du * du + dv * dv);
+            if (!(len > cutoff)) continue;
+            const float dir = std::atan2(dv, du);
+            const CvPoint tail = cvPoint(x, y);
+            const CvPoint tip = cvPoint(x + (int)lrint(multiplier * len * std::cos(dir)), y + (int)lrint(multiplier * len * std::sin(dir)));
+            cvLine(imgMotion, tail, tip, color, 1, CV_AA, 0);
+            for (int side = -1; side <= 1; side += 2) {
+                const double a = dir - pi - side * (pi / 4);
+                const CvPoint barb = cvPoint(tip.x + (int)lrint(3 * std::cos(a)), tip.y + (int)lrint(3 * std::sin(a)));
+                cvLine(imgMotion, barb, tip, color, 1, CV_AA, 0);
+            }
+        }
+    }
+}
+
+// cpp:509-541: two text files, "<filename>_h" (dx) and "<filename>_f" (dy); one line per grid row (rows and columns in steps
+// of pixel_step), values separated by ", ", failed vectors (x == -1, cpp:112-115) written as 0, default ostream formatting.
+void OpticalFlowCalculator::writeFlow(const cv::Mat &flow_vectors, const std::string &filename, int pixel_step)
+{
+    if (pixel_step < 1 || flow_vectors.type() != CV_64FC4) return;
+    std::ofstream fh((filename + "_h").c_str()), fv((filename + "_f").c_str());
+    for (int r = 0; r < flow_vectors.rows; r += pixel_step) {
+        for (int c = 0; c < flow_vectors.cols; c += pixel_step) {
+            const cv::Vec4d &e = flow_vectors.at<cv::Vec4d>(r, c);
+            const bool failed = e[0] == -1.0;
+            if (c) { fh << ", "; fv << ", "; }
+            fh << (failed ? 0.0 : e[2]);
+            fv << (failed ? 0.0 : e[3]);
+        }
+        fh << std::endl;
+        fv << std::endl;
+    }
+}
+
+// cpp:543-562: one line per trajectory, "x0, y0, x1, y1, ..."
+void OpticalFlowCalculator::writeTrajectories(const std::vector<std::vector<cv::Point2f> > &trajectories, const std::string &filename)
+{
+    std::ofstream ft(filename.c_str());
+    for (size_t i = 0; i < trajectories.size(); i++) {
+        const std::vector<cv::Point2f> &t = trajectories[i];
+        for (size_t j = 0; j < t.size(); j++) ft << (j ? ", " : "") << t[j].x << ", " << t[j].y;
+        ft << std::endl;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 OutlierDetector::OutlierDetector() : ctx_(0), device_(0), seed_((unsigned)time(NULL)), last_inliers_(0) {}
 
@@ -249,9 +315,11 @@ VarFlow::VarFlow(int width_in, int height_in, int max_level_in, int start_level_
     cfg.vf_max_level = max_level_in < start_level_in ? start_level_in : max_level_in;      // VarFlow.cpp:33-37
     cfg.vf_start_level = start_level_in; cfg.vf_n1 = n1_in; cfg.vf_n2 = n2_in;
     cfg.vf_rho = rho_in; cfg.vf_alpha = alpha_in; cfg.vf_sigma = sigma_in;
-    if (md_create(&cfg, 0, &ctx_) == MD_OK) initialized = 1;
+    if (md_create(&cfg, default_device_, &ctx_) == MD_OK) initialized = 1;
     else ctx_ = 0;
 }
+
+int VarFlow::default_device_ = 0;
 
 VarFlow::~VarFlow() { if (ctx_) md_destroy(ctx_); }
 
@@ -320,18 +388,98 @@ FlowClusterer::FlowClusterer() : ctx_(0), device_(0) {}
 
 FlowClusterer::~FlowClusterer() { if (ctx_) md_destroy(ctx_); }
 
+bool FlowClusterer::ensureContext()
+{
+    if (ctx_) return true;
+    md_config cfg;
+    md_config_default(&cfg);
+    cfg.width = 64; cfg.height = 64;               // geometry is irrelevant for the grouping
+    if (md_create(&cfg, device_, &ctx_) != MD_OK) { ctx_ = 0; return false; }
+    return true;
+}
+
+cv::Mat FlowClusterer::clusterFlowVectors(const cv::Mat &flow_vectors)
+{
+    (void)flow_vectors;                            // FLANN k-means with a rand()-seeded start: no call site, not reproducible
+    return cv::Mat(0, 2, CV_32F);
+}
+
+// the vectors the reference's loops visit (flow_clusterer.cpp:180-185): rows outer, columns inner, non-zero flow only
+static void gather_vectors(const cv::Mat &flow_vectors, int pixel_step, std::vector<cv::Vec4d> &out)
+{
+    if (pixel_step < 1 || flow_vectors.type() != CV_64FC4) return;
+    for (int r = 0; r < flow_vectors.rows; r += pixel_step)
+        for (int c = 0; c < flow_vectors.cols; c += pixel_step) {
+            const cv::Vec4d &e = flow_vectors.at<cv::Vec4d>(r, c);
+            if (std::fabs(e[2]) > 0.0 || std::fabs(e[3]) > 0.0) out.push_back(e);
+        }
+}
+
+std::vector<std::vector<cv::Vec4d> > FlowClusterer::getClusters(const cv::Mat &flow_vectors, int pixel_step, double distance_threshold,
+                                                                  double angular_threshold)
+{
+    std::vector<std::vector<cv::Vec4d> > mat_clusters;
+    std::vector<cv::Vec4d> vec;
+    gather_vectors(flow_vectors, pixel_step, vec);
+    const int n = (int)vec.size();
+    if (n < 1 || !ensureContext()) return mat_clusters;
+    std::vector<int32_t> labels(n);
+    int32_t nall = 0;
+    if (md_cluster_vectors(ctx_, &vec[0][0], n, distance_threshold, angular_threshold, labels.data(), &nall, MD_MEM_HOST) != MD_OK)
+        return mat_clusters;
+    // clusters with more than 5 members in creation order, members in arrival order (:210-217)
+    std::vector<int> size(nall > 0 ? nall : 1, 0), slot(nall > 0 ? nall : 1, -1);
+    for (int i = 0; i < n; i++) size[labels[i]]++;
+    int k = 0;
+    for (int c = 0; c < nall; c++)
+        if (size[c] > 5) slot[c] = k++;
+    mat_clusters.resize(k);
+    for (int c = 0; c < nall; c++)
+        if (slot[c] >= 0) mat_clusters[slot[c]].reserve(size[c]);
+    for (int i = 0; i < n; i++)
+        if (slot[labels[i]] >= 0) mat_clusters[slot[labels[i]]].push_back(vec[i]);
+    return mat_clusters;
+}
+
+// flow_clusterer.cpp:80-115 (no call site): every qualifying cluster takes the vector; centroids of all clusters.
+std::vector<cv::Point2f> FlowClusterer::getClustersCenters(const cv::Mat &flow_vectors, int pixel_step, double distance_threshold,
+                                                           double angular_threshold)
+{
+    std::vector<cv::Vec4d> vec;
+    gather_vectors(flow_vectors, pixel_step, vec);
+    const double two_pi = 2 * 3.14159265358979323846;
+    std::vector<double> ang(vec.size());
+    for (size_t i = 0; i < vec.size(); i++) { ang[i] = std::atan2(vec[i][3], vec[i][2]); if (ang[i] < 0.0) ang[i] += two_pi; }
+    std::vector<std::vector<int> > members;
+    for (size_t i = 0; i < vec.size(); i++) {
+        bool added = false;
+        for (size_t c = 0; c < members.size(); c++) {
+            double dmin = std::numeric_limits<double>::max(), amin = dmin;
+            for (size_t m = 0; m < members[c].size(); m++) {
+                const int j = members[c][m];
+                const double dx = vec[i][0] - vec[j][0], dy = vec[i][1] - vec[j][1], da = ang[i] - ang[j];
+                dmin = std::min(dmin, std::sqrt(dx * dx + dy * dy));
+                amin = std::min(amin, std::fabs(std::atan2(std::sin(da), std::cos(da))));
+            }
+            if (dmin < distance_threshold && amin < angular_threshold) { members[c].push_back((int)i); added = true; }
+        }
+        if (!added) members.push_back(std::vector<int>(1, (int)i));
+    }
+    std::vector<cv::Point2f> centroids;
+    for (size_t c = 0; c < members.size(); c++) {
+        double sx = 0.0, sy = 0.0;
+        for (size_t m = 0; m < members[c].size(); m++) { sx += vec[members[c][m]][0]; sy += vec[members[c][m]][1]; }
+        centroids.push_back(cv::Point2f((float)(sx / members[c].size()), (float)(sy / members[c].size())));
+    }
+    return centroids;
+}
+
 std::vector<std::vector<cv::Point2f> > FlowClusterer::clusterEuclidean(const std::vector<cv::Point2f> &points, double distance_threshold)
 {
     std::vector<std::vector<cv::Point2f> > mat_clusters;
     boxes_.clear();
     const int n = (int)points.size();
-    if (n < 1) return mat_clusters;
-    if (!ctx_) {
-        md_config cfg;
-        md_config_default(&cfg);
-        cfg.width = 64; cfg.height = 64;           // geometry is irrelevant for the grouping
-        if (md_create(&cfg, device_, &ctx_) != MD_OK) { ctx_ = 0; return mat_clusters; }
-    }
+    if (n < 1 || !ensureContext()) return mat_clusters;
     std::vector<int32_t> labels(n), boxes(4 * (size_t)n), sizes(n), ids(n);
     int32_t nall = 0, k = 0;
     if (md_cluster_points(ctx_, &points[0].x, n, distance_threshold, 5, labels.data(), &nall, &k, boxes.data(), sizes.data(), ids.data(),

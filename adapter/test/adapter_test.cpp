@@ -53,7 +53,7 @@ int main(int argc, char **argv)
     {
         OutlierDetector odm;
         cv::Mat prob, outv;
-        odm.findOutliers(flow, prob, false, 10);
+        odm.findOutliers(flow, prob, false, 10, false);
         odm.getOutlierVectors(flow, prob, outv, 10);
         int32_t nflag = 0, nvec = 0;
         for (int y = 0; y < h; y += 10)

@@ -225,6 +225,15 @@ int md_cluster_points(md_ctx *ctx, const float *pts, int32_t n, double distance_
                       int32_t *labels, int32_t *num_clusters_all, int32_t *num_clusters, int32_t *boxes, int32_t *sizes,
                       int32_t *ids, int mem);
 
+/* ---- FlowClusterer::getClusters (common/src/flow_clusterer.cpp:178-227; node.cpp:127,169,375) --------------------------------- */
+/* vec4 [n][4] f64 = (x, y, dx, dy) of the participating flow vectors in the reference's traversal order (rows outer, columns
+ * inner, steps of pixel_step, only |dx| > 0 or |dy| > 0, :180-185).  labels[n] = id (creation order) of the cluster every
+ * vector joins: the FIRST cluster with a member nearer than distance_threshold and a member whose orientation differs by
+ * less than angular_threshold (VectorCluster::getClosestDistance / getClosestOrientation, vector_cluster.cpp:25-50).
+ * The reference returns the clusters with more than 5 members (:210-217); sizes follow from the labels. */
+int md_cluster_vectors(md_ctx *ctx, const double *vec4, int32_t n, double distance_threshold, double angular_threshold,
+                       int32_t *labels, int32_t *num_clusters_all, int mem);
+
 /* ---- OutlierDetector::fitSubspace (common/src/outlier_detector.cpp:236-331) ------------------------------------ */
 /* traj [T][F][2]; forced_cols NULL (rand() % T after srand(seed)) or [iters][4*num_motions] host indices.
  * residual[T] f32, best_cols[4*num_motions] i32, outlier[T] u8 (residual > threshold, :318-324). */

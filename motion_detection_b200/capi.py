@@ -25,7 +25,7 @@ SYMBOLS = [
     "md_pyramid_read", "md_pyramid_read_deriv", "md_lk_flow", "md_fit_egomotion", "md_motion_mask",
     "md_process_batch", "md_process_pair", "md_track_trajectories", "md_fit_subspace", "md_varflow", "md_stats_get",
     "md_stats_reset", "md_profile", "md_profile_read", "md_live_params_default", "md_window_reset", "md_window_push",
-    "md_window_detect", "md_cluster_points", "md_find_outliers",
+    "md_window_detect", "md_cluster_points", "md_find_outliers", "md_cluster_vectors",
 ]
 
 
@@ -331,6 +331,16 @@ class Context:
         self._ck(lib().md_cluster_points(self._h, _ptr(pts), n, C.c_double(distance_threshold), min_cluster_size, _ptr(labels),
                                          C.byref(nall), C.byref(k), _ptr(boxes), _ptr(sizes), _ptr(ids), MD_MEM_HOST))
         return labels[:n], nall.value, boxes[:k.value], sizes[:k.value], ids[:k.value]
+
+    def cluster_vectors(self, vec4, distance_threshold=50.0, angular_threshold=0.15):
+        """FlowClusterer::getClusters on the participating vectors [n][4] f64: (labels [n], clusters founded)."""
+        vec4 = np.ascontiguousarray(vec4, np.float64).reshape(-1, 4)
+        n = len(vec4)
+        labels = np.zeros(max(n, 1), np.int32)
+        nall = C.c_int32()
+        self._ck(lib().md_cluster_vectors(self._h, _ptr(vec4), n, C.c_double(distance_threshold), C.c_double(angular_threshold),
+                                          _ptr(labels), C.byref(nall), MD_MEM_HOST))
+        return labels[:n], nall.value
 
     def find_outliers(self, dxdy, include_zeros=False):
         dxdy = np.ascontiguousarray(dxdy, np.float64).reshape(-1, 2)

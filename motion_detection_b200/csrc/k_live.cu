@@ -156,12 +156,16 @@ cudaError_t launch_compact_outliers(const float2 *traj_c, const uint8_t *outlier
 #define CL_MAXC 8             // tie candidates kept per point; more -> the label pass rescans that point
 
 // PointCluster::getDistance (point_cluster.cpp:62-65): float differences, float products and sum (no FMA on the
-// reference's x86-64 build), sqrt is monotonic and is applied only for the threshold test.
+// reference's x86-64 build); the unqualified sqrt() on that float resolves to the float overload, so the distance the
+// reference compares (against the threshold and between clusters, strict '<') is the f32-rounded root.  sqrt is monotonic:
+// the minimum is taken on the squared distance; ties are decided on the ROUNDED root (two different squares can collapse to
+// one root, and the reference then keeps the older cluster).
 __device__ __forceinline__ float cl_d2(float2 a, float2 b)
 {
     const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y);
     return __fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy));
 }
+__device__ __forceinline__ float cl_dist(float2 a, float2 b) { return __fsqrt_rn(cl_d2(a, b)); }
 
 // one warp per point i: min over j < i, then the (ascending) list of j attaining it
 __global__ void __launch_bounds__(256) k_cl_nearest(const float2 *pts, const int *n_ptr, float *m2, int *cand, int *ncand)
@@ -174,10 +178,11 @@ __global__ void __launch_bounds__(256) k_cl_nearest(const float2 *pts, const int
         for (int j = lane; j < i; j += 32) m = fminf(m, cl_d2(a, pts[j]));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        m = __fsqrt_rn(m);                          // i == 0: root of FLT_MAX, unused (no candidates)
         int cnt = 0;
         for (int j0 = 0; j0 < i; j0 += 32) {
             const int j = j0 + lane;
-            const bool hit = j < i && cl_d2(a, pts[j]) == m;
+            const bool hit = j < i && cl_dist(a, pts[j]) == m;
             const unsigned bal = __ballot_sync(0xffffffffu, hit);
             if (hit) {
                 const int slot = cnt + __popc(bal & ((1u << lane) - 1));
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(32) k_cl_label(const float2 *pts, const int *n
             const int4 *cp = reinterpret_cast<const int4 *>(cand + (size_t)i * CL_MAXC);
             const int4 a = cp[0], b = cp[1];
             c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = b.x; c[5] = b.y; c[6] = b.z; c[7] = b.w;
-            join = nc > 0 && sqrt((double)m) < thr;
+            join = nc > 0 && (double)m < thr;
         }
         const int cnt = min(32, n - i0);
         for (int t = 0; t < cnt; t++) {
@@ -224,7 +229,7 @@ __global__ void __launch_bounds__(32) k_cl_label(const float2 *pts, const int *n
                 const float mt = __shfl_sync(0xffffffffu, m, t);
                 int bb = 0x7fffffff;
                 for (int j = lane; j < it; j += 32)
-                    if (cl_d2(a, pts[j]) == mt) bb = min(bb, lab[j]);
+                    if (cl_dist(a, pts[j]) == mt) bb = min(bb, lab[j]);
                 best = __reduce_min_sync(0xffffffffu, bb);
             }
             if (lane == t) {
@@ -286,6 +291,82 @@ __global__ void __launch_bounds__(32) k_cl_select(const int *nclusters, const in
             k++;
         }
     *nout = k;
+}
+
+// ---- FlowClusterer::getClusters (common/src/flow_clusterer.cpp:178-227) ---------------------------------------------------
+// Greedy FIRST-FIT grouping of flow vectors: a vector joins the first cluster (creation order) that has a member nearer than
+// distance_threshold (VectorCluster::getClosestDistance, vector_cluster.cpp:25-37) AND a member -- not necessarily the same
+// one -- whose orientation differs by less than angular_threshold (getClosestOrientation :38-50, getAngularDistance
+// :121-127).  The choice depends on the labels of all earlier vectors, so the vectors are walked in order by ONE block; for
+// every vector the block's threads test all earlier vectors in parallel and raise two flags per cluster in shared memory,
+// then the smallest cluster id with both flags wins.  Orientations (getAngle :129-136) come from a parallel pre-pass.
+// All arithmetic in f64 in the reference's operation order.
+__global__ void __launch_bounds__(256) k_vc_angle(const double4 *vec, int n, double *ang)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double a = atan2(vec[i].w, vec[i].z);
+        if (a < 0.0) a = __dadd_rn(a, 2 * 3.14159265358979323846);
+        ang[i] = a;
+    }
+}
+
+#define VC_THREADS 1024
+__global__ void __launch_bounds__(VC_THREADS) k_vc_cluster(const double4 *vec, const double *ang, int n, double dthr, double athr,
+                                                           int *label, int *nclusters)
+{
+    extern __shared__ uint8_t vc_flags[];          // [n] bit 0: a member is near, bit 1: a member is aligned
+    __shared__ int s_best[VC_THREADS / 32];
+    __shared__ int s_ncl;
+    const int t = threadIdx.x;
+    for (int k = t; k < n; k += VC_THREADS) vc_flags[k] = 0;
+    if (t == 0) s_ncl = 0;
+    __syncthreads();
+    for (int i = 0; i < n; i++) {
+        const double4 v = vec[i];
+        const double ai = ang[i];
+        for (int j = t; j < i; j += VC_THREADS) {
+            const double4 u = vec[j];
+            const double dx = __dsub_rn(v.x, u.x), dy = __dsub_rn(v.y, u.y);
+            const double d = __dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)));
+            const double da = __dsub_rn(ai, ang[j]);
+            const double ad = fabs(atan2(sin(da), cos(da)));
+            const int f = (d < dthr ? 1 : 0) | (ad < athr ? 2 : 0);
+            if (f) atomicOr(reinterpret_cast<unsigned *>(vc_flags + (label[j] & ~3)), (unsigned)f << (8 * (label[j] & 3)));
+        }
+        __syncthreads();
+        const int ncl = s_ncl;
+        int best = 0x7fffffff;
+        for (int k = t; k < ncl; k += VC_THREADS) {
+            if (vc_flags[k] == 3 && k < best) best = k;
+            vc_flags[k] = 0;
+        }
+        best = __reduce_min_sync(0xffffffffu, best);
+        if ((t & 31) == 0) s_best[t >> 5] = best;
+        __syncthreads();
+        if (t < 32) {
+            int b = s_best[t];
+            b = __reduce_min_sync(0xffffffffu, b);
+            if (t == 0) {
+                if (b == 0x7fffffff) b = s_ncl++;
+                label[i] = b;
+            }
+        }
+        __syncthreads();
+    }
+    if (t == 0) *nclusters = s_ncl;
+}
+
+cudaError_t launch_cluster_vectors(const double *vec4, int n, double dthr, double athr, double *ang, int *label, int *nclusters,
+                                   cudaStream_t s)
+{
+    const size_t smem = ((size_t)n + 3) / 4 * 4 + 16;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_vc_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+    if (e != cudaSuccess) return e;
+    k_vc_angle<<<(n + 255) / 256, 256, 0, s>>>(reinterpret_cast<const double4 *>(vec4), n, ang);
+    k_vc_cluster<<<1, VC_THREADS, smem, s>>>(reinterpret_cast<const double4 *>(vec4), ang, n, dthr, athr, label, nclusters);
+    MD_COUNT_LAUNCH(2);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_cluster(const float2 *pts, const int *n_ptr, int n_max, double thr, int min_size, float *m2, int *cand, int *ncand,

@@ -27,7 +27,7 @@
         return (code);      \
     } while (0)
 
-long long g_md_launches = 0;
+std::atomic<long long> g_md_launches(0);
 
 static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -143,10 +143,21 @@ static bool ensure_phase(md_ctx *ctx)
     return true;
 }
 
+static int ensure_scratch(md_ctx *ctx, size_t bytes)
+{
+    if (ctx->scratch && ctx->scratch_bytes >= bytes) return MD_OK;
+    if (ctx->scratch) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_bytes = 0; }
+    bytes = (bytes + 4095) / 4096 * 4096;
+    if (cudaMalloc(&ctx->scratch, bytes) != cudaSuccess) { cudaGetLastError(); ctx->scratch = nullptr; FAIL(MD_ERR_NOMEM, "out of device memory (scratch)"); }
+    ctx->scratch_bytes = bytes;
+    return MD_OK;
+}
+
 static void free_ctx(md_ctx *ctx)
 {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    if (ctx->scratch) cudaFree(ctx->scratch);
     void *ptrs[] = {ctx->d_img, ctx->d_der, ctx->d_frames, ctx->d_mask, ctx->d_pts_in, ctx->d_next, ctx->d_status, ctx->d_keep,
                     ctx->d_inlier_mask, ctx->d_blockcnt, ctx->d_kept_idx, ctx->d_M, ctx->d_hyp_valid, ctx->d_counts,
                     ctx->d_inliers, ctx->d_valid, ctx->d_hyp, ctx->d_partial, ctx->d_H, ctx->d_Hinv, ctx->d_stats,
@@ -295,6 +306,16 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
         ctx->lk_maps.valid = 1;
     }
     phase_geometry(ctx);
+    {
+        // tuning / tracing aids, read once per context (not per call, and not into process-wide statics)
+        const char *e = getenv("MD_PIPE_CHUNKS");
+        ctx->pipe_chunks = e ? atoi(e) : 0;
+        if (ctx->pipe_chunks < 2 || ctx->pipe_chunks > 8) ctx->pipe_chunks = 0;
+        e = getenv("MD_PIPE_FIRST");
+        ctx->pipe_first = e ? atoi(e) : 0;
+        e = getenv("MD_TRACE");
+        ctx->trace_calls = e ? atoi(e) : 0;
+    }
     ctx->stats.device = device;
     *out = ctx;
     return MD_OK;
@@ -374,15 +395,13 @@ extern "C" int md_gray_u8(md_ctx *ctx, const uint8_t *src3, int32_t src_pitch, i
         CK(launch_gray(src3, src_pitch, w, h, dst, dst_pitch, ctx->stream));
         return MD_OK;
     }
-    uint8_t *d_in = nullptr, *d_out = nullptr;
-    CK(cudaMalloc((void **)&d_in, (size_t)3 * w * h));
-    if (cudaMalloc((void **)&d_out, (size_t)w * h) != cudaSuccess) { cudaFree(d_in); FAIL(MD_ERR_NOMEM, "md_gray_u8: out of memory"); }
-    cudaError_t e = cudaMemcpy2DAsync(d_in, 3 * w, src3, src_pitch, 3 * w, h, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = launch_gray(d_in, 3 * w, w, h, d_out, w, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemcpy2DAsync(dst, dst_pitch, d_out, w, w, h, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(d_in); cudaFree(d_out);
-    CK(e);
+    const size_t in_bytes = ((size_t)3 * w * h + 255) / 256 * 256;
+    { int r = ensure_scratch(ctx, in_bytes + (size_t)w * h); if (r != MD_OK) return r; }
+    uint8_t *d_in = (uint8_t *)ctx->scratch, *d_out = d_in + in_bytes;
+    CK(cudaMemcpy2DAsync(d_in, 3 * w, src3, src_pitch, 3 * w, h, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_gray(d_in, 3 * w, w, h, d_out, w, ctx->stream));
+    CK(cudaMemcpy2DAsync(dst, dst_pitch, d_out, w, w, h, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return MD_OK;
 }
 
@@ -575,7 +594,7 @@ extern "C" int md_motion_mask(md_ctx *ctx, const uint8_t *prev, const uint8_t *c
     CK(cudaSetDevice(ctx->device));
     double Hinv[9];
     invert3_host(H9, Hinv);
-    // d_Hinv row `max_batch-1` is scratch for this call; copy is stream ordered (pageable source is staged before return)
+    // d_Hinv row 0 is scratch for this call; the copy is stream ordered (a pageable source is staged before the call returns)
     double *d_hi = ctx->d_Hinv;
     CK(cudaMemcpyAsync(d_hi, Hinv, sizeof Hinv, cudaMemcpyHostToDevice, ctx->stream));
     MaskParams p;
@@ -758,8 +777,7 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
     if (serial) { nch = 1; bounds[1] = pairs; }
     else if (pairs < 8) { nch = 2; bounds[1] = pairs / 2; bounds[2] = pairs; }
     else {
-        static int tuned = -1;                     // MD_PIPE_CHUNKS=<2..7> in the environment overrides the default (tuning aid)
-        if (tuned < 0) { const char *e = getenv("MD_PIPE_CHUNKS"); tuned = e ? atoi(e) : 0; if (tuned < 2 || tuned > 8) tuned = 0; }
+        const int tuned = ctx->pipe_chunks;        // MD_PIPE_CHUNKS=<2..8> in the environment overrides the default (tuning aid)
         const int total = tuned ? tuned : (host ? MD_PIPE_CHUNKS : MD_PIPE_CHUNKS_DEVICE);
         if (host) {
             // a short first chunk (its H2D is exposed) and a short last chunk (its D2H is exposed) around even middle chunks
@@ -769,13 +787,18 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
             bounds[++nch] = pairs;
         } else {
             // device-resident frames: a short first chunk (its pyramids, planes and sums are exposed), then even chunks
-            static int first_env = -1;
-            if (first_env < 0) { const char *e = getenv("MD_PIPE_FIRST"); first_env = e ? atoi(e) : 0; }
-            const int first = first_env > 0 && first_env < pairs ? first_env : 0;
+            const int first = ctx->pipe_first > 0 && ctx->pipe_first < pairs ? ctx->pipe_first : 0;
             if (first) bounds[++nch] = first;
             const int rest = pairs - first, nrest = first ? total - 1 : total;
             for (int i = 1; i <= nrest; i++) bounds[++nch] = first + (int)((long long)rest * i / nrest);
         }
+    }
+    {
+        // every chunk holds at least one pair (a tuning knob or a small batch can produce empty ones: drop them)
+        int m = 0;
+        for (int i = 1; i <= nch; i++)
+            if (bounds[i] > bounds[m]) bounds[++m] = bounds[i];
+        nch = m;
     }
     cudaStream_t s_pyr = serial ? s : ctx->aux_pyr, s_post = serial ? s : ctx->aux_post;
 
@@ -800,9 +823,7 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
         return MD_OK;
     };
 
-    static int trace_env = -1;
-    if (trace_env < 0) { const char *e = getenv("MD_TRACE"); trace_env = e ? atoi(e) : 0; }
-    const bool trace = trace_env > 0 && !serial;
+    const bool trace = ctx->trace_calls > 0 && !serial;
     cudaEvent_t tev[8][6];            // per chunk: K1 begin, K1+planes end, LK begin, LK end, post begin, post end
     cudaEvent_t tev0 = nullptr;
     if (trace) {
@@ -881,7 +902,7 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
             for (int k = 0; k < 6; k++) cudaEventDestroy(tev[i][k]);
         }
         cudaEventDestroy(tev0);
-        trace_env--;                  // MD_TRACE=n traces the next n calls
+        ctx->trace_calls--;           // MD_TRACE=n traces the first n pipelined calls of a context
     }
     if (host) {
         CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[nch - 1], 0));
@@ -1154,6 +1175,34 @@ extern "C" int md_cluster_points(md_ctx *ctx, const float *pts, int32_t n, doubl
     return MD_OK;
 }
 
+// FlowClusterer::getClusters (flow_clusterer.cpp:178-227) on the participating vectors
+extern "C" int md_cluster_vectors(md_ctx *ctx, const double *vec4, int32_t n, double distance_threshold, double angular_threshold,
+                                  int32_t *labels, int32_t *num_clusters_all, int mem)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    if (!vec4 || !labels || n < 0) FAIL(MD_ERR_INVALID, "md_cluster_vectors: bad arguments");
+    if (n > 200000) FAIL(MD_ERR_UNSUPPORTED, "md_cluster_vectors: more than 200 000 vectors (the grouping is O(n^2) and sequential)");
+    if (num_clusters_all) *num_clusters_all = 0;
+    if (n == 0) return MD_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const size_t vb = sizeof(double) * 4 * (size_t)n, ab = sizeof(double) * (size_t)n, lb = (sizeof(int) * (size_t)n + 15) / 16 * 16;
+    { int r = ensure_scratch(ctx, vb + ab + lb + 16); if (r != MD_OK) return r; }
+    double *d_vec = (double *)ctx->scratch, *d_ang = d_vec + 4 * (size_t)n;
+    int *d_label = (int *)((uint8_t *)ctx->scratch + vb + ab), *d_ncl = (int *)((uint8_t *)d_label + lb);
+    const double *dv = vec4;
+    if (mem == MD_MEM_HOST) { CK(cudaMemcpyAsync(d_vec, vec4, vb, cudaMemcpyHostToDevice, s)); dv = d_vec; }
+    else if (((uintptr_t)vec4 & 31) != 0) { CK(cudaMemcpyAsync(d_vec, vec4, vb, cudaMemcpyDeviceToDevice, s)); dv = d_vec; }   // double4 loads
+    CK(launch_cluster_vectors(dv, n, distance_threshold, angular_threshold, d_ang, d_label, d_ncl, s));
+    const cudaMemcpyKind outk = mem == MD_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CK(cudaMemcpyAsync(labels, d_label, sizeof(int) * (size_t)n, outk, s));
+    int ncl = 0;
+    CK(cudaMemcpyAsync(&ncl, d_ncl, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (num_clusters_all) *num_clusters_all = ncl;
+    return MD_OK;
+}
+
 // ---- statistics --------------------------------------------------------------------------------------------------------
 extern "C" int md_stats_get(md_ctx *ctx, md_stats *out)
 {
@@ -1168,7 +1217,7 @@ extern "C" int md_stats_get(md_ctx *ctx, md_stats *out)
     ctx->stats.inliers = (int64_t)v[2];
     ctx->stats.lk_iterations = 0; ctx->stats.lk_levels = 0;
     for (int i = 0; i < 64; i++) { ctx->stats.lk_iterations += (int64_t)v[8 + 2 * i]; ctx->stats.lk_levels += (int64_t)v[9 + 2 * i]; }
-    ctx->stats.kernel_launches = g_md_launches;
+    ctx->stats.kernel_launches = g_md_launches.load(std::memory_order_relaxed);
     *out = ctx->stats;
     return MD_OK;
 }

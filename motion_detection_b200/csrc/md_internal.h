@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <string>
 
 #include "../../include/motion_b200.h"
@@ -193,6 +194,10 @@ struct md_ctx {
     void *mad_ws;         // findOutliers workspace (k_mad.cu)
     void *live_ws;        // live-path workspace (md_api.cu: md_window_*)
     void *vf_ws;          // VarFlow workspace (k_varflow.cu), allocated on the first md_varflow call
+    void *scratch;        // grow-only device scratch of the small host-memory entry points (md_gray_u8, md_cluster_vectors)
+    size_t scratch_bytes;
+    long long launches;   // kernels launched through this context's calls (md_stats.kernel_launches)
+    int pipe_chunks, pipe_first, trace_calls;   // MD_PIPE_CHUNKS / MD_PIPE_FIRST / MD_TRACE, read once in md_create
 };
 
 void vf_free_workspace(void *ws);
@@ -203,8 +208,9 @@ int sub_enqueue(md_ctx *ctx, const float *d_traj, int T, int F, int num_motions,
 int vf_compute_device(md_ctx *ctx, const uint8_t *dA, const uint8_t *dB, int dpitch);
 cudaError_t vf_sample_grid(md_ctx *ctx, float2 *next, uint8_t *status, cudaStream_t s);
 
-extern long long g_md_launches;   // kernels launched by this library (process wide)
-#define MD_COUNT_LAUNCH(n) (g_md_launches += (n))
+// kernels launched by this library, process wide (md_stats.kernel_launches): contexts may live on different threads
+extern std::atomic<long long> g_md_launches;
+#define MD_COUNT_LAUNCH(n) (g_md_launches.fetch_add((n), std::memory_order_relaxed))
 
 // kernel launchers (each in its own .cu)
 cudaError_t launch_gray(const uint8_t *src3, int src_pitch, int w, int h, uint8_t *dst, int dst_pitch, cudaStream_t s);
@@ -220,6 +226,8 @@ cudaError_t launch_compact_outliers(const float2 *traj_c, const uint8_t *outlier
 cudaError_t launch_cluster(const float2 *pts, const int *n_ptr, int n_max, double thr, int min_size, float *m2, int *cand, int *ncand,
                            int *label, int *nclusters, int *sizes, int *box, int *nout, int32_t *out_box, int32_t *out_size,
                            int32_t *out_id, cudaStream_t s);
+cudaError_t launch_cluster_vectors(const double *vec4, int n, double dthr, double athr, double *ang, int *label, int *nclusters,
+                                   cudaStream_t s);
 cudaError_t launch_lk_planes(const LkParams &p, int pairs, cudaStream_t s);
 cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1, cudaStream_t s);
 cudaError_t launch_pyramid_level0(const PyrGeom &g, uint8_t *img, int slot0, int nframes, const uint8_t *frames, int channels,

@@ -46,6 +46,7 @@ void orc_subspace_projector(const float *data, int n, int T, const int *cols, in
 /* md_oracle_live.c */
 void orc_traj_step(float *cur, const float *next, const uint8_t *status, float *traj, int32_t *len, int P, int F, int w, int h);
 int orc_cluster_euclidean(const float *pts, int n, double distance_threshold, int32_t *labels);
+int orc_cluster_vectors(const double *vec4, int n, double distance_threshold, double angular_threshold, int32_t *labels);
 int orc_find_outliers(const double *dxdy, int n, int include_zeros, uint8_t *outlier, double *stats4);
 int orc_bounding_boxes(const float *pts, int n, const int32_t *labels, int nclusters, int min_size, int32_t *boxes,
                        int32_t *sizes, int32_t *ids);

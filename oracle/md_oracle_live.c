@@ -3,6 +3,9 @@
  *   orc_traj_step          calculateOpticalFlowTrajectory bookkeeping, common/src/optical_flow_calculator.cpp:178-241
  *   orc_cluster_euclidean  FlowClusterer::clusterEuclidean, common/src/flow_clusterer.cpp:227-269, with
  *                          PointCluster::getClosestDistance / getDistance, common/src/point_cluster.cpp:26-38,62-65
+ *   orc_cluster_vectors    FlowClusterer::getClusters, common/src/flow_clusterer.cpp:178-227 (the live code after the
+ *                          #ifdef NEW_THING block), with VectorCluster::getClosestDistance / getClosestOrientation /
+ *                          getDistance / getAngularDistance / getAngle, common/src/vector_cluster.cpp:25-50,116-136
  *   orc_bounding_boxes     OpticalFlowVisualizer::showBoundingBoxes, common/src/optical_flow_visualizer.cpp:223-240
  *                          (cv::Mat(Point2f).copyTo(vector<Point>) = saturate_cast<int> = round half to even;
  *                          cv::boundingRect of integer points: tl = min, size = max - min + 1; br = tl + size) --
@@ -37,10 +40,13 @@ typedef struct { int *member; int n, cap; } orc_cluster;
 
 static double cl_distance(const float *a, const float *b)
 {
-    /* point_cluster.cpp:62-65: float arithmetic inside, sqrt on the promoted value */
+    /* point_cluster.cpp:62-65: float arithmetic inside; the unqualified sqrt() gets a float argument, so with a libstdc++
+     * whose <math.h> exports the std:: overloads (gcc >= 6) the FLOAT overload is chosen and the distance is rounded to
+     * f32 before it becomes the double return value.  (gcc 4.8-era headers would pick sqrt(double); the two differ only
+     * when a distance sits within one f32 ulp of the threshold or of another cluster's distance.) */
     const float dx = a[0] - b[0], dy = a[1] - b[1];
     const float s = dx * dx + dy * dy;
-    return sqrt((double)s);
+    return (double)sqrtf(s);
 }
 
 /* labels[i] = id (creation order) of the cluster point i joined; returns the number of clusters founded */
@@ -66,6 +72,57 @@ int orc_cluster_euclidean(const float *pts, int n, double distance_threshold, in
             c->member[c->n++] = i;
             labels[i] = index;
         } else {                                                       /* :249-254 */
+            if (ncl == capcl) { capcl = capcl ? 2 * capcl : 16; cl = (orc_cluster *)realloc(cl, sizeof(orc_cluster) * capcl); }
+            cl[ncl].cap = 8; cl[ncl].n = 1;
+            cl[ncl].member = (int *)malloc(sizeof(int) * 8);
+            cl[ncl].member[0] = i;
+            labels[i] = ncl++;
+        }
+    }
+    for (int k = 0; k < ncl; k++) free(cl[k].member);
+    free(cl);
+    return ncl;
+}
+
+/* ---- FlowClusterer::getClusters (flow_clusterer.cpp:178-227), literal ---------------------------------------------------
+ * vec4 [n][4] = (x, y, dx, dy) of the participating flow vectors in the reference's traversal order (rows outer, columns
+ * inner, both in steps of pixel_step, only vectors with |dx| > 0 or |dy| > 0, :184-185).  A vector joins the FIRST cluster
+ * (creation order) whose closest member is nearer than distance_threshold AND whose closest orientation differs by less
+ * than angular_threshold -- the two minima may come from different members (:192-199); otherwise it founds a cluster.
+ * VectorCluster::getClosestOrientation calls an unqualified abs() on a double (vector_cluster.cpp:43): as for sqrt above,
+ * the std::abs(double) overload is assumed (an int abs() would truncate every angle below 1 rad to 0). */
+static double vc_angle(const double *v)
+{
+    double ang = atan2(v[3], v[2]);                                    /* vector_cluster.cpp:129-136 */
+    if (ang < 0.0) ang += 2 * M_PI;
+    return ang;
+}
+int orc_cluster_vectors(const double *vec4, int n, double distance_threshold, double angular_threshold, int32_t *labels)
+{
+    orc_cluster *cl = NULL;
+    int ncl = 0, capcl = 0;
+    for (int i = 0; i < n; i++) {
+        const double *v = vec4 + 4 * i;
+        int added = 0;
+        for (int k = 0; k < ncl && !added; k++) {                      /* flow_clusterer.cpp:190-201 */
+            double md = DBL_MAX, ma = DBL_MAX;
+            for (int m = 0; m < cl[k].n; m++) {
+                const double *u = vec4 + 4 * cl[k].member[m];
+                const double d = sqrt((v[0] - u[0]) * (v[0] - u[0]) + (v[1] - u[1]) * (v[1] - u[1]));   /* vector_cluster.cpp:116-119 */
+                if (d < md) md = d;
+                const double a1 = vc_angle(v), a2 = vc_angle(u);       /* :121-127 */
+                const double ad = fabs(atan2(sin(a1 - a2), cos(a1 - a2)));
+                if (ad < ma) ma = ad;
+            }
+            if (md < distance_threshold && ma < angular_threshold) {
+                orc_cluster *c = &cl[k];
+                if (c->n == c->cap) { c->cap *= 2; c->member = (int *)realloc(c->member, sizeof(int) * c->cap); }
+                c->member[c->n++] = i;
+                labels[i] = k;
+                added = 1;
+            }
+        }
+        if (!added) {                                                  /* :202-207 */
             if (ncl == capcl) { capcl = capcl ? 2 * capcl : 16; cl = (orc_cluster *)realloc(cl, sizeof(orc_cluster) * capcl); }
             cl[ncl].cap = 8; cl[ncl].n = 1;
             cl[ncl].member = (int *)malloc(sizeof(int) * 8);

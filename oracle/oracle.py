@@ -48,6 +48,7 @@ def lib():
         _LIB.orc_cluster_euclidean.restype = C.c_int
         _LIB.orc_bounding_boxes.restype = C.c_int
         _LIB.orc_find_outliers.restype = C.c_int
+        _LIB.orc_cluster_vectors.restype = C.c_int
     return _LIB
 
 
@@ -320,6 +321,24 @@ def cluster_euclidean(pts, distance_threshold=50.0, min_size=5):
     k = lib().orc_bounding_boxes(pts.ctypes.data_as(f32p), n, labels.ctypes.data_as(i32p), ncl, min_size, boxes.ctypes.data_as(i32p),
                                  sizes.ctypes.data_as(i32p), ids.ctypes.data_as(i32p))
     return labels[:n], ncl, boxes[:k], sizes[:k], ids[:k]
+
+
+def cluster_vectors(vec4, distance_threshold=50.0, angular_threshold=0.15):
+    """FlowClusterer::getClusters (flow_clusterer.cpp:178-227) on the participating vectors [n][4] = (x, y, dx, dy) in the
+    reference's traversal order: (labels [n], number of clusters founded)."""
+    vec4 = np.ascontiguousarray(vec4, np.float64).reshape(-1, 4)
+    n = len(vec4)
+    labels = np.zeros(max(n, 1), np.int32)
+    ncl = lib().orc_cluster_vectors(vec4.ctypes.data_as(f64p), n, C.c_double(distance_threshold), C.c_double(angular_threshold),
+                                    labels.ctypes.data_as(i32p))
+    return labels[:n], ncl
+
+
+def flow_field_vectors(flow, pixel_step):
+    """The vectors getClusters visits (flow_clusterer.cpp:180-185): rows outer, columns inner, |dx| > 0 or |dy| > 0.
+    flow: [h][w][4] f64 (the Vec4d field)."""
+    sub = flow[::pixel_step, ::pixel_step].reshape(-1, 4)
+    return np.ascontiguousarray(sub[(np.abs(sub[:, 2]) > 0.0) | (np.abs(sub[:, 3]) > 0.0)])
 
 
 def live_detect(frames, pixel_step=10, num_motions=2, sigma=0.5, distance_threshold=50.0, seed=1, iters=50, min_size=5):

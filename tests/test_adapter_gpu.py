@@ -33,7 +33,8 @@ def test_adapter_classes_end_to_end(oracle, tmp_path):
 
     nv, crows, ccols, ftype = take(np.int32, 4)
     H = take(np.float64, 9).reshape(3, 3)
-    ref = oracle.process_pair(frames[0], frames[1], pixel_step=10, min_vector_size=0.2, seed=11)
+    # `comp` is the thresholded difference as at cpp:124-127: no erode / dilate unless setMorphology(true)
+    ref = oracle.process_pair(frames[0], frames[1], pixel_step=10, min_vector_size=0.2, seed=11, morph=False)
     assert abs(int(nv) - ref["num_vectors"]) <= 2 and nv > 500
     assert (crows, ccols) == (h, w)
     assert ftype == 6 + (3 << 3)                       # CV_64FC4: the adapter repairs the node's CV_32FC4 allocation
@@ -91,3 +92,16 @@ def test_adapter_classes_end_to_end(oracle, tmp_path):
     assert vf_ok == 1 and off == len(buf)
     Uo, Vo = oracle.varflow(frames[0], frames[1])
     assert np.sqrt((U - Uo) ** 2 + (V - Vo) ** 2).mean() < 0.01
+
+
+def test_node_call_sites_run_on_the_device(tmp_path):
+    """adapter/test/node_callsites.cpp with "gpu": every ofc_. / od_. / fc_. call expression of the node executed once."""
+    exe = os.path.join(ROOT, "adapter", "node_callsites")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "adapter"), "-s"])
+    r = subprocess.run([exe, "gpu", str(tmp_path)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    last = [l for l in r.stdout.splitlines() if l.startswith("== gpu")]
+    assert last, r.stdout
+    ntraj, ftype = int(last[0].split()[3]), int(last[0].split()[-1])
+    assert ntraj > 300 and ftype == 6 + (3 << 3)

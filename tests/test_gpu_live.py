@@ -185,3 +185,89 @@ def test_find_outliers_degenerate(capi, oracle):
     got, st = ctx.find_outliers(d, False)
     ref, rst = oracle.find_outliers(d, False)
     assert np.array_equal(got, ref) and got[7] == 1 and got.sum() == 1
+
+
+# ---- clusterEuclidean: f32-rounded distances (point_cluster.cpp:62-65, sqrt(float) overload) --------------------------------
+def test_cluster_points_near_threshold_and_collapsed_ties(capi, oracle):
+    """(i) a squared distance whose f64 root is below the threshold but whose f32 root equals it: the reference (strict '<'
+    on the f32 root) founds a new cluster; (ii) two different squared distances that collapse to the same f32 root: the
+    reference keeps the OLDER cluster."""
+    ctx = _ctx(capi, 640, 480)
+    # (i) d2 = nextafter(2500, 0) in f32: sqrt -> 49.999998 in f64 but 50.0f in f32
+    d2 = np.nextafter(np.float32(2500.0), np.float32(0.0))
+    x = np.sqrt(np.float64(d2))
+    pts = np.array([[0.0, 0.0], [x, 0.0]], np.float32)
+    got_d2 = np.float32(pts[1, 0]) * np.float32(pts[1, 0])
+    ref = oracle.cluster_euclidean(pts, 50.0, 0)
+    got = ctx.cluster_points(pts, 50.0, 0)
+    assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
+    if np.sqrt(np.float32(got_d2), dtype=np.float32) == np.float32(50.0) and np.sqrt(np.float64(got_d2)) < 50.0:
+        assert ref[1] == 2                     # not joined although the exact root is below the threshold
+    # (ii) search squares near 1e6 for two distinct f32 values with the same f32 root
+    base = np.float32(1.0e6)
+    cands = [base]
+    for _ in range(6):
+        cands.append(np.nextafter(cands[-1], np.float32(2e6)))
+    roots = [np.sqrt(c, dtype=np.float32) for c in cands]
+    pair = next((i for i in range(len(cands) - 1) if roots[i] == roots[i + 1]), None)
+    assert pair is not None
+    # point 2 sits at distances sqrt(cands[pair + 1]) from point 0 (cluster 0) and sqrt(cands[pair]) from point 1 (cluster 1):
+    # the younger cluster is nearer in d2, equal in f32 distance -> the reference keeps cluster 0
+    rng = np.random.default_rng(1)
+    for trial in range(200):
+        a = np.float32(rng.uniform(900, 1100))
+        pts = np.array([[0, 0], [3000, 0], [a, 0]], np.float32)
+        ref = oracle.cluster_euclidean(pts, 5000.0, 0)
+        got = ctx.cluster_points(pts, 5000.0, 0)
+        assert np.array_equal(got[0], ref[0]) and got[1] == ref[1]
+    # dense random layouts with f32 coordinates on a coarse lattice produce many collapsed ties
+    for seed in range(4):
+        rng = np.random.default_rng(100 + seed)
+        pts = (rng.integers(0, 4000, (600, 2)).astype(np.float32) * np.float32(0.37))
+        for thr in (20.0, 55.5):
+            ref = oracle.cluster_euclidean(pts, thr, 5)
+            got = ctx.cluster_points(pts, thr, 5)
+            assert got[1] == ref[1] and np.array_equal(got[0], ref[0])
+            for a_, b_ in zip(got[2:], ref[2:]):
+                assert np.array_equal(a_, b_)
+
+
+# ---- FlowClusterer::getClusters (flow_clusterer.cpp:178-227): the node's path when egomotion is off (node.cpp:375) ----------
+@pytest.mark.parametrize("n,dthr,athr,layout", [(600, 50.0, 0.15, "blobs"), (1500, 90.0, 0.26, "uniform"), (300, 20.0, 3.2, "uniform"),
+                                                (1, 50.0, 0.15, "uniform"), (2500, 30.0, 0.15, "field")])
+def test_cluster_vectors_identical_to_oracle(capi, oracle, n, dthr, athr, layout):
+    rng = np.random.default_rng(n + int(dthr))
+    if layout == "blobs":
+        c = rng.uniform(50, 600, (5, 2))
+        k = rng.integers(0, 5, n)
+        pos = c[k] + rng.normal(0, 25, (n, 2))
+        dirs = rng.uniform(0, 2 * np.pi, 5)[k] + rng.normal(0, 0.1, n)
+        mag = rng.uniform(0.5, 4.0, n)
+        vec = np.c_[pos, mag * np.cos(dirs), mag * np.sin(dirs)]
+    elif layout == "field":
+        # what the node hands over: a Vec4d field on the pixel_step grid, zero vectors skipped, row-major traversal
+        h, w, ps = 480, 640, 10
+        flow = np.zeros((h, w, 4))
+        yy, xx = np.mgrid[0:h:ps, 0:w:ps]
+        flow[::ps, ::ps, 0] = xx; flow[::ps, ::ps, 1] = yy
+        moving = ((xx - 200) ** 2 + (yy - 150) ** 2 < 90 ** 2) | ((xx - 450) ** 2 + (yy - 300) ** 2 < 70 ** 2)
+        flow[::ps, ::ps, 2] = np.where(moving, 2.0 + 0.3 * rng.standard_normal(xx.shape), 0.0)
+        flow[::ps, ::ps, 3] = np.where(moving, -1.0 + 0.3 * rng.standard_normal(xx.shape), 0.0)
+        vec = oracle.flow_field_vectors(flow, ps)
+        assert 50 < len(vec) < 1000
+    else:
+        vec = np.c_[rng.uniform(0, 640, (n, 2)), rng.normal(0, 2, (n, 2))]
+    ctx = _ctx(capi, 640, 480)
+    ref_lab, ref_n = oracle.cluster_vectors(vec, dthr, athr)
+    lab, ncl = ctx.cluster_vectors(vec, dthr, athr)
+    assert ncl == ref_n
+    assert np.array_equal(lab, ref_lab)
+    # deterministic
+    lab2, _ = ctx.cluster_vectors(vec, dthr, athr)
+    assert np.array_equal(lab, lab2)
+
+
+def test_cluster_vectors_empty(capi):
+    ctx = _ctx(capi, 640, 480)
+    lab, ncl = ctx.cluster_vectors(np.zeros((0, 4)))
+    assert len(lab) == 0 and ncl == 0
