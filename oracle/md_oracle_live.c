@@ -12,8 +12,11 @@
  *                          the row MotionLogger::writeBoundingBox logs (common/src/motion_logger.cpp:43-47).
  * Written as the reference writes it (explicit cluster member lists, clusters scanned in creation order); the GPU path
  * uses a different but equivalent formulation, which is what the parity test checks.
- * Parity unpinned by the reference (no tests/fixtures for these functions); pinned here by construction checks in
- * tests/test_oracle_golden.py (hand-worked cases).
+ * The reference holds no tests / fixtures for these functions.  orc_cluster_euclidean and orc_cluster_vectors are PINNED TO THE
+ * REFERENCE'S OWN CODE: oracle/_ref/libcluster_ref.so is the unmodified flow_clusterer.cpp + vector_cluster.cpp +
+ * point_cluster.cpp compiled against the cv:: shim of oracle/ref_shim/opencv2, and the clusters it returns equal the ones
+ * derived from these labels exactly (tests/test_oracle_ref.py, frozen in tests/golden/golden_ref.npz).  orc_traj_step,
+ * orc_bounding_boxes, orc_find_outliers: hand-worked cases in tests/test_oracle_golden.py (parity unpinned for those).
  */
 #include <float.h>
 #include <math.h>

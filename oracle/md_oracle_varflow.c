@@ -11,6 +11,9 @@
  * OpenCV algorithm (BORDER_REPLICATE Gaussian of cvRound(8*sigma+1)|1 taps, correlation, half-pixel
  * bilinear resize with the exact-2x area shortcut) and pinned against cv2 4.13.0 in
  * tests/test_oracle_vs_cv2.py.  Float arithmetic, no FMA contraction (build with -ffp-contract=off).
+ * PINNED TO THE REFERENCE'S OWN CODE: oracle/_ref/libvarflow_ref.so is the unmodified common/src/VarFlow.cpp compiled
+ * against the legacy-C-API shim of oracle/ref_shim (same Gaussian / resize / filter primitives as here); orc_varflow equals
+ * it bit for bit for every size and parameter set tried (tests/test_oracle_ref.py, frozen in tests/golden/golden_ref.npz).
  */
 #include <math.h>
 #include <stdint.h>

@@ -368,3 +368,65 @@ def find_outliers(dxdy, include_zeros=False):
     stats = np.zeros(4, np.float64)
     lib().orc_find_outliers(dxdy.ctypes.data_as(f64p), n, 1 if include_zeros else 0, out.ctypes.data_as(u8p), stats.ctypes.data_as(f64p))
     return out, stats
+
+
+# ---- oracle/_ref: the reference's OWN sources compiled against the shims of oracle/ref_shim (recipe: oracle/Makefile) --------
+# Used only to validate the restatement above (tests/test_oracle_ref.py) and to generate tests/golden/golden_ref.npz.
+_REF = {}
+
+
+def ref_lib(name):
+    """'varflow' (common/src/VarFlow.cpp) or 'cluster' (flow_clusterer.cpp + vector_cluster.cpp + point_cluster.cpp);
+    None when oracle/_ref was not built (no /root/reference at build time)."""
+    if name not in _REF:
+        so = os.path.join(_HERE, "_ref", "lib%s_ref.so" % name)
+        if not os.path.exists(so) and os.path.exists("/root/reference/common/src/VarFlow.cpp"):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        _REF[name] = C.CDLL(so) if os.path.exists(so) else None
+    return _REF[name]
+
+
+def ref_varflow(A, B, max_level=4, start_level=0, n1=2, n2=2, rho=2.8, alpha=1400.0, sigma=1.5):
+    """The reference's VarFlow class itself (ctor + CalcFlow, VarFlow.cpp:27-162,600-697)."""
+    A, pa = _u8(A)
+    B, pb = _u8(B)
+    h, w = A.shape
+    U = np.zeros((h, w), np.float32)
+    V = np.zeros((h, w), np.float32)
+    rc = ref_lib("varflow").ref_varflow(pa, pb, w, h, w, max_level, start_level, n1, n2, C.c_float(rho), C.c_float(alpha),
+                                        C.c_float(sigma), U.ctypes.data_as(f32p), V.ctypes.data_as(f32p))
+    if rc != 1:
+        raise RuntimeError("reference VarFlow::CalcFlow returned %d" % rc)
+    return U, V
+
+
+def ref_cluster_euclidean(pts, distance_threshold):
+    """The reference's FlowClusterer::clusterEuclidean: (sizes [K], members [sum sizes][2]) of the clusters it returns."""
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 2)
+    n = len(pts)
+    sizes = np.zeros(n + 1, np.int32)
+    mem = np.zeros((max(n, 1), 2), np.float32)
+    k = ref_lib("cluster").ref_cluster_euclidean(pts.ctypes.data_as(f32p), n, C.c_double(distance_threshold),
+                                                 sizes.ctypes.data_as(i32p), mem.ctypes.data_as(f32p))
+    return sizes[:k].copy(), mem[:int(sizes[:k].sum())].copy()
+
+
+def ref_get_clusters(flow, pixel_step, distance_threshold, angular_threshold):
+    """The reference's FlowClusterer::getClusters on a Vec4d field [h][w][4] f64: (sizes [K], members [sum sizes][4])."""
+    flow = np.ascontiguousarray(flow, np.float64)
+    h, w, _ = flow.shape
+    n = ((h + pixel_step - 1) // pixel_step) * ((w + pixel_step - 1) // pixel_step)
+    sizes = np.zeros(n + 1, np.int32)
+    mem = np.zeros((max(n, 1), 4), np.float64)
+    k = ref_lib("cluster").ref_get_clusters(flow.ctypes.data_as(f64p), w, h, pixel_step, C.c_double(distance_threshold),
+                                            C.c_double(angular_threshold), sizes.ctypes.data_as(i32p), mem.ctypes.data_as(f64p))
+    return sizes[:k].copy(), mem[:int(sizes[:k].sum())].copy()
+
+
+def clusters_from_labels(items, labels, ncl, min_size=5):
+    """What the reference returns (clusters with MORE than min_size members, creation order, members in arrival order) from the
+    oracle's labels: (sizes [K], members concatenated)."""
+    cnt = np.bincount(labels, minlength=ncl) if len(labels) else np.zeros(0, np.int64)
+    ids = [i for i in range(ncl) if cnt[i] > min_size]
+    mem = np.concatenate([items[labels == i] for i in ids]) if ids else items[:0]
+    return cnt[ids].astype(np.int32), mem

@@ -1,0 +1,25 @@
+"""Writes tests/golden/golden_ref.npz: outputs of the REFERENCE's own code (oracle/_ref: the unmodified
+/root/reference/common/src/VarFlow.cpp and flow_clusterer.cpp / vector_cluster.cpp / point_cluster.cpp compiled against
+oracle/ref_shim, recipe oracle/Makefile) on the seeded inputs tests/test_oracle_ref.py rebuilds.  Run in the container that
+holds /root/reference:  python tests/golden/make_golden_ref.py"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import oracle as O  # noqa: E402
+import test_oracle_ref as T  # noqa: E402
+
+out = {}
+fr = T._vf_pair(96, 80, 5)
+out["vf_U_96x80"], out["vf_V_96x80"] = O.ref_varflow(fr[0], fr[1])
+fr = T._vf_pair(160, 120, 9)
+out["vf_U_160x120_l2"], out["vf_V_160x120_l2"] = O.ref_varflow(fr[0], fr[1], max_level=2, n1=1, n2=3)
+out["ce_sizes"], out["ce_members"] = O.ref_cluster_euclidean(T._lattice_points(3), 33.3)
+out["gc_sizes"], out["gc_members"] = O.ref_get_clusters(T._flow_field(2), 10, 50.0, 0.5)
+np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden_ref.npz"), **out)
+print({k: v.shape for k, v in out.items()})
