@@ -305,6 +305,11 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
         if (!mok) { free_ctx(ctx); return MD_ERR_CUDA; }
         ctx->lk_maps.valid = 1;
     }
+    // K4: tensor maps over the INTERIOR of the ring's level-0 planes (the frames themselves); failure -> gather path
+    {
+        const uint8_t *f0 = ctx->d_img + g.lv[0].img_off + (size_t)g.pady * g.lv[0].pitch + g.padx;
+        mask_encode_maps(&ctx->mask_maps, f0, f0, w, h, g.lv[0].pitch, (long long)g.slot_img_bytes, g.nslots);
+    }
     phase_geometry(ctx);
     {
         // tuning / tracing aids, read once per context (not per call, and not into process-wide statics)
@@ -601,6 +606,13 @@ extern "C" int md_motion_mask(md_ctx *ctx, const uint8_t *prev, const uint8_t *c
     memset(&p, 0, sizeof p);
     p.w = w; p.h = h; p.Hinv = d_hi; p.valid = nullptr; p.thresh = thresh; p.morph = morph; p.nslots = 0;
     p.stat_mask = nullptr;
+    auto user_maps = [&](const uint8_t *a, const uint8_t *c, int pt) -> const MaskTmaMaps * {
+        if (ctx->mask_user_key[0] != a || ctx->mask_user_key[1] != c || ctx->mask_user_pitch != pt) {
+            mask_encode_maps(&ctx->mask_maps_user, a, c, w, h, pt, 0, 1);
+            ctx->mask_user_key[0] = a; ctx->mask_user_key[1] = c; ctx->mask_user_pitch = pt;
+        }
+        return &ctx->mask_maps_user;
+    };
     if (mem == MD_MEM_HOST) {
         if (ctx->cfg.max_batch < 1) FAIL(MD_ERR_STATE, "md_motion_mask: no staging");
         int r = ensure_frames(ctx, 1);
@@ -610,13 +622,13 @@ extern "C" int md_motion_mask(md_ctx *ctx, const uint8_t *prev, const uint8_t *c
         CK(cudaMemcpy2DAsync(ctx->d_frames + fs, ctx->fpitch, cur, pitch, w, h, cudaMemcpyHostToDevice, ctx->stream));
         p.prev = ctx->d_frames; p.cur = ctx->d_frames + fs; p.pitch = ctx->fpitch; p.stride = 0;
         p.mask = ctx->d_mask; p.mask_pitch = ctx->fpitch; p.mask_stride = 0;
-        CK(launch_mask(p, 1, ctx->stream));
+        CK(launch_mask(p, 1, user_maps(p.prev, p.cur, p.pitch), ctx->stream));
         CK(cudaMemcpy2DAsync(mask, mask_pitch, ctx->d_mask, ctx->fpitch, w, h, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     } else {
         p.prev = prev; p.cur = cur; p.pitch = pitch; p.stride = 0;
         p.mask = mask; p.mask_pitch = mask_pitch; p.mask_stride = 0;
-        CK(launch_mask(p, 1, ctx->stream));
+        CK(launch_mask(p, 1, user_maps(prev, cur, pitch), ctx->stream));
     }
     return MD_OK;
 }
@@ -711,7 +723,7 @@ static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
         mp.thresh = ctx->cfg.diff_threshold; mp.morph = ctx->cfg.morph;
         mp.mask = d_mask + (size_t)p0 * mask_stride; mp.mask_pitch = mask_pitch; mp.mask_stride = mask_stride;
         mp.stat_mask = ctx->d_stats;
-        CK(launch_mask(mp, n, s));
+        CK(launch_mask(mp, n, &ctx->mask_maps, s));
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[4], s));
     return MD_OK;

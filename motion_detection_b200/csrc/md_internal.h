@@ -124,6 +124,14 @@ struct EgoParams {
     unsigned long long *stat_tracked, *stat_inliers;
 };
 
+// K4 TMA boxes: the source bounding box of a 136 x 36 output region in `prev` (16-byte aligned start: up to 15 columns of slack)
+#define MD_MASK_PREV_BOX_W 176
+#define MD_MASK_PREV_BOX_H 44
+struct alignas(64) MaskTmaMaps {
+    CUtensorMap prev, cur;   // u8, dims (x, y, frame) over the image INTERIOR: out-of-image elements are zero-filled
+    int valid;
+};
+
 struct MaskParams {
     // frame b of prev lives at prev + ((prev_slot0 + b) % nslots) * stride when nslots > 0 (pyramid ring),
     // at prev + b * stride when nslots == 0 (plain frame arrays); same for cur.
@@ -139,6 +147,7 @@ struct MaskParams {
     int mask_pitch;
     long long mask_stride;
     unsigned long long *stat_mask;   // nullable
+    int use_tma;             // set by launch_mask: 1 = the tensor maps are usable (TMA-staged fast path)
 };
 
 struct md_ctx {
@@ -186,6 +195,10 @@ struct md_ctx {
     cudaEvent_t ev[5];
     LkTmaMaps lk_maps;
     LkPhaseMaps ph_maps;
+    MaskTmaMaps mask_maps;        // level-0 planes of the pyramid ring (frames of md_process_batch)
+    MaskTmaMaps mask_maps_user;   // plain frame arrays of md_motion_mask, re-encoded when the buffers change
+    const void *mask_user_key[2];
+    int mask_user_pitch;
     PhaseGeom pg;
     int16_t *d_phase;     // [max_batch] pair arenas of phase planes, allocated on the first grid-mode LK call
     long long *d_wsum;    // [max_batch][nlev][P][5] per-point window sums
@@ -218,7 +231,8 @@ cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot
                            int channels, int fpitch, long long fstride, cudaStream_t s);
 cudaError_t launch_lk(const LkParams &p, const LkTmaMaps *maps, const LkPhaseMaps *pmaps, int pairs, cudaStream_t s);
 cudaError_t launch_ego(const EgoParams &p, int pairs, cudaStream_t s);
-cudaError_t launch_mask(const MaskParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_mask(const MaskParams &p, int pairs, const MaskTmaMaps *maps, cudaStream_t s);
+bool mask_encode_maps(MaskTmaMaps *m, const uint8_t *prev, const uint8_t *cur, int w, int h, int pitch, long long stride, int nframes);
 cudaError_t launch_compact_trajectories(const float2 *traj, const int32_t *len, int P, int F, int *blockcnt, int *idx, int *total,
                                         float2 *traj_c, cudaStream_t s);
 cudaError_t launch_compact_outliers(const float2 *traj_c, const uint8_t *outlier, int T, int F, int *blockcnt, int *oidx, int *total,

@@ -149,3 +149,39 @@ def test_lk_large_displacement_restages_the_next_frame_tile(capi, oracle):
     assert np.linalg.norm(a[ok] - ref[ok], axis=1).mean() < 0.01
     inner = ok & (pts[:, 0] > 80) & (pts[:, 0] < w - 80) & (pts[:, 1] > 80) & (pts[:, 1] < h - 80)
     assert np.abs(np.median(a[inner] - pts[inner], axis=0) - np.array([13.0, -9.0])).max() < 0.1
+
+
+# ---- K4 fast path (TMA-staged boxes + fixed-point coordinates): bit-exactness over many near-identity homographies ---------------
+@pytest.mark.parametrize("size", [(1920, 1080), (641, 479), (3840, 2160)])
+def test_mask_fast_path_random_homographies(capi, oracle, size):
+    """Frame-to-frame egomotion is near-identity: those tiles run from TMA boxes with the expansion-based reciprocal and the
+    2^-15 rounding guard.  Random small rotations / zooms / translations / projective terms, sub-pixel translations that put
+    EVERY pixel on a rounding boundary (multiples of 1/64 px), and homographies strong enough to send some tiles to the gather
+    path: the mask must equal the oracle's bit for bit (warpPerspective + absdiff + threshold + erode + dilate,
+    optical_flow_calculator.cpp:124-127, background_subtractor.cpp:31-32)."""
+    w, h = size
+    rng = np.random.default_rng(w + h)
+    prev = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    cur = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    ctx = _ctx(capi, w, h)
+    cases = []
+    n_rand = 6 if w < 3000 else 2
+    for _ in range(n_rand):
+        a = rng.normal(0, 0.002)
+        s = 1.0 + rng.normal(0, 0.002)
+        H = np.array([[s * np.cos(a), -s * np.sin(a), rng.normal(0, 3.0)], [s * np.sin(a), s * np.cos(a), rng.normal(0, 3.0)],
+                      [rng.normal(0, 2e-6), rng.normal(0, 2e-6), 1.0]])
+        cases.append(H)
+    cases.append(np.array([[1, 0, 3 / 64.0], [0, 1, -5 / 64.0], [0, 0, 1.0]]))          # every coordinate is a rounding tie
+    cases.append(np.array([[1, 0, 7.0], [0, 1, -2.0], [0, 0, 1.0]]))                    # integer shift: fractions are all 0
+    cases.append(np.array([[1.0, 0, 0.25], [0, 1.0, 0.75], [3e-5, -2e-5, 1.0]]))        # projective terms near the expansion limit
+    cases.append(np.array([[1.12, 0.05, -40.0], [-0.04, 1.1, 12.0], [0, 0, 1.0]]))      # zoom: boxes near / over the size limit
+    cases.append(np.array([[np.cos(0.2), -np.sin(0.2), 100.0], [np.sin(0.2), np.cos(0.2), -80.0], [0, 0, 1.0]]))   # rotation: gather tiles
+    cases.append(np.array([[1, 0, -float(w)], [0, 1, 0], [0, 0, 1.0]]))                 # the source lies entirely outside the image
+    for H in cases:
+        for thresh in (190, 60):
+            got = ctx.motion_mask(prev, cur, H, thresh=thresh, morph=True)
+            ref = oracle.motion_mask(prev, cur, H, thresh=thresh, morph=True)
+            assert np.array_equal(got, ref), (size, H.tolist(), thresh, int((got != ref).sum()))
+        got = ctx.motion_mask(prev, cur, H, thresh=60, morph=False)
+        assert np.array_equal(got, oracle.motion_mask(prev, cur, H, thresh=60, morph=False)), (size, H.tolist(), "raw")
