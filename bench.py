@@ -47,6 +47,11 @@ def parse():
                     help="pairs = the motion-mask chain (BASELINE metric); live = the node's imageCallback path "
                          "(trajectory window -> fitSubspace -> clusterEuclidean -> boxes), a secondary line")
     ap.add_argument("--num-motions", type=int, default=2)
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the short secondary measurements (dense 1080p, VGA, 4K LK, 4K VarFlow chain, VarFlow 1080p, live path) "
+                         "the default N = 1 run appends under \"secondary\"")
+    ap.add_argument("--lean", action="store_true", help="skip the extra figures (two streams per GPU, 1-thread CPU) -- used by the secondary runs")
+    ap.add_argument("--no-pin", action="store_true", help="do not pin the rank to the host cores next to its GPU")
     ap.add_argument("--flow-engine", default="lk", choices=["lk", "varflow"],
                     help="flow feeding the egomotion fit: grid LK (default) or the dense variational flow VarFlow::CalcFlow "
                          "sampled at the grid (BASELINE configs[2]: 4-level pyramid, dense flow + homography)")
@@ -56,6 +61,52 @@ def parse():
 def workload_name(a):
     return "C2 %dx%d synthetic affine camera + 3 moving blobs, pixel_step=%d, min_vector_size=0.2, RANSAC homography%s" % (
         a.width, a.height, a.pixel_step, ", dense VarFlow engine (max_level 4)" if a.flow_engine == "varflow" else "")
+
+
+def copies_resident(a):
+    """inputs larger than L2: the timed loop rotates over R resident copies of the batch (R * (B+1) frames > 300 MB)"""
+    return max(2, int(np.ceil(300e6 / ((a.batch + 1) * a.width * a.height))))
+
+
+def config_dict(a, world):
+    """`config` of the JSON line -- the SAME dict for the B200 arm and the reference arm (the reference arm times a bounded
+    sample of this workload; what the sample was is said in its cpu_baseline.sample)."""
+    gx = (a.width + a.pixel_step - 1) // a.pixel_step
+    gy = (a.height + a.pixel_step - 1) // a.pixel_step
+    R = copies_resident(a)
+    return {"workload": workload_name(a), "pairs_per_step": a.batch, "grid_points": gx * gy, "streams": world,
+            "l2": "inputs rotate over %d resident copies (%.0f MB > 126 MB L2)" % (R, R * (a.batch + 1) * a.width * a.height / 1e6),
+            "parallelism": "independent camera streams, one per GPU, no frame-path collective"}
+
+
+def pin_to_gpu_cores(local, world):
+    """N > 1: pin this rank to host cores next to its GPU (the cores of the GPU's NUMA node that the container may use, else
+    the container's cores), a disjoint slice per rank: a step is ~100 API calls per 7 ms, and launching threads that migrate
+    or share cores show up as launch jitter at N >= 2.  Returns what was done (reported in the JSON line)."""
+    try:
+        import torch
+        avail = sorted(os.sched_getaffinity(0))
+
+        def node_cores(dev):
+            pr = torch.cuda.get_device_properties(dev)
+            path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/local_cpulist" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            cpus = []
+            for part in open(path).read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus += list(range(int(lo), int(hi or lo) + 1))
+            near = sorted(set(cpus) & set(avail))
+            return tuple(near) if near else tuple(avail)
+
+        bases = [node_cores(d) for d in range(world)]
+        mine = bases[local]
+        sharers = [d for d in range(world) if bases[d] == mine]
+        per = max(1, len(mine) // len(sharers))
+        k = sharers.index(local)
+        cores = list(mine[k * per:(k + 1) * per]) or list(mine)
+        os.sched_setaffinity(0, cores)
+        return {"cores": len(cores), "first": cores[0], "last": cores[-1], "numa_local": set(cores) <= set(node_cores(local)) and len(mine) < len(avail)}
+    except Exception as e:          # no sysfs entry, no permission: run unpinned
+        return {"cores": None, "error": str(e)[:80]}
 
 
 def make_frames(a, rank, n):
@@ -121,14 +172,14 @@ def run_reference(a, rank, world):
         step()
     dt = time.perf_counter() - t0
     val = a.ref_pairs * a.steps / dt
-    sample = "%d steps x %d pairs of the same %s" % (a.steps, a.ref_pairs, workload_name(a))
+    sample = "%d steps x %d pairs (a bounded sample of the %d-pair step) of the same %s" % (a.steps, a.ref_pairs, a.batch, workload_name(a))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/f32/f64 (integer samples, f32 sums, f64 homography)", "data": "synthetic",
-        "config": {"workload": workload_name(a), "pairs_per_step": a.ref_pairs, "host": "cv2 %s" % (
-            "present" if cv_chain.have_cv2() else "absent -> plain-C oracle")},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cv_chain.threads(), "kind": "port", "sample": sample},
+        "config": config_dict(a, max(world, 1)),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cv_chain.threads(), "kind": "port", "sample": sample,
+                         "host": "cv2 %s" % ("present" if cv_chain.have_cv2() else "absent -> plain-C oracle")},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mpx_per_s": val * a.width * a.height / 1e6,
     }
@@ -281,6 +332,49 @@ def run_live(a, rank, local, world):
         dist.destroy_process_group()
 
 
+SECONDARY = [
+    # (key, BASELINE config it stands for, extra flags)  -- a few steps each, every one a full bench line of its own
+    ("dense_1080p", "configs[1] dense: every pixel tracked (pixel_step 1, 2 073 600 points per pair)",
+     ["--pixel-step", "1", "--batch", "2", "--steps", "3", "--warmup", "3", "--cpu-baseline-seconds", "4"]),
+    ("c1_vga", "configs[0]: 640x480", ["--width", "640", "--height", "480", "--batch", "128", "--steps", "10", "--warmup", "3",
+                                       "--cpu-baseline-seconds", "4"]),
+    ("c3_4k_lk", "configs[2] with the LK engine: 3840x2160, 6 pyramid levels", ["--width", "3840", "--height", "2160", "--batch", "8",
+                                                                                "--steps", "6", "--warmup", "3", "--cpu-baseline-seconds", "4"]),
+    ("c3_4k_varflow", "configs[2] as written: 3840x2160, dense variational flow (VarFlow, max_level 4) + homography egomotion",
+     ["--width", "3840", "--height", "2160", "--flow-engine", "varflow", "--batch", "2", "--steps", "3", "--warmup", "3",
+      "--cpu-baseline-seconds", "1"]),
+    ("varflow_1080p", "configs[1] with the dense variational flow engine", ["--flow-engine", "varflow", "--batch", "4", "--steps", "3",
+                                                                            "--warmup", "3", "--cpu-baseline-seconds", "1"]),
+    ("live_1080p", "configs[4]-style live path: imageCallback (window of 5 frames -> trajectories -> fitSubspace -> clusters)",
+     ["--workload", "live", "--batch", "8", "--steps", "4", "--warmup", "3", "--cpu-baseline-seconds", "4"]),
+]
+
+
+def run_secondary(a):
+    """The other BASELINE configurations, a few steps each, every one measured by this same script in a child process (own
+    contexts, own timing rules: >= 3 warm-up steps, inputs larger than L2, CUDA events, e2e with host buffers, CPU beside it)."""
+    out = {}
+    for key, what, flags in SECONDARY:
+        cmd = [sys.executable, os.path.abspath(__file__), "--gpus", "1", "--no-secondary", "--lean"] + flags
+        t0 = time.perf_counter()
+        try:
+            pr = subprocess.run(cmd, capture_output=True, text=True, timeout=420)
+            rows = [l for l in pr.stdout.splitlines() if l.startswith("{")]
+            if pr.returncode != 0 or not rows:
+                out[key] = {"what": what, "error": (pr.stderr or pr.stdout)[-300:]}
+                continue
+            d = json.loads(rows[-1])
+            keep = {k: d.get(k) for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "config", "roofline", "stages",
+                                          "cpu_baseline", "e2e", "gpu_launches", "lk_work", "mpx_per_s", "live_stats")}
+            keep["what"] = what
+            keep["flags"] = " ".join(flags)
+            keep["wall_s"] = round(time.perf_counter() - t0, 1)
+            out[key] = keep
+        except Exception as e:                      # a secondary line never takes the headline down with it
+            out[key] = {"what": what, "error": str(e)[-300:]}
+    return out
+
+
 def main():
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -302,6 +396,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    pinned = pin_to_gpu_cores(local, world) if world > 1 and not a.no_pin else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -321,7 +416,7 @@ def main():
     frames_np = make_frames(a, rank, B + 1)
     frame_bytes = w * h
     # inputs larger than L2: rotate over R resident copies of the batch (R * (B+1) * 2 MB > 126 MB)
-    R = max(2, int(np.ceil(300e6 / ((B + 1) * frame_bytes))))
+    R = copies_resident(a)
     host = torch.from_numpy(frames_np)
     sets = torch.empty((R, B + 1, h, w), dtype=torch.uint8, device=dev)
     for r in range(R):
@@ -384,9 +479,15 @@ def main():
     ctx.profile(False)
     stage_ms /= nprof
     N = w * h
-    stage_bytes = [1.3333 * N * (B + 1), (2.6667 * N + 9 * P) * B, 9.0 * P * B, 3.0 * N * B]
-    names = ["K1 pyramid+scharr (k_level0/k_pyrdown/k_scharr)", "K2 pyramidal LK (k_lk)", "K3 egomotion (k_keep..k_solve)",
-             "K4 fused warp+diff+threshold+morph (k_mask)"]
+    vf = a.flow_engine == "varflow"
+    # algorithmic bytes per stage.  VarFlow: the two frames in, U and V out = 10 N per pair; the multigrid
+    # solver's own streaming model (every smoothing sweep reading its operands once: ~800 N) is reported beside it.
+    stage_bytes = [1.3333 * N * (B + 1), (10.0 * N if vf else 2.6667 * N + 9 * P) * B, 9.0 * P * B, 3.0 * N * B]
+    names = ["K1 pyramid+scharr (k_level0/k_pyrdown/k_scharr)",
+             "K2 dense variational flow VarFlow::CalcFlow (k_vf_*: presmooth, derivatives, Gauss-Seidel wavefront V-cycles)" if vf else
+             "K2 pyramidal LK on the tracked grid (k_phase_planes + k_window_sums + k_lk_phase)",
+             "K3 egomotion (k_keep_count/k_scan/k_compact/k_hypotheses/k_score/k_accum/k_solve)",
+             "K4 fused warp+diff+threshold+erode+dilate (k_mask, TMA-staged tiles)"]
     peak, peak_src = peaks()
     stages = []
     for n_, m_, by in zip(names, stage_ms, stage_bytes):
@@ -412,6 +513,9 @@ def main():
                 "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src, "peak_spec": 8000.0,
                 "frac_of_spec": stages[dom]["gbs"] / 8000.0,
                 "share_of_step": float(stage_ms[dom] / stage_ms.sum()),
+                "streaming_model": ({"bytes_per_pair": 800.0 * N, "frac": 800.0 * N * B / (stage_ms[1] * 1e-3) / 1e9 / peak,
+                                     "note": "VarFlow multigrid: ~800 N bytes if every smoothing sweep streamed its operands from HBM once"}
+                                    if vf else None),
                 "note": "LK with a 40x40 window is ALU/shared-memory bound by construction (1600 taps x levels x iterations "
                         "per point); its HBM fraction is small by design, see stages[] for the HBM-bound kernels (K1, K4)"}
 
@@ -479,7 +583,7 @@ def main():
     # ---- two camera streams on this GPU (two contexts, two CUDA streams): the head and tail of one stream's batch are filled by
     # the other stream's LK.  An extra figure; `value` above stays the single-stream number.
     multi = None
-    if not a.no_e2e:
+    if not a.no_e2e and not a.lean:
         ctxs, strs, outs2 = [ctx], [stream], [outs]
         cB = capi.Context(width=w, height=h, max_batch=B, pixel_step=a.pixel_step, min_vector_size=0.2, seed=2, device=local,
                           flow_engine=engine)
@@ -539,7 +643,7 @@ def main():
         dt = time.perf_counter() - t0
         cpu = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "%d pairs of the same workload in %.1f s (%s)" % (n, dt, how)}
-        if a.flow_engine != "varflow" and cv_chain.have_cv2() and cores > 1:
+        if a.flow_engine != "varflow" and cv_chain.have_cv2() and cores > 1 and not a.lean:
             # the same chain on ONE host thread beside the all-threads figure (short sample)
             import cv2
             cv2.setNumThreads(1)
@@ -555,15 +659,17 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/f32/f64 (integer samples, f32 sums, f64 homography)", "data": "synthetic",
-            "config": {"workload": workload_name(a), "pairs_per_step": B, "grid_points": P, "streams": world,
-                       "l2": "inputs rotate over %d resident copies (%.0f MB > 126 MB L2)" % (R, R * (B + 1) * frame_bytes / 1e6),
-                       "parallelism": "independent camera streams, one per GPU, no frame-path collective"},
+            "config": config_dict(a, world),
             "mpx_per_s": value * N / 1e6,
             "roofline": roofline, "lk_work": lk_taps, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "stream_stats": gathered, "two_streams_per_gpu": multi,
+            "clocks": clocks, "stream_stats": gathered, "two_streams_per_gpu": multi, "host_pinning": pinned,
         }
-        print(json.dumps(line), flush=True)
+        assert line["config"]["grid_points"] == P
     ctx.close()
+    if rank == 0:
+        if world == 1 and not a.no_secondary and not vf and (w, h, a.pixel_step) == (1920, 1080, 10):
+            line["secondary"] = run_secondary(a)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -47,6 +47,7 @@
 #define NCONS 256            // consumer threads (8 warps); warp 8 is the producer
 #define NSTAGE 2             // stages of the box ring
 #define PREV_BYTES 8192      // staging buffer of the prev box (PBW * PBH = 7744 bytes used): a power of two, indices are wrapped
+#define PREV_STAGE ((PREV_BYTES + 2 * PBW + 127) / 128 * 128)   // + the footprint of a wrapped index; a TMA destination is 128-byte aligned
 
 __device__ __forceinline__ int bilinear_fetch(const uint8_t *__restrict__ src, int pitch, int w, int h, int X, int Y)
 {
@@ -293,8 +294,9 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, const __grid_constant__ MaskKernelMaps maps, int ntx, int nty,
                                                         int ntiles)
 {
-    __shared__ __align__(128) uint8_t sPrev[NSTAGE][PREV_BYTES + 2 * PBW];   // + the footprint of a wrapped index
+    __shared__ __align__(128) uint8_t sPrev[NSTAGE][PREV_STAGE];
     __shared__ __align__(128) uint8_t sCur[NSTAGE][CBW * CBH];
+    static_assert((CBW * CBH) % 128 == 0 && PREV_STAGE % 128 == 0, "TMA destinations are 128-byte aligned");
     __shared__ uint32_t T[TR][SP];
     __shared__ uint32_t E[ER][SP];
     __shared__ MaskTile sT[NSTAGE];
