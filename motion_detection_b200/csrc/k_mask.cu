@@ -12,9 +12,12 @@
 // 5-bit fraction; out = ((32-ax)(32-ay) p00 + ax(32-ay) p01 + (32-ax)ay p10 + ax ay p11 + 512) >> 10, taps outside the
 // image read 0.  Threshold is strict '>'.  Erode ignores out-of-image pixels (identity 255), dilate likewise (identity 0).
 //
-// Layout: CTA = 256 threads, output tile 128 x 32 (+ the 2-pixel halo erode-then-dilate needs).  A thread owns runs of 4
-// consecutive pixels: the thresholded bytes (0x00 / 0xFF) of a run are one 32-bit word in shared memory, so the 3x3
-// erode / dilate are AND / OR of nine funnel-shifted words and the mask leaves as coalesced 32-bit stores.
+// Layout: persistent CTAs of 8 consumer warps + 1 producer warp; output tile 120 x 36, computed region 128 x 40 (the 2-pixel
+// halo erode-then-dilate needs, rounded to whole 4-pixel runs).  A WARP owns a row of the computed region, a lane a run of 4
+// consecutive pixels; the thresholded pixels leave the sampling loop as predicates and __ballot_sync turns a row into four
+// 32-bit words (word j, bit l = pixel 4 l + j), so the 3x3 erode / dilate of a whole 128-pixel row are a few dozen AND / OR /
+// shift instructions on ONE thread (bit-parallel morphology: 1/30 of the byte-SIMD version's instructions), and the mask
+// leaves as coalesced 32-bit stores expanded from the bit planes.
 //
 // TMA-staged tiles (the common case).  The `cur` tile and the SOURCE BOUNDING BOX of the tile in `prev` under H^-1 are
 // fetched by two cp.async.bulk.tensor boxes of tensor maps laid over the image INTERIOR: every tap outside the image is
@@ -24,30 +27,29 @@
 // does not fit (strong zoom / rotation, horizon inside the tile, misaligned caller buffers) take the per-pixel gather path.
 //
 // Coordinates.  The reference divides per pixel in f64 and rounds to 1/32 px; the result must be the same integer.  Fast
-// path: 32 * 2^k / den from a third-order expansion around the exact reciprocal at the tile centre (relative error e^4,
-// e <= 1e-3 checked per tile), numerators by FMA, and rint(v * 2^k) read off the low mantissa bits after adding 1.5 * 2^52
-// -- eight DFMA and no conversion per pixel.  The k extra bits tell how close v is to a rounding boundary: only when it is
-// within 2^-k of one (where the < 1e-3 unit error of the fast path could flip the rint) the pixel is recomputed with the
-// reference's exact operation sequence, so the mask stays bit-identical.
+// path: 32 * 2^KB / den from a third-order expansion around the exact reciprocal at the tile centre (relative error e^4,
+// e <= 1e-3 checked per tile), numerators by FMA from per-row terms the producer warp tabulates, and rint(v * 2^KB) of the
+// BOX-RELATIVE coordinate read off the low mantissa word after adding 1.5 * 2^52 (-32 * 2^KB * box origin folded in): one
+// shift gives the sample column, one shift + mask the 5-bit fraction, the low 16 bits tell how close v is to a rounding
+// boundary.  Only when it is within 2^-(KB-2) of one (where the < 1e-3 unit error of the fast path could flip the rint) the
+// run is recomputed with the reference's exact operation sequence, so the mask stays bit-identical.
 #include "md_internal.h"
 #include "tma.h"
 
-#define TW 128
-#define TH 32
-#define GW (TW / 4 + 2)      // 34 groups of 4 columns: [tx0 - 4, tx0 + 132)
-#define TR (TH + 4)          // 36 rows of thresholded words
-#define ER (TH + 2)          // 34 rows of eroded words
-#define SP (GW + 1)          // shared-memory pitch in words
+#define TW 120               // output tile
+#define TH 36
+#define CW (TW + 8)          // computed region: columns [tx0 - 4, tx0 + 124) = 32 runs of 4 pixels = one warp per row
+#define TR (TH + 4)          // rows [ty0 - 2, ty0 + TH + 2) = 5 rows per consumer warp
 
 // TMA boxes (bytes x rows); the inner extent and the start column are multiples of 16 bytes
-#define CBW 160              // cur: columns [tx0 - 16, tx0 + 144)
+#define CBW 144              // cur: columns [(tx0 - 4) & ~15, + 144)
 #define CBH TR
 #define PBW MD_MASK_PREV_BOX_W
 #define PBH MD_MASK_PREV_BOX_H
 #define NCONS 256            // consumer threads (8 warps); warp 8 is the producer
 #define NSTAGE 2             // stages of the box ring
-#define PREV_BYTES 8192      // staging buffer of the prev box (PBW * PBH = 7744 bytes used): a power of two, indices are wrapped
-#define PREV_STAGE ((PREV_BYTES + 2 * PBW + 127) / 128 * 128)   // + the footprint of a wrapped index; a TMA destination is 128-byte aligned
+#define PREV_STAGE (PBW * PBH)
+#define PREV_AMAX (PBW * PBH - PBW - 2)      // largest index whose 2 x 2 footprint stays inside the staged box
 
 __device__ __forceinline__ int bilinear_fetch(const uint8_t *__restrict__ src, int pitch, int w, int h, int X, int Y)
 {
@@ -138,21 +140,26 @@ __device__ __noinline__ int slow_pixel(const uint8_t *__restrict__ prev, int pit
 // What the producer warp hands to the consumers with every staged tile
 struct MaskTile {
     double M[9];                 // H^-1 of the tile's pair
-    double rc, RS, de6;          // reciprocal of the denominator at the tile centre, 32 * 2^KB * rc, -M6 * rc
-    int bxs, bys;                // image coordinates of the first column / row of the prev box
+    double RS, de6;              // 32 * 2^KB * rc (rc = reciprocal of the denominator at the tile centre), -M6 * rc
+    double magx, magy;           // MASK_MAGIC - 32 * 2^KB * (box origin): the fixed point holds BOX-RELATIVE coordinates
+    double rowX[TR], rowY[TR], rowE[TR];   // per row y: M1 y + M2, M4 y + M5, 1 - (M7 y + M8) rc
     int mode;                    // 0 = gather path, 1 = TMA-staged fast path, 2 = pair without egomotion (empty mask)
     int tx0, ty0, b;             // tile origin, pair
     int zp;                      // frame index of `prev` (ring slot or pair)
-    int pad;
+    int cxo;                     // byte offset of column tx0 - 4 inside the cur box
+    uint32_t colin[4];           // plane j, bit l: column tx0 - 4 + 4 l + j lies inside the image
+    int pad[2];
 };
 
-// Fixed point of the fast path: v = 32 * coordinate * 2^KB is rounded to an integer n by the FP adder itself (sum with
-// 1.5 * 2^52: the 52-bit fraction field of the result is n + 2^51).  Folding 2^(KB-1) + 1 into that constant makes
-//   bits [0, KB) of the low word  <= 2   <=>  v within one unit of a rounding boundary of rint(v / 2^KB)  (-> exact path),
+// Fixed point of the fast path: v = 32 * (coordinate - box origin) * 2^KB is rounded to an integer n by the FP adder itself
+// (sum with 1.5 * 2^52: the 52-bit fraction field of the result is n + 2^51).  Folding 2^(KB-1) + 2 into that constant makes
+//   bits [0, KB) of the low word  <= 4   <=>  v within two units of a rounding boundary of rint(v / 2^KB)  (-> exact path),
 //   bits [KB, KB + 5)                  =  the 5-bit fraction ax of the reference's 1/32-pixel grid,
-//   bits [KB + 5, 52)                  =  the integer sample column, offset by 2^31 (one funnel shift across hi:lo).
-#define KB 15
-#define MASK_MAGIC (6755399441055744.0 + (double)(1 << (KB - 1)) + 1.0)
+//   bits [KB + 5, 32)                  =  the sample column inside the box (< 2^11).
+// (the fast path's own error is < 1e-2 unit: series truncation e^4 <= 1e-12 relative of v < 2^33, FMA roundings 2^-53 relative)
+#define KB 16
+#define MASK_MAGIC (6755399441055744.0 + (double)(1 << (KB - 1)) + 2.0)
+#define MASK_GUARD 4u
 
 __device__ __forceinline__ int lds_u8(uint32_t addr)
 {
@@ -166,67 +173,90 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
     return v;
 }
-
-template <bool INTERIOR>
-__device__ __forceinline__ void mask_phase1_fast(const MaskParams &p, const MaskTile &sT, uint32_t aPrev, uint32_t aCur,
-                                                 uint32_t (*T)[SP], const uint8_t *prev, int tx0, int ty0, int bw0, int tid)
+__device__ __forceinline__ double lds_f64(uint32_t addr)
 {
-    const double *sM = sT.M;
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+// per-halfword unsigned minimum of three packed pairs (DPX: VIMNMX3.U16x2)
+__device__ __forceinline__ uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+
+// The thresholded pixel as a predicate without unpacking the warped value: with v = the bilinear sum before its `+ 512 >> 10`,
+// |((v + 512) >> 10) - c| <= thr  <=>  0 <= v + 512 - (c - thr) * 1024 < (2 thr + 1) * 1024, so "motion" is ONE unsigned compare of
+// v + kc against lim, kc = 512 - (c - thr) * 1024 folded into the interpolation.  thr < 0 (everything is motion): lim = 0.
+struct ThreshConst { int kt; uint32_t lim; };      // kc = kt - c * 1024
+__device__ __forceinline__ ThreshConst thresh_const(int thresh)
+{
+    ThreshConst t;
+    const int thr = min(max(thresh, 0), 255);
+    t.kt = 512 + thr * 1024;
+    t.lim = thresh < 0 ? 0u : (uint32_t)(2 * thr + 1) * 1024u;
+    return t;
+}
+
+// ---- phase 1 (fast): one row of the computed region per warp-iteration, a run of 4 pixels per lane -----------------------------
+__device__ __forceinline__ void mask_phase1_fast(const MaskParams &p, const MaskTile &sT, uint32_t aT, uint32_t aPrev, uint32_t aCur,
+                                                 uint4 *Wp, const uint8_t *prev, int bw0, int warp, int lane)
+{
     const int w = p.w, h = p.h;
-    const uint32_t thr4 = (uint32_t)min(max(p.thresh, 0), 255) * 0x01010101u;
-    const double M0 = sM[0], M1 = sM[1], M2 = sM[2], M3 = sM[3], M4 = sM[4], M5 = sM[5], M6 = sM[6], M7 = sM[7], M8 = sM[8];
-    const double rc = sT.rc, RS = sT.RS, de6 = sT.de6;
-    const uint32_t bxo = (uint32_t)sT.bxs ^ 0x80000000u, byo = (uint32_t)sT.bys ^ 0x80000000u;
-    for (int g = tid; g < GW * TR; g += NCONS) {
-        const int ry = g / GW, gx = g - ry * GW;
-        const int x = tx0 - 4 + 4 * gx, y = ty0 - 2 + ry;
-        uint32_t word = 0xffffffffu;            // erode identity outside the image
-        if (INTERIOR || (y >= 0 && y < h && x + 3 >= 0 && x < w)) {
-            const uint32_t c4 = lds_u32(aCur + ry * CBW + 12 + 4 * gx);
-            const double xd = (double)x, yd = (double)y;
-            const double Xr = fma(M0, xd, fma(M1, yd, M2)), Yr = fma(M3, xd, fma(M4, yd, M5));
-            const double e0 = fma(-fma(M6, xd, fma(M7, yd, M8)), rc, 1.0);
-            uint32_t gmin = 0xffffffffu;        // smallest distance (in 2^-KB units, offset by one) of a coordinate to a rounding boundary
-            bool inbox = true;
-            int wv[4];
+    const ThreshConst tc = thresh_const(p.thresh);
+    const int tx0 = sT.tx0, ty0 = sT.ty0;
+    const int x = tx0 - 4 + 4 * lane;
+    const double xd = (double)x;
+    const double M0 = sT.M[0], M3 = sT.M[3], de6 = sT.de6, RS = sT.RS, magx = sT.magx, magy = sT.magy;
+    const uint32_t aRow = aT + (uint32_t)offsetof(MaskTile, rowX);
+    const uint32_t aC = aCur + sT.cxo + 4 * lane;
+    const uint32_t ci0 = sT.colin[0], ci1 = sT.colin[1], ci2 = sT.colin[2], ci3 = sT.colin[3];
+#pragma unroll 1
+    for (int ry = warp; ry < TR; ry += NCONS / 32) {
+        const int y = ty0 - 2 + ry;
+        const uint32_t c4 = lds_u32(aC + ry * CBW);
+        const double Xr = fma(M0, xd, lds_f64(aRow + 8 * ry)), Yr = fma(M3, xd, lds_f64(aRow + 8 * (TR + ry)));
+        const double e0 = fma(de6, xd, lds_f64(aRow + 8 * (2 * TR + ry)));
+        uint32_t gmin = 0xffffffffu;            // smallest distance (in 2^-KB units, offset by two) of a coordinate to a rounding boundary
+        uint32_t dist[4];
+        bool inbox = true;
+        bool mot[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const double nx = j ? fma(M0, (double)j, Xr) : Xr, ny = j ? fma(M3, (double)j, Yr) : Yr;
-                const double e = j ? fma(de6, (double)j, e0) : e0;
-                const double e3 = fma(fma(e, e, e), e, e);             // e + e^2 + e^3
-                const double rs = fma(RS, e3, RS);
-                const double vX = fma(nx, rs, MASK_MAGIC), vY = fma(ny, rs, MASK_MAGIC);
-                const uint32_t loX = (uint32_t)__double2loint(vX), loY = (uint32_t)__double2loint(vY);
-                const uint32_t lx = __funnelshift_r(loX, (uint32_t)__double2hiint(vX), KB + 5) - bxo;
-                const uint32_t ly = __funnelshift_r(loY, (uint32_t)__double2hiint(vY), KB + 5) - byo;
-                const int ax = (loX >> KB) & 31, ay = (loY >> KB) & 31;
-                gmin = min(gmin, min(loX & ((1u << KB) - 1), loY & ((1u << KB) - 1)));
-                // the ends of the run prove that every footprint is inside the staged box (the run maps to a segment: its inner
-                // pixels lie between the ends)
-                if (j == 0 || j == 3) inbox = inbox && lx < (uint32_t)(PBW - 1) && ly < (uint32_t)(PBH - 1);
-                // the fetch itself is unconditional: the index is wrapped into the (8 KB) staging buffer, so a run that is redone
-                // below reads harmless bytes
-                const uint32_t r = aPrev + ((ly * PBW + lx) & (PREV_BYTES - 1));
-                const int p00 = lds_u8(r), p01 = lds_u8(r + 1), p10 = lds_u8(r + PBW), p11 = lds_u8(r + PBW + 1);
-                const int h0 = (p00 << 5) + ax * (p01 - p00), h1 = (p10 << 5) + ax * (p11 - p10);
-                wv[j] = ((h0 << 5) + ay * (h1 - h0) + 512) >> 10;
-            }
-            if (gmin <= 2u || !inbox) {
-                // rare: a coordinate of the run sits on a rounding boundary (or, never expected, a footprint leaves the box):
-                // redo the run with the reference's exact operation sequence and bounds-checked fetches through L2
-                for (int j = 0; j < 4; j++)
-                    if (INTERIOR || (x + j >= 0 && x + j < w)) wv[j] = slow_pixel(prev, p.pitch, w, h, sM, bw0, x + j, y);
-            }
-            // |warp - cur| > thresh on four pixels at once
-            const uint32_t w4 = __byte_perm(__byte_perm((uint32_t)wv[0], (uint32_t)wv[1], 0x0040), __byte_perm((uint32_t)wv[2], (uint32_t)wv[3], 0x0040), 0x5410);
-            word = p.thresh < 0 ? 0xffffffffu : __vcmpgtu4(__vabsdiffu4(w4, c4), thr4);      // d >= 0 > a negative threshold
-            if (!INTERIOR) {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (x + j < 0 || x + j >= w) word |= 0xffu << (8 * j);
-            }
+        for (int j = 0; j < 4; j++) {
+            const double nx = j ? fma(M0, (double)j, Xr) : Xr, ny = j ? fma(M3, (double)j, Yr) : Yr;
+            const double e = j ? fma(de6, (double)j, e0) : e0;
+            const double e3 = fma(fma(e, e, e), e, e);             // e + e^2 + e^3
+            const double rs = fma(RS, e3, RS);
+            const double vX = fma(nx, rs, magx), vY = fma(ny, rs, magy);
+            const uint32_t loX = (uint32_t)__double2loint(vX), loY = (uint32_t)__double2loint(vY);
+            const uint32_t lx = loX >> (KB + 5), ly = loY >> (KB + 5);
+            const int ax = (loX >> KB) & 31, ay = (loY >> KB) & 31;
+            dist[j] = __byte_perm(loX, loY, 0x5410);               // the two 16-bit boundary distances side by side
+            // the ends of the run prove that every footprint is inside the staged box (the run maps to a segment: its inner
+            // pixels lie between the ends); a coordinate left of / above the box origin borrows into the high bits: lx >= 2^10
+            if (j == 0 || j == 3) inbox = inbox && lx < (uint32_t)(PBW - 1) && ly < (uint32_t)(PBH - 1);
+            // the fetch itself is unconditional: the index is clamped into the staging buffer, so a run that is redone below
+            // reads harmless bytes
+            const uint32_t r = aPrev + min(ly * PBW + lx, (uint32_t)PREV_AMAX);
+            const int p00 = lds_u8(r), p01 = lds_u8(r + 1), p10 = lds_u8(r + PBW), p11 = lds_u8(r + PBW + 1);
+            const int kc = tc.kt - (int)((c4 >> (8 * j)) & 0xffu) * 1024;
+            const int h0 = (p00 << 5) + ax * (p01 - p00), h1 = (p10 << 5) + ax * (p11 - p10);
+            mot[j] = (uint32_t)((h0 << 5) + ay * (h1 - h0) + kc) >= tc.lim;
         }
-        T[ry][gx] = word;
+        gmin = min3_u16x2(min3_u16x2(dist[0], dist[1], dist[2]), dist[3], 0xffffffffu);
+        gmin = min(gmin & 0xffffu, gmin >> 16);
+        if (gmin <= MASK_GUARD || !inbox) {
+            // rare: a coordinate of the run sits on a rounding boundary (or, never expected, a footprint leaves the box):
+            // redo the run with the reference's exact operation sequence and bounds-checked fetches through L2
+            if (y >= 0 && y < h)
+                for (int j = 0; j < 4; j++)
+                    if (x + j >= 0 && x + j < w) {
+                        const int wv = slow_pixel(prev, p.pitch, w, h, sT.M, bw0, x + j, y);
+                        mot[j] = (uint32_t)((wv - (int)((c4 >> (8 * j)) & 0xffu)) * 1024 + tc.kt) >= tc.lim;
+                    }
+        }
+        // the row as four bit planes; pixels outside the image are the erode identity (1)
+        uint32_t w0 = __ballot_sync(0xffffffffu, mot[0]), w1 = __ballot_sync(0xffffffffu, mot[1]);
+        uint32_t w2 = __ballot_sync(0xffffffffu, mot[2]), w3 = __ballot_sync(0xffffffffu, mot[3]);
+        if (y < 0 || y >= h) w0 = w1 = w2 = w3 = 0xffffffffu;
+        if (lane == 0) Wp[ry] = make_uint4(w0 | ~ci0, w1 | ~ci1, w2 | ~ci2, w3 | ~ci3);
     }
 }
 
@@ -243,20 +273,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 
 // The producer's per-tile work: where the tile's source box lies and whether the tile can run from TMA-staged boxes.
-__device__ __forceinline__ void mask_tile_setup(const MaskParams &p, MaskTile &t, int tile, int ntx, int nty)
+// Executed by the whole producer warp (the row tables are filled lane-parallel); returns the same record to every lane.
+__device__ __forceinline__ void mask_tile_setup(const MaskParams &p, MaskTile &t, int tile, int ntx, int nty, int lane)
 {
-    const int w = p.w, h = p.h;
+    const int w = p.w;
     const int b = tile / (ntx * nty), r = tile - b * ntx * nty, tyi = r / ntx, txi = r - tyi * ntx;
     const int tx0 = txi * TW, ty0 = tyi * TH;
-    t.tx0 = tx0; t.ty0 = ty0; t.b = b;
-    t.zp = p.nslots ? (p.prev_slot0 + b) % p.nslots : b;
-    t.rc = 0; t.RS = 0; t.de6 = 0; t.bxs = 0; t.bys = 0; t.pad = 0;
-    if (p.valid && p.valid[b] == 0) { t.mode = 2; return; }
     double M[9];
+    int mode = 0;
+    const bool novalid = p.valid && p.valid[b] == 0;
+    if (!novalid) {
 #pragma unroll
-    for (int i = 0; i < 9; i++) { M[i] = p.Hinv[b * 9 + i]; t.M[i] = M[i]; }
-    int fast = p.use_tma;
-    const int x0 = max(tx0 - 4, 0), x1 = min(tx0 + TW + 3, w - 1), y0 = max(ty0 - 2, 0), y1 = min(ty0 + TH + 1, h - 1);
+        for (int i = 0; i < 9; i++) M[i] = p.Hinv[b * 9 + i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 9; i++) M[i] = 0.0;
+    }
+    int fast = p.use_tma && !novalid;
+    // corners of the computed region (not clamped to the image: pixels outside it are computed and discarded)
+    const int x0 = tx0 - 4, x1 = tx0 + CW - 5, y0 = ty0 - 2, y1 = ty0 + TH + 1;
     double lo_x = 1e300, hi_x = -1e300, lo_y = 1e300, hi_y = -1e300, dmin = 1e300, dmax = -1e300;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -269,27 +304,71 @@ __device__ __forceinline__ void mask_tile_setup(const MaskParams &p, MaskTile &t
     }
     // one sign, away from zero, finite; |32 * coordinate * 2^KB| stays far below the 2^51 the fixed point holds
     if (!(dmin * dmax > 0.0) || !(fmin(fabs(dmin), fabs(dmax)) > 1e-9) || !(lo_x > -1e6 && hi_x < 1e6 && lo_y > -1e6 && hi_y < 1e6)) fast = 0;
+    int bxs = 0, bys = 0;
+    double rc = 0.0, de6 = 0.0;
     if (fast) {
         const int bx0 = (int)floor(lo_x) - 1, bx1 = (int)floor(hi_x) + 2, by0 = (int)floor(lo_y) - 1, by1 = (int)floor(hi_y) + 2;
-        t.bxs = bx0 & ~15;                    // 16-byte aligned box start (two's complement: rounds towards -inf)
-        t.bys = by0;
-        if (bx1 - t.bxs + 1 > PBW || by1 - t.bys + 1 > PBH) fast = 0;
+        bxs = bx0 & ~15;                      // 16-byte aligned box start (two's complement: rounds towards -inf)
+        bys = by0;
+        if (bx1 - bxs + 1 > PBW || by1 - bys + 1 > PBH) fast = 0;
         // a box that misses the image altogether is left to the gather path
-        if (t.bxs >= w || t.bxs + PBW <= 0 || t.bys >= h || t.bys + PBH <= 0) fast = 0;
+        if (bxs >= w || bxs + PBW <= 0 || bys >= p.h || bys + PBH <= 0) fast = 0;
         const double xc = 0.5 * (x0 + x1), yc = 0.5 * (y0 + y1);
         const double denc = fma(M[6], xc, fma(M[7], yc, M[8]));
-        t.rc = 1.0 / denc;
-        t.RS = t.rc * (double)(32 << KB);
-        t.de6 = -M[6] * t.rc;
+        rc = 1.0 / denc;
+        de6 = -M[6] * rc;
         // |1 - den * rc| over the tile: the third-order expansion is good to e^4 <= 1e-12
-        if (!((fabs(t.de6) * (0.5 * (x1 - x0) + 1.0) + fabs(M[7] * t.rc) * (0.5 * (y1 - y0) + 1.0)) < 1e-3)) fast = 0;
+        if (!((fabs(de6) * (0.5 * (x1 - x0) + 1.0) + fabs(M[7] * rc) * (0.5 * (y1 - y0) + 1.0)) < 1e-3)) fast = 0;
     }
-    t.mode = fast ? 1 : 0;
+    mode = novalid ? 2 : (fast ? 1 : 0);
+    const double RS = rc * (double)(32u << KB) ;
+    // the per-row terms of the numerators and of e = 1 - den * rc
+    for (int ry = lane; ry < TR; ry += 32) {
+        const double yd = (double)(ty0 - 2 + ry);
+        t.rowX[ry] = fma(M[1], yd, M[2]);
+        t.rowY[ry] = fma(M[4], yd, M[5]);
+        t.rowE[ry] = fma(-fma(M[7], yd, M[8]), rc, 1.0);
+    }
+    if (lane < 4) {
+        uint32_t m = 0;
+        for (int l = 0; l < 32; l++) {
+            const int xx = x0 + 4 * l + lane;
+            if (xx >= 0 && xx < w) m |= 1u << l;
+        }
+        t.colin[lane] = m;
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < 9; i++) t.M[i] = M[i];
+        t.tx0 = tx0; t.ty0 = ty0; t.b = b;
+        t.zp = p.nslots ? (p.prev_slot0 + b) % p.nslots : b;
+        t.RS = RS; t.de6 = de6;
+        t.magx = MASK_MAGIC - (double)bxs * (double)(32u << KB);
+        t.magy = MASK_MAGIC - (double)bys * (double)(32u << KB);
+        t.cxo = x0 - (x0 & ~15);
+        t.mode = mode;
+        t.pad[0] = bxs; t.pad[1] = bys;
+    }
+    __syncwarp();
 }
 
-// Persistent, warp-specialised: warp 8 (one lane) walks the CTA's tiles ahead of the others -- source box, expansion
-// constants, two TMA box loads per tile into a two-stage ring guarded by full / empty mbarriers -- while warps 0-7 sample,
-// threshold, erode, dilate and store the tile that has landed.
+// one row of three-neighbour AND (erode) / OR (dilate) along x on the interleaved planes: pixel 4 l + j has its left
+// neighbour in plane j - 1 (plane 3 of lane l - 1 for j = 0) and its right neighbour in plane j + 1 (plane 0 of lane l + 1)
+template <bool AND>
+__device__ __forceinline__ uint4 morph_row_x(const uint4 v)
+{
+    uint4 r;
+    if (AND) {
+        r.x = v.x & (v.w << 1 | 1u) & v.y; r.y = v.y & v.x & v.z; r.z = v.z & v.y & v.w; r.w = v.w & v.z & (v.x >> 1 | 0x80000000u);
+    } else {
+        r.x = v.x | (v.w << 1) | v.y; r.y = v.y | v.x | v.z; r.z = v.z | v.y | v.w; r.w = v.w | v.z | (v.x >> 1);
+    }
+    return r;
+}
+
+// Persistent, warp-specialised: warp 8 walks the CTA's tiles ahead of the others -- source box, expansion constants, row
+// tables, two TMA box loads per tile into a two-stage ring guarded by full / empty mbarriers -- while warps 0-7 sample and
+// threshold the tile that has landed (phase 1), erode + dilate it on bit planes (phase 2) and expand / store it (phase 3).
 template <bool ALIGNED>
 __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, const __grid_constant__ MaskKernelMaps maps, int ntx, int nty,
                                                         int ntiles)
@@ -297,9 +376,9 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
     __shared__ __align__(128) uint8_t sPrev[NSTAGE][PREV_STAGE];
     __shared__ __align__(128) uint8_t sCur[NSTAGE][CBW * CBH];
     static_assert((CBW * CBH) % 128 == 0 && PREV_STAGE % 128 == 0, "TMA destinations are 128-byte aligned");
-    __shared__ uint32_t T[TR][SP];
-    __shared__ uint32_t E[ER][SP];
-    __shared__ MaskTile sT[NSTAGE];
+    __shared__ __align__(16) uint4 Wp[TR];       // thresholded rows, four interleaved bit planes each
+    __shared__ __align__(16) uint4 Dp[TR];       // after erode + dilate (rows 2 .. TR - 3 are the output rows)
+    __shared__ __align__(16) MaskTile sT[NSTAGE];
     __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
     const int w = p.w, h = p.h;
     const int bh0 = h < 16 ? h : 16;
@@ -309,29 +388,31 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
         mbar_fence_init();
     }
     __syncthreads();
+    const int lane = threadIdx.x & 31;
 
     if (threadIdx.x >= NCONS) {
-        // ---- producer -------------------------------------------------------------------------------------------------------
-        if (threadIdx.x == NCONS) {
-            int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
-                const int s = it % NSTAGE;
-                if (it >= NSTAGE) mbar_wait(&empty[s], ((it / NSTAGE) - 1) & 1);
-                MaskTile &t = sT[s];
-                mask_tile_setup(p, t, tile, ntx, nty);
+        // ---- producer warp ------------------------------------------------------------------------------------------------------
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const int s = it % NSTAGE;
+            if (it >= NSTAGE) mbar_wait(&empty[s], ((it / NSTAGE) - 1) & 1);
+            MaskTile &t = sT[s];
+            mask_tile_setup(p, t, tile, ntx, nty, lane);
+            if (lane == 0) {
                 if (t.mode == 1) {
                     const int zc = p.nslots ? (p.cur_slot0 + t.b) % p.nslots : t.b;
                     mbar_expect_tx(&full[s], PBW * PBH + CBW * CBH);
-                    tma_load_3d(sPrev[s], &maps.prev, t.bxs, t.bys, t.zp, &full[s]);
-                    tma_load_3d(sCur[s], &maps.cur, t.tx0 - 16, t.ty0 - 2, zc, &full[s]);
+                    tma_load_3d(sPrev[s], &maps.prev, t.pad[0], t.pad[1], t.zp, &full[s]);
+                    tma_load_3d(sCur[s], &maps.cur, (t.tx0 - 4) & ~15, t.ty0 - 2, zc, &full[s]);
                 } else mbar_arrive(&full[s]);
             }
+            __syncwarp();
         }
         return;
     }
 
     // ---- consumers ----------------------------------------------------------------------------------------------------------
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5;
     int local = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
@@ -343,7 +424,7 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
         if (mode == 2) {
             // no egomotion (fewer than the minimal number of vectors): empty mask
             __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+            if (lane == 0) mbar_arrive(&empty[s]);
             for (int i = tid; i < TW * TH; i += NCONS) {
                 int x = tx0 + i % TW, y = ty0 + i / TW;
                 if (x < w && y < h) out[(size_t)y * p.mask_pitch + x] = 0;
@@ -351,20 +432,19 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
             continue;
         }
         const uint8_t *prev = p.prev + (long long)t.zp * p.stride;
-        const bool interior = tx0 - 4 >= 0 && tx0 + TW + 4 <= w && ty0 - 2 >= 0 && ty0 + TH + 2 <= h;
+        const uint32_t ci0 = t.colin[0], ci1 = t.colin[1], ci2 = t.colin[2], ci3 = t.colin[3];
         if (mode == 1) {
-            // ---- phase 1 (fast): warp + absdiff + threshold from the staged boxes, 4 pixels per thread-iteration -----------
-            if (interior) mask_phase1_fast<true>(p, t, smem_u32(sPrev[s]), smem_u32(sCur[s]), T, prev, tx0, ty0, bw0, tid);
-            else mask_phase1_fast<false>(p, t, smem_u32(sPrev[s]), smem_u32(sCur[s]), T, prev, tx0, ty0, bw0, tid);
+            mask_phase1_fast(p, t, smem_u32(&t), smem_u32(sPrev[s]), smem_u32(sCur[s]), Wp, prev, bw0, warp, lane);
         } else {
             // ---- phase 1 (gather): per-pixel loads through L2, reference operation sequence with the Newton shortcut ---------
             const double *sM = t.M;
+            const ThreshConst tc = thresh_const(p.thresh);
             const uint8_t *cur = p.cur + (long long)(p.nslots ? (p.cur_slot0 + b) % p.nslots : b) * p.stride;
             const bool uniform_block = (bw0 & 3) == 0;     // a run of 4 aligned columns never straddles a 64-column block
-            for (int g = tid; g < GW * TR; g += NCONS) {
-                const int ry = g / GW, gx = g - ry * GW;
-                const int x = tx0 - 4 + 4 * gx, y = ty0 - 2 + ry;
-                uint32_t word = 0xffffffffu;            // erode identity outside the image
+            const int x = tx0 - 4 + 4 * lane;
+            for (int ry = warp; ry < TR; ry += NCONS / 32) {
+                const int y = ty0 - 2 + ry;
+                bool mot[4] = {true, true, true, true};
                 if (y >= 0 && y < h && x + 3 >= 0 && x < w) {
                     uint32_t c4;
                     if (ALIGNED && x >= 0 && x + 3 < w) c4 = __ldg(reinterpret_cast<const uint32_t *>(cur + (size_t)y * p.pitch + x));
@@ -385,11 +465,9 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
                         Y0 = __dadd_rn(__dadd_rn(__dmul_rn(sM[3], dbx), __dmul_rn(sM[4], dy)), sM[5]);
                         W0 = __dadd_rn(__dadd_rn(__dmul_rn(sM[6], dbx), __dmul_rn(sM[7], dy)), sM[8]);
                     }
-                    word = 0;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int xj = x + j;
-                        uint32_t tt = 0xffu;
                         if (xj >= 0 && xj < w) {
                             double nx, ny, den;
                             if (uniform_block) {
@@ -400,89 +478,71 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
                             int X, Y;
                             project(nx, ny, den, X, Y);
                             const int wv = bilinear_fetch(prev, p.pitch, w, h, X, Y);
-                            int d = wv - (int)((c4 >> (8 * j)) & 0xffu);
-                            d = d < 0 ? -d : d;
-                            tt = d > p.thresh ? 0xffu : 0u;
+                            mot[j] = (uint32_t)((wv - (int)((c4 >> (8 * j)) & 0xffu)) * 1024 + tc.kt) >= tc.lim;
                         }
-                        word |= tt << (8 * j);
                     }
                 }
-                T[ry][gx] = word;
+                const uint32_t w0 = __ballot_sync(0xffffffffu, mot[0]), w1 = __ballot_sync(0xffffffffu, mot[1]);
+                const uint32_t w2 = __ballot_sync(0xffffffffu, mot[2]), w3 = __ballot_sync(0xffffffffu, mot[3]);
+                if (lane == 0) Wp[ry] = make_uint4(w0 | ~ci0, w1 | ~ci1, w2 | ~ci2, w3 | ~ci3);
             }
         }
         consumer_sync();
         // the staged boxes and the tile record are consumed: hand the stage back to the producer
-        // (the tile's scalars were copied to registers above; phases 2 and 3 only touch T / E)
-        if ((tid & 31) == 0) mbar_arrive(&empty[s]);
+        // (the tile's scalars were copied to registers above; phases 2 and 3 only touch Wp / Dp)
+        if (lane == 0) mbar_arrive(&empty[s]);
 
-        if (p.morph) {
-            // ---- phase 2: erode = AND of the nine neighbours, four pixels per word ----------------------------------
-            for (int g = tid; g < GW * ER; g += NCONS) {
-                const int ry = g / GW, gx = g - ry * GW;
-                const int x = tx0 - 4 + 4 * gx, y = ty0 - 1 + ry;
-                uint32_t e = 0xffffffffu;
+        // ---- phase 2: erode then dilate on the bit planes; one thread per output row of the tile --------------------------------
+        if (tid < TH) {
+            const int r = tid + 2;                              // row of the computed region
+            uint4 o;
+            if (p.morph) {
+                uint4 hx[5];
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const uint32_t c = T[ry + j][gx];
-                    const uint32_t l = gx > 0 ? T[ry + j][gx - 1] : 0xffffffffu;
-                    const uint32_t r = gx < GW - 1 ? T[ry + j][gx + 1] : 0xffffffffu;
-                    e &= c & __funnelshift_l(l, c, 8) & __funnelshift_r(c, r, 8);
-                }
-                // dilate identity (0) for pixels outside the image
-                uint32_t m = interior ? 0xffffffffu : 0u;
-                if (!interior && y >= 0 && y < h) {
+                for (int k = 0; k < 5; k++) hx[k] = morph_row_x<true>(Wp[r - 2 + k]);
+                uint4 e[3];
 #pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (x + j >= 0 && x + j < w) m |= 0xffu << (8 * j);
+                for (int k = 0; k < 3; k++) {
+                    // eroded row r - 1 + k; outside the image it is the dilate identity (0)
+                    const int y = ty0 - 2 + r - 1 + k;
+                    const bool in = y >= 0 && y < h;
+                    e[k].x = in ? (hx[k].x & hx[k + 1].x & hx[k + 2].x & ci0) : 0u;
+                    e[k].y = in ? (hx[k].y & hx[k + 1].y & hx[k + 2].y & ci1) : 0u;
+                    e[k].z = in ? (hx[k].z & hx[k + 1].z & hx[k + 2].z & ci2) : 0u;
+                    e[k].w = in ? (hx[k].w & hx[k + 1].w & hx[k + 2].w & ci3) : 0u;
                 }
-                E[ry][gx] = e & m;
-            }
-            consumer_sync();
-            // ---- phase 3: dilate = OR of the nine neighbours, coalesced 32-bit stores -------------------------------
-            for (int g = tid; g < (TW / 4) * TH; g += NCONS) {
-                const int ry = g / (TW / 4), go = g - ry * (TW / 4);
-                const int gx = go + 1;
-                const int x = tx0 + 4 * go, y = ty0 + ry;
+                const uint4 d0 = morph_row_x<false>(e[0]), d1 = morph_row_x<false>(e[1]), d2 = morph_row_x<false>(e[2]);
+                o = make_uint4(d0.x | d1.x | d2.x, d0.y | d1.y | d2.y, d0.z | d1.z | d2.z, d0.w | d1.w | d2.w);
+            } else o = Wp[r];
+            // only the tile's own columns (lanes 1 .. 30) inside the image count and are stored
+            o.x &= ci0 & 0x7ffffffeu; o.y &= ci1 & 0x7ffffffeu; o.z &= ci2 & 0x7ffffffeu; o.w &= ci3 & 0x7ffffffeu;
+            Dp[r] = o;
+            if (ty0 + tid < h) local += __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
+        }
+        consumer_sync();
+        // ---- phase 3: bits -> bytes, coalesced 32-bit stores ---------------------------------------------------------------------
+        if (lane >= 1 && lane <= TW / 4) {
+            const int x = tx0 - 4 + 4 * lane;
+            for (int ry = warp; ry < TH; ry += NCONS / 32) {
+                const int y = ty0 + ry;
                 if (x >= w || y >= h) continue;
-                uint32_t o = 0;
-#pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    const uint32_t c = E[ry + j][gx], l = E[ry + j][gx - 1], r = E[ry + j][gx + 1];
-                    o |= c | __funnelshift_l(l, c, 8) | __funnelshift_r(c, r, 8);
-                }
+                const uint4 d = Dp[ry + 2];
+                const uint32_t o = (((d.x >> lane) & 1u) | (((d.y >> lane) & 1u) << 8) | (((d.z >> lane) & 1u) << 16) | (((d.w >> lane) & 1u) << 24)) * 255u;
                 uint8_t *dst = out + (size_t)y * p.mask_pitch + x;
-                if (ALIGNED && x + 3 < w) {
-                    *reinterpret_cast<uint32_t *>(dst) = o;
-                    local += __popc(o & 0x01010101u);
-                } else {
+                if (ALIGNED && x + 3 < w) *reinterpret_cast<uint32_t *>(dst) = o;
+                else {
 #pragma unroll
                     for (int j = 0; j < 4; j++)
-                        if (x + j < w) { dst[j] = (uint8_t)(o >> (8 * j)); local += (o >> (8 * j)) & 1; }
-                }
-            }
-        } else {
-            for (int g = tid; g < (TW / 4) * TH; g += NCONS) {
-                const int ry = g / (TW / 4), go = g - ry * (TW / 4);
-                const int x = tx0 + 4 * go, y = ty0 + ry;
-                if (x >= w || y >= h) continue;
-                const uint32_t o = T[ry + 2][go + 1];
-                uint8_t *dst = out + (size_t)y * p.mask_pitch + x;
-                if (ALIGNED && x + 3 < w) {
-                    *reinterpret_cast<uint32_t *>(dst) = o;
-                    local += __popc(o & 0x01010101u);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (x + j < w) { dst[j] = (uint8_t)(o >> (8 * j)); local += (o >> (8 * j)) & 1; }
+                        if (x + j < w) dst[j] = (uint8_t)(o >> (8 * j));
                 }
             }
         }
-        // T is rewritten by the next tile's phase 1: every consumer must be done reading it (phase 2 / the raw copy)
-        consumer_sync();
+        // Wp is rewritten by the next tile's phase 1 only after every consumer passed the barrier above (phase 2 is done); Dp is
+        // rewritten by the next tile's phase 2, which sits behind the next tile's first barrier
     }
     if (p.stat_mask) {
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-        if ((tid & 31) == 0 && local) atomicAdd(p.stat_mask, (unsigned long long)local);
+        if (lane == 0 && local) atomicAdd(p.stat_mask, (unsigned long long)local);
     }
 }
 
