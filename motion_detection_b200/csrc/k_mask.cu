@@ -50,6 +50,7 @@
 #define NSTAGE 2             // stages of the box ring
 #define PREV_STAGE (PBW * PBH)
 #define PREV_AMAX (PBW * PBH - PBW - 2)      // largest index whose 2 x 2 footprint stays inside the staged box
+static_assert(PBW == 256, "the sample address is (row byte, column byte) of the fixed-point coordinates: the box pitch is 256");
 
 __device__ __forceinline__ int bilinear_fetch(const uint8_t *__restrict__ src, int pitch, int w, int h, int X, int Y)
 {
@@ -143,7 +144,7 @@ struct MaskTile {
     double RS, de6;              // 32 * 2^KB * rc (rc = reciprocal of the denominator at the tile centre), -M6 * rc
     double magx, magy;           // MASK_MAGIC - 32 * 2^KB * (box origin): the fixed point holds BOX-RELATIVE coordinates
     double rowX[TR], rowY[TR], rowE[TR];   // per row y: M1 y + M2, M4 y + M5, 1 - (M7 y + M8) rc
-    int mode;                    // 0 = gather path, 1 = TMA-staged fast path, 2 = pair without egomotion (empty mask)
+    int mode;                    // 0 = gather path, 1 = TMA-staged fast path (3 = its first-order variant), 2 = pair without egomotion (empty mask)
     int tx0, ty0, b;             // tile origin, pair
     int zp;                      // frame index of `prev` (ring slot or pair)
     int cxo;                     // byte offset of column tx0 - 4 inside the cur box
@@ -153,11 +154,13 @@ struct MaskTile {
 
 // Fixed point of the fast path: v = 32 * (coordinate - box origin) * 2^KB is rounded to an integer n by the FP adder itself
 // (sum with 1.5 * 2^52: the 52-bit fraction field of the result is n + 2^51).  Folding 2^(KB-1) + 2 into that constant makes
-//   bits [0, KB) of the low word  <= 4   <=>  v within two units of a rounding boundary of rint(v / 2^KB)  (-> exact path),
+//   bits [0, KB) of the low word  <= 4   <=>  v within two units of a rounding boundary of rint(v / 2^KB)  (-> exact path;
+//                                              only the low 16 of the 19 bits are looked at: a superset, 8e-5 of the coordinates),
 //   bits [KB, KB + 5)                  =  the 5-bit fraction ax of the reference's 1/32-pixel grid,
-//   bits [KB + 5, 32)                  =  the sample column inside the box (< 2^11).
-// (the fast path's own error is < 1e-2 unit: series truncation e^4 <= 1e-12 relative of v < 2^33, FMA roundings 2^-53 relative)
-#define KB 16
+//   bits [KB + 5, 32) = byte 3         =  the sample column / row inside the box (box pitch 256: PRMT of the two bytes = the address).
+// (the fast path's own error is < 1e-2 unit: series truncation e^4 <= 1e-12 relative of v < 2^32, FMA roundings 2^-53 relative of
+// the absolute coordinate)
+#define KB 19
 #define MASK_MAGIC (6755399441055744.0 + (double)(1 << (KB - 1)) + 2.0)
 #define MASK_GUARD 4u
 
@@ -179,6 +182,14 @@ __device__ __forceinline__ double lds_f64(uint32_t addr)
     asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
+// prmt.b32 with the full selector semantics (bit 3 of a selector nibble replicates the sign bit of the chosen byte; __byte_perm
+// only looks at the low three bits)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
 // per-halfword unsigned minimum of three packed pairs (DPX: VIMNMX3.U16x2)
 __device__ __forceinline__ uint32_t min3_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 
@@ -196,6 +207,9 @@ __device__ __forceinline__ ThreshConst thresh_const(int thresh)
 }
 
 // ---- phase 1 (fast): one row of the computed region per warp-iteration, a run of 4 pixels per lane -----------------------------
+// ORDER = 3: rs = RS (1 + e + e^2 + e^3) per pixel.  ORDER = 1 (|e| < 2e-6 over the tile, i.e. a nearly affine map -- the usual
+// frame-to-frame egomotion): rs = RS (1 + e), which is linear along the run: one FMA per pixel (e^2 < 4e-12 relative).
+template <int ORDER>
 __device__ __forceinline__ void mask_phase1_fast(const MaskParams &p, const MaskTile &sT, uint32_t aT, uint32_t aPrev, uint32_t aCur,
                                                  uint4 *Wp, const uint8_t *prev, int bw0, int warp, int lane)
 {
@@ -205,56 +219,61 @@ __device__ __forceinline__ void mask_phase1_fast(const MaskParams &p, const Mask
     const int x = tx0 - 4 + 4 * lane;
     const double xd = (double)x;
     const double M0 = sT.M[0], M3 = sT.M[3], de6 = sT.de6, RS = sT.RS, magx = sT.magx, magy = sT.magy;
-    const uint32_t aRow = aT + (uint32_t)offsetof(MaskTile, rowX);
-    const uint32_t aC = aCur + sT.cxo + 4 * lane;
+    const double drs = RS * de6;                     // ORDER 1: d rs / d x
+    uint32_t aRow = aT + (uint32_t)offsetof(MaskTile, rowX) + 8 * warp;
+    uint32_t aC = aCur + sT.cxo + 4 * lane + warp * CBW;
     const uint32_t ci0 = sT.colin[0], ci1 = sT.colin[1], ci2 = sT.colin[2], ci3 = sT.colin[3];
+    int y = ty0 - 2 + warp;
 #pragma unroll 1
-    for (int ry = warp; ry < TR; ry += NCONS / 32) {
-        const int y = ty0 - 2 + ry;
-        const uint32_t c4 = lds_u32(aC + ry * CBW);
-        const double Xr = fma(M0, xd, lds_f64(aRow + 8 * ry)), Yr = fma(M3, xd, lds_f64(aRow + 8 * (TR + ry)));
-        const double e0 = fma(de6, xd, lds_f64(aRow + 8 * (2 * TR + ry)));
-        uint32_t gmin = 0xffffffffu;            // smallest distance (in 2^-KB units, offset by two) of a coordinate to a rounding boundary
-        uint32_t dist[4];
-        bool inbox = true;
-        bool mot[4];
+    for (int ry = warp; ry < TR; ry += NCONS / 32, y += NCONS / 32, aRow += 8 * (NCONS / 32), aC += (NCONS / 32) * CBW) {
+        const uint32_t c4 = lds_u32(aC);
+        const double Xr = fma(M0, xd, lds_f64(aRow)), Yr = fma(M3, xd, lds_f64(aRow + 8 * TR));
+        const double e0 = fma(de6, xd, lds_f64(aRow + 16 * TR));
+        const double rs0 = fma(RS, e0, RS);
+        uint32_t dist[4], a16[4];
+        int vp[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const double nx = j ? fma(M0, (double)j, Xr) : Xr, ny = j ? fma(M3, (double)j, Yr) : Yr;
-            const double e = j ? fma(de6, (double)j, e0) : e0;
-            const double e3 = fma(fma(e, e, e), e, e);             // e + e^2 + e^3
-            const double rs = fma(RS, e3, RS);
+            double rs;
+            if (ORDER == 1) rs = j ? fma(drs, (double)j, rs0) : rs0;
+            else {
+                const double e = j ? fma(de6, (double)j, e0) : e0;
+                rs = fma(RS, fma(fma(e, e, e), e, e), RS);            // RS (1 + e + e^2 + e^3)
+            }
             const double vX = fma(nx, rs, magx), vY = fma(ny, rs, magy);
             const uint32_t loX = (uint32_t)__double2loint(vX), loY = (uint32_t)__double2loint(vY);
-            const uint32_t lx = loX >> (KB + 5), ly = loY >> (KB + 5);
             const int ax = (loX >> KB) & 31, ay = (loY >> KB) & 31;
             dist[j] = __byte_perm(loX, loY, 0x5410);               // the two 16-bit boundary distances side by side
-            // the ends of the run prove that every footprint is inside the staged box (the run maps to a segment: its inner
-            // pixels lie between the ends); a coordinate left of / above the box origin borrows into the high bits: lx >= 2^10
-            if (j == 0 || j == 3) inbox = inbox && lx < (uint32_t)(PBW - 1) && ly < (uint32_t)(PBH - 1);
-            // the fetch itself is unconditional: the index is clamped into the staging buffer, so a run that is redone below
-            // reads harmless bytes
-            const uint32_t r = aPrev + min(ly * PBW + lx, (uint32_t)PREV_AMAX);
-            const int p00 = lds_u8(r), p01 = lds_u8(r + 1), p10 = lds_u8(r + PBW), p11 = lds_u8(r + PBW + 1);
-            const int kc = tc.kt - (int)((c4 >> (8 * j)) & 0xffu) * 1024;
-            const int h0 = (p00 << 5) + ax * (p01 - p00), h1 = (p10 << 5) + ax * (p11 - p10);
-            mot[j] = (uint32_t)((h0 << 5) + ay * (h1 - h0) + kc) >= tc.lim;
+            // byte 3 of the low words = column / row inside the box.  Every footprint of the tile lies inside the staged box: the
+            // producer sized it from the images of the region's corners (a projective map with a denominator of one sign maps the
+            // rectangle into the convex hull of its corner images) and sends tiles that do not fit down the gather path.  The
+            // index is clamped all the same, so the loads stay inside the staging buffer whatever the coordinates are.
+            a16[j] = __byte_perm(loX, loY, 0x7373);
+            const uint32_t r = aPrev + min3_u16x2(a16[j], (uint32_t)PREV_AMAX, (uint32_t)PREV_AMAX);   // low half clamped, high half -> 0
+            const uint32_t p00 = (uint32_t)lds_u8(r), p01 = (uint32_t)lds_u8(r + 1), p10 = (uint32_t)lds_u8(r + PBW), p11 = (uint32_t)lds_u8(r + PBW + 1);
+            // both rows at once: (h0, h1) = (32 - ax) (p00, p10) + ax (p01, p11) as 16-bit halves, then (32 - ay) h0 + ay h1 by dp2a
+            const uint32_t hh = (uint32_t)(32 - ax) * __byte_perm(p00, p10, 0x5410) + (uint32_t)ax * __byte_perm(p01, p11, 0x5410);
+            const int kc = tc.kt - (int)__byte_perm(c4, 0, 0x4440 + j) * 1024;
+            int v;
+            asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(v) : "r"(hh), "r"(32 + 255 * ay), "r"(kc));
+            vp[j] = v;
         }
-        gmin = min3_u16x2(min3_u16x2(dist[0], dist[1], dist[2]), dist[3], 0xffffffffu);
-        gmin = min(gmin & 0xffffu, gmin >> 16);
-        if (gmin <= MASK_GUARD || !inbox) {
-            // rare: a coordinate of the run sits on a rounding boundary (or, never expected, a footprint leaves the box):
+        uint32_t gmin = min3_u16x2(min3_u16x2(dist[0], dist[1], dist[2]), dist[3], 0xffffffffu);
+        gmin = min(gmin & 0xffffu, gmin >> 16);     // smallest distance (in 2^-KB units, offset by two) of a coordinate to a rounding boundary
+        if (gmin <= MASK_GUARD) {
+            // rare: a coordinate of the run sits on a rounding boundary:
             // redo the run with the reference's exact operation sequence and bounds-checked fetches through L2
             if (y >= 0 && y < h)
                 for (int j = 0; j < 4; j++)
                     if (x + j >= 0 && x + j < w) {
                         const int wv = slow_pixel(prev, p.pitch, w, h, sT.M, bw0, x + j, y);
-                        mot[j] = (uint32_t)((wv - (int)((c4 >> (8 * j)) & 0xffu)) * 1024 + tc.kt) >= tc.lim;
+                        vp[j] = (wv - (int)((c4 >> (8 * j)) & 0xffu)) * 1024 + tc.kt;
                     }
         }
         // the row as four bit planes; pixels outside the image are the erode identity (1)
-        uint32_t w0 = __ballot_sync(0xffffffffu, mot[0]), w1 = __ballot_sync(0xffffffffu, mot[1]);
-        uint32_t w2 = __ballot_sync(0xffffffffu, mot[2]), w3 = __ballot_sync(0xffffffffu, mot[3]);
+        uint32_t w0 = __ballot_sync(0xffffffffu, (uint32_t)vp[0] >= tc.lim), w1 = __ballot_sync(0xffffffffu, (uint32_t)vp[1] >= tc.lim);
+        uint32_t w2 = __ballot_sync(0xffffffffu, (uint32_t)vp[2] >= tc.lim), w3 = __ballot_sync(0xffffffffu, (uint32_t)vp[3] >= tc.lim);
         if (y < 0 || y >= h) w0 = w1 = w2 = w3 = 0xffffffffu;
         if (lane == 0) Wp[ry] = make_uint4(w0 | ~ci0, w1 | ~ci1, w2 | ~ci2, w3 | ~ci3);
     }
@@ -317,10 +336,12 @@ __device__ __forceinline__ void mask_tile_setup(const MaskParams &p, MaskTile &t
         const double denc = fma(M[6], xc, fma(M[7], yc, M[8]));
         rc = 1.0 / denc;
         de6 = -M[6] * rc;
-        // |1 - den * rc| over the tile: the third-order expansion is good to e^4 <= 1e-12
-        if (!((fabs(de6) * (0.5 * (x1 - x0) + 1.0) + fabs(M[7] * rc) * (0.5 * (y1 - y0) + 1.0)) < 1e-3)) fast = 0;
+        // |1 - den * rc| over the tile: the third-order expansion is good to e^4 <= 1e-12, the first-order one to e^2 <= 4e-12
+        const double emax = fabs(de6) * (0.5 * (x1 - x0) + 1.0) + fabs(M[7] * rc) * (0.5 * (y1 - y0) + 1.0);
+        if (!(emax < 1e-3)) fast = 0;
+        else if (fast && emax < 2e-6) fast = 3;
     }
-    mode = novalid ? 2 : (fast ? 1 : 0);
+    mode = novalid ? 2 : fast;
     const double RS = rc * (double)(32u << KB) ;
     // the per-row terms of the numerators and of e = 1 - den * rc
     for (int ry = lane; ry < TR; ry += 32) {
@@ -376,8 +397,8 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
     __shared__ __align__(128) uint8_t sPrev[NSTAGE][PREV_STAGE];
     __shared__ __align__(128) uint8_t sCur[NSTAGE][CBW * CBH];
     static_assert((CBW * CBH) % 128 == 0 && PREV_STAGE % 128 == 0, "TMA destinations are 128-byte aligned");
-    __shared__ __align__(16) uint4 Wp[TR];       // thresholded rows, four interleaved bit planes each
-    __shared__ __align__(16) uint4 Dp[TR];       // after erode + dilate (rows 2 .. TR - 3 are the output rows)
+    __shared__ __align__(16) uint4 Wp[2][TR];    // thresholded rows, four interleaved bit planes each (double buffered over tiles)
+    __shared__ __align__(16) uint4 Dp[2][TR];    // after erode + dilate (rows 2 .. TR - 3 are the output rows)
     __shared__ __align__(16) MaskTile sT[NSTAGE];
     __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
     const int w = p.w, h = p.h;
@@ -399,7 +420,7 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
             MaskTile &t = sT[s];
             mask_tile_setup(p, t, tile, ntx, nty, lane);
             if (lane == 0) {
-                if (t.mode == 1) {
+                if (t.mode == 1 || t.mode == 3) {
                     const int zc = p.nslots ? (p.cur_slot0 + t.b) % p.nslots : t.b;
                     mbar_expect_tx(&full[s], PBW * PBH + CBW * CBH);
                     tma_load_3d(sPrev[s], &maps.prev, t.pad[0], t.pad[1], t.zp, &full[s]);
@@ -412,31 +433,52 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
     }
 
     // ---- consumers ----------------------------------------------------------------------------------------------------------
+    // One CTA barrier per tile: phase 1 of tile i fills Wp[i & 1]; after the barrier the first TH threads erode + dilate it into
+    // Dp[i & 1] while everybody expands and stores tile i - 1 from Dp[(i - 1) & 1] (finished before the barrier).
     const int tid = threadIdx.x, warp = tid >> 5;
     int local = 0;
     int it = 0;
+    int ptx0 = 0, pty0 = 0, pb = -1;                  // the tile whose bit planes wait in Dp for phase 3
+    // phase 3: bits -> bytes, coalesced 32-bit stores.  Lane l owns the 4-pixel run at bit l of the four planes: rotating a plane so
+    // that the bit becomes the sign bit of byte 0 lets PRMT's sign replication write 0x00 / 0xff.
+    const int rot = (lane - 7) & 31;
+    auto phase3 = [&](const uint4 *D, int tx0, int ty0, int b) {
+        if (lane < 1 || lane > TW / 4) return;
+        const int x = tx0 - 4 + 4 * lane;
+        if (x >= w) return;
+        uint8_t *dst = p.mask + (size_t)b * p.mask_stride + (size_t)(ty0 + warp) * p.mask_pitch + x;
+        const size_t step = (size_t)(NCONS / 32) * p.mask_pitch;
+        const int nrow = min(TH, h - ty0);
+        for (int ry = warp; ry < nrow; ry += NCONS / 32, dst += step) {
+            const uint4 d = D[ry + 2];
+            const uint32_t r0 = __funnelshift_r(d.x, d.x, rot), r1 = __funnelshift_r(d.y, d.y, rot);
+            const uint32_t r2 = __funnelshift_r(d.z, d.z, rot), r3 = __funnelshift_r(d.w, d.w, rot);
+            const uint32_t o = prmt(prmt(r0, r1, 0x00c8u), prmt(r2, r3, 0x00c8u), 0x5410u);
+            if (ALIGNED && x + 3 < w) *reinterpret_cast<uint32_t *>(dst) = o;
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (x + j < w) dst[j] = (uint8_t)(o >> (8 * j));
+            }
+        }
+    };
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
         const int s = it % NSTAGE;
         mbar_wait(&full[s], (it / NSTAGE) & 1);
         const MaskTile &t = sT[s];
         const int tx0 = t.tx0, ty0 = t.ty0, b = t.b, mode = t.mode;
-        uint8_t *out = p.mask + (size_t)b * p.mask_stride;
-        if (mode == 2) {
-            // no egomotion (fewer than the minimal number of vectors): empty mask
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            for (int i = tid; i < TW * TH; i += NCONS) {
-                int x = tx0 + i % TW, y = ty0 + i / TW;
-                if (x < w && y < h) out[(size_t)y * p.mask_pitch + x] = 0;
-            }
-            continue;
-        }
-        const uint8_t *prev = p.prev + (long long)t.zp * p.stride;
+        uint4 *W = Wp[it & 1], *D = Dp[it & 1];
         const uint32_t ci0 = t.colin[0], ci1 = t.colin[1], ci2 = t.colin[2], ci3 = t.colin[3];
-        if (mode == 1) {
-            mask_phase1_fast(p, t, smem_u32(&t), smem_u32(sPrev[s]), smem_u32(sCur[s]), Wp, prev, bw0, warp, lane);
+        if (mode == 2) {
+            // no egomotion (fewer than the minimal number of vectors): empty mask (all-zero planes, stored like any other tile)
+            if (tid < TR) W[tid] = make_uint4(0u, 0u, 0u, 0u);
+        } else if (mode == 1 || mode == 3) {
+            const uint8_t *prev = p.prev + (long long)t.zp * p.stride;
+            if (mode == 3) mask_phase1_fast<1>(p, t, smem_u32(&t), smem_u32(sPrev[s]), smem_u32(sCur[s]), W, prev, bw0, warp, lane);
+            else mask_phase1_fast<3>(p, t, smem_u32(&t), smem_u32(sPrev[s]), smem_u32(sCur[s]), W, prev, bw0, warp, lane);
         } else {
             // ---- phase 1 (gather): per-pixel loads through L2, reference operation sequence with the Newton shortcut ---------
+            const uint8_t *prev = p.prev + (long long)t.zp * p.stride;
             const double *sM = t.M;
             const ThreshConst tc = thresh_const(p.thresh);
             const uint8_t *cur = p.cur + (long long)(p.nslots ? (p.cur_slot0 + b) % p.nslots : b) * p.stride;
@@ -484,22 +526,22 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
                 }
                 const uint32_t w0 = __ballot_sync(0xffffffffu, mot[0]), w1 = __ballot_sync(0xffffffffu, mot[1]);
                 const uint32_t w2 = __ballot_sync(0xffffffffu, mot[2]), w3 = __ballot_sync(0xffffffffu, mot[3]);
-                if (lane == 0) Wp[ry] = make_uint4(w0 | ~ci0, w1 | ~ci1, w2 | ~ci2, w3 | ~ci3);
+                if (lane == 0) W[ry] = make_uint4(w0 | ~ci0, w1 | ~ci1, w2 | ~ci2, w3 | ~ci3);
             }
         }
         consumer_sync();
         // the staged boxes and the tile record are consumed: hand the stage back to the producer
-        // (the tile's scalars were copied to registers above; phases 2 and 3 only touch Wp / Dp)
+        // (the tile's scalars were copied to registers above; phases 2 and 3 only touch the bit planes)
         if (lane == 0) mbar_arrive(&empty[s]);
 
         // ---- phase 2: erode then dilate on the bit planes; one thread per output row of the tile --------------------------------
         if (tid < TH) {
             const int r = tid + 2;                              // row of the computed region
             uint4 o;
-            if (p.morph) {
+            if (p.morph && mode != 2) {
                 uint4 hx[5];
 #pragma unroll
-                for (int k = 0; k < 5; k++) hx[k] = morph_row_x<true>(Wp[r - 2 + k]);
+                for (int k = 0; k < 5; k++) hx[k] = morph_row_x<true>(W[r - 2 + k]);
                 uint4 e[3];
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
@@ -513,33 +555,18 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
                 }
                 const uint4 d0 = morph_row_x<false>(e[0]), d1 = morph_row_x<false>(e[1]), d2 = morph_row_x<false>(e[2]);
                 o = make_uint4(d0.x | d1.x | d2.x, d0.y | d1.y | d2.y, d0.z | d1.z | d2.z, d0.w | d1.w | d2.w);
-            } else o = Wp[r];
+            } else o = W[r];
             // only the tile's own columns (lanes 1 .. 30) inside the image count and are stored
             o.x &= ci0 & 0x7ffffffeu; o.y &= ci1 & 0x7ffffffeu; o.z &= ci2 & 0x7ffffffeu; o.w &= ci3 & 0x7ffffffeu;
-            Dp[r] = o;
+            D[r] = o;
             if (ty0 + tid < h) local += __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
         }
-        consumer_sync();
-        // ---- phase 3: bits -> bytes, coalesced 32-bit stores ---------------------------------------------------------------------
-        if (lane >= 1 && lane <= TW / 4) {
-            const int x = tx0 - 4 + 4 * lane;
-            for (int ry = warp; ry < TH; ry += NCONS / 32) {
-                const int y = ty0 + ry;
-                if (x >= w || y >= h) continue;
-                const uint4 d = Dp[ry + 2];
-                const uint32_t o = (((d.x >> lane) & 1u) | (((d.y >> lane) & 1u) << 8) | (((d.z >> lane) & 1u) << 16) | (((d.w >> lane) & 1u) << 24)) * 255u;
-                uint8_t *dst = out + (size_t)y * p.mask_pitch + x;
-                if (ALIGNED && x + 3 < w) *reinterpret_cast<uint32_t *>(dst) = o;
-                else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++)
-                        if (x + j < w) dst[j] = (uint8_t)(o >> (8 * j));
-                }
-            }
-        }
-        // Wp is rewritten by the next tile's phase 1 only after every consumer passed the barrier above (phase 2 is done); Dp is
-        // rewritten by the next tile's phase 2, which sits behind the next tile's first barrier
+        // ---- phase 3 of the PREVIOUS tile (its planes were finished before the barrier above) -------------------------------------
+        if (pb >= 0) phase3(Dp[(it - 1) & 1], ptx0, pty0, pb);
+        ptx0 = tx0; pty0 = ty0; pb = b;
     }
+    consumer_sync();
+    if (pb >= 0) phase3(Dp[(it - 1) & 1], ptx0, pty0, pb);
     if (p.stat_mask) {
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
         if (lane == 0 && local) atomicAdd(p.stat_mask, (unsigned long long)local);

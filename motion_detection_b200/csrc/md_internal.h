@@ -125,7 +125,7 @@ struct EgoParams {
 };
 
 // K4 TMA boxes: the source bounding box of a 128 x 40 computed region in `prev` (16-byte aligned start: up to 15 columns of slack)
-#define MD_MASK_PREV_BOX_W 176
+#define MD_MASK_PREV_BOX_W 256
 #define MD_MASK_PREV_BOX_H 48
 struct alignas(64) MaskTmaMaps {
     CUtensorMap prev, cur;   // u8, dims (x, y, frame) over the image INTERIOR: out-of-image elements are zero-filled
