@@ -182,6 +182,24 @@ __device__ __forceinline__ double lds_f64(uint32_t addr)
     asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
+// A fast-path pixel that sits on a rounding boundary: the reference's exact coordinates; the four taps from the staged box when
+// the footprint lies inside it (always, short of a pixel outside the image), else bounds-checked through L2.
+__device__ __noinline__ int redo_pixel(const uint8_t *__restrict__ prev, int pitch, int w, int h, const MaskTile &t, int bw0, int xj, int y,
+                                       uint32_t aPrev)
+{
+    int X, Y;
+    exact_xy(t.M, bw0, xj, y, X, Y);
+    const int lx = (X >> 5) - t.pad[0], ly = (Y >> 5) - t.pad[1];
+    if ((unsigned)lx < (unsigned)(PBW - 1) && (unsigned)ly < (unsigned)(PBH - 1)) {
+        const uint32_t r = aPrev + ly * PBW + lx;
+        const int ax = X & 31, ay = Y & 31;
+        const int p00 = lds_u8(r), p01 = lds_u8(r + 1), p10 = lds_u8(r + PBW), p11 = lds_u8(r + PBW + 1);
+        const int h0 = (p00 << 5) + ax * (p01 - p00), h1 = (p10 << 5) + ax * (p11 - p10);
+        return ((h0 << 5) + ay * (h1 - h0) + 512) >> 10;
+    }
+    return bilinear_fetch(prev, pitch, w, h, X, Y);
+}
+
 // prmt.b32 with the full selector semantics (bit 3 of a selector nibble replicates the sign bit of the chosen byte; __byte_perm
 // only looks at the low three bits)
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
@@ -204,6 +222,20 @@ __device__ __forceinline__ ThreshConst thresh_const(int thresh)
     t.kt = 512 + thr * 1024;
     t.lim = thresh < 0 ? 0u : (uint32_t)(2 * thr + 1) * 1024u;
     return t;
+}
+
+// one row of three-neighbour AND (erode) / OR (dilate) along x on the interleaved planes: pixel 4 l + j has its left
+// neighbour in plane j - 1 (plane 3 of lane l - 1 for j = 0) and its right neighbour in plane j + 1 (plane 0 of lane l + 1)
+template <bool AND>
+__device__ __forceinline__ uint4 morph_row_x(const uint4 v)
+{
+    uint4 r;
+    if (AND) {
+        r.x = v.x & (v.w << 1 | 1u) & v.y; r.y = v.y & v.x & v.z; r.z = v.z & v.y & v.w; r.w = v.w & v.z & (v.x >> 1 | 0x80000000u);
+    } else {
+        r.x = v.x | (v.w << 1) | v.y; r.y = v.y | v.x | v.z; r.z = v.z | v.y | v.w; r.w = v.w | v.z | (v.x >> 1);
+    }
+    return r;
 }
 
 // ---- phase 1 (fast): one row of the computed region per warp-iteration, a run of 4 pixels per lane -----------------------------
@@ -262,20 +294,22 @@ __device__ __forceinline__ void mask_phase1_fast(const MaskParams &p, const Mask
         uint32_t gmin = min3_u16x2(min3_u16x2(dist[0], dist[1], dist[2]), dist[3], 0xffffffffu);
         gmin = min(gmin & 0xffffu, gmin >> 16);     // smallest distance (in 2^-KB units, offset by two) of a coordinate to a rounding boundary
         if (gmin <= MASK_GUARD) {
-            // rare: a coordinate of the run sits on a rounding boundary:
-            // redo the run with the reference's exact operation sequence and bounds-checked fetches through L2
-            if (y >= 0 && y < h)
-                for (int j = 0; j < 4; j++)
-                    if (x + j >= 0 && x + j < w) {
-                        const int wv = slow_pixel(prev, p.pitch, w, h, sT.M, bw0, x + j, y);
-                        vp[j] = (wv - (int)((c4 >> (8 * j)) & 0xffu)) * 1024 + tc.kt;
-                    }
+            // rare (1.5e-4 of the pixels): a coordinate sits within the guard band of a rounding boundary -> that pixel is redone
+            // with the reference's exact operation sequence (its taps come from the staged box when they lie inside it)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (min(dist[j] & 0xffffu, dist[j] >> 16) <= MASK_GUARD)
+                    vp[j] = (redo_pixel(prev, p.pitch, w, h, sT, bw0, x + j, y, aPrev) - (int)((c4 >> (8 * j)) & 0xffu)) * 1024 + tc.kt;
         }
         // the row as four bit planes; pixels outside the image are the erode identity (1)
         uint32_t w0 = __ballot_sync(0xffffffffu, (uint32_t)vp[0] >= tc.lim), w1 = __ballot_sync(0xffffffffu, (uint32_t)vp[1] >= tc.lim);
         uint32_t w2 = __ballot_sync(0xffffffffu, (uint32_t)vp[2] >= tc.lim), w3 = __ballot_sync(0xffffffffu, (uint32_t)vp[3] >= tc.lim);
         if (y < 0 || y >= h) w0 = w1 = w2 = w3 = 0xffffffffu;
-        if (lane == 0) Wp[ry] = make_uint4(w0 | ~ci0, w1 | ~ci1, w2 | ~ci2, w3 | ~ci3);
+        if (lane == 0) {
+            // the erode's pass along x happens here, on the row's four words (phase 2 only combines rows)
+            const uint4 row = make_uint4(w0 | ~ci0, w1 | ~ci1, w2 | ~ci2, w3 | ~ci3);
+            Wp[ry] = p.morph ? morph_row_x<true>(row) : row;
+        }
     }
 }
 
@@ -311,15 +345,21 @@ __device__ __forceinline__ void mask_tile_setup(const MaskParams &p, MaskTile &t
     int fast = p.use_tma && !novalid;
     // corners of the computed region (not clamped to the image: pixels outside it are computed and discarded)
     const int x0 = tx0 - 4, x1 = tx0 + CW - 5, y0 = ty0 - 2, y1 = ty0 + TH + 1;
-    double lo_x = 1e300, hi_x = -1e300, lo_y = 1e300, hi_y = -1e300, dmin = 1e300, dmax = -1e300;
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
+    // the four corners on lanes 0-3 (one division each instead of four in a row), min / max by shuffles
+    double lo_x, hi_x, lo_y, hi_y, dmin, dmax;
+    {
+        const int c = lane & 3;
         const double cx = (double)((c & 1) ? x1 : x0), cy = (double)((c & 2) ? y1 : y0);
         const double den = fma(M[6], cx, fma(M[7], cy, M[8]));
         const double rr = 1.0 / den;
         const double sx = fma(M[0], cx, fma(M[1], cy, M[2])) * rr, sy = fma(M[3], cx, fma(M[4], cy, M[5])) * rr;
-        lo_x = fmin(lo_x, sx); hi_x = fmax(hi_x, sx); lo_y = fmin(lo_y, sy); hi_y = fmax(hi_y, sy);
-        dmin = fmin(dmin, den); dmax = fmax(dmax, den);
+        lo_x = hi_x = sx; lo_y = hi_y = sy; dmin = dmax = den;
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            lo_x = fmin(lo_x, __shfl_xor_sync(0xffffffffu, lo_x, o)); hi_x = fmax(hi_x, __shfl_xor_sync(0xffffffffu, hi_x, o));
+            lo_y = fmin(lo_y, __shfl_xor_sync(0xffffffffu, lo_y, o)); hi_y = fmax(hi_y, __shfl_xor_sync(0xffffffffu, hi_y, o));
+            dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o)); dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+        }
     }
     // one sign, away from zero, finite; |32 * coordinate * 2^KB| stays far below the 2^51 the fixed point holds
     if (!(dmin * dmax > 0.0) || !(fmin(fabs(dmin), fabs(dmax)) > 1e-9) || !(lo_x > -1e6 && hi_x < 1e6 && lo_y > -1e6 && hi_y < 1e6)) fast = 0;
@@ -351,11 +391,12 @@ __device__ __forceinline__ void mask_tile_setup(const MaskParams &p, MaskTile &t
         t.rowE[ry] = fma(-fma(M[7], yd, M[8]), rc, 1.0);
     }
     if (lane < 4) {
+        // plane `lane`, bit l: column x0 + 4 l + lane inside [0, w)  <=>  l in [lmin, lmax]
+        const int xs = x0 + lane;
+        const int lmin = xs >= 0 ? 0 : (-xs + 3) >> 2;
+        const int lmax = min(31, (w - 1 - xs) >> 2);              // arithmetic shift: negative when the plane starts beyond the image
         uint32_t m = 0;
-        for (int l = 0; l < 32; l++) {
-            const int xx = x0 + 4 * l + lane;
-            if (xx >= 0 && xx < w) m |= 1u << l;
-        }
+        if (lmax >= lmin) m = (0xffffffffu >> (31 - lmax)) & (0xffffffffu << lmin);
         t.colin[lane] = m;
     }
     if (lane == 0) {
@@ -371,20 +412,6 @@ __device__ __forceinline__ void mask_tile_setup(const MaskParams &p, MaskTile &t
         t.pad[0] = bxs; t.pad[1] = bys;
     }
     __syncwarp();
-}
-
-// one row of three-neighbour AND (erode) / OR (dilate) along x on the interleaved planes: pixel 4 l + j has its left
-// neighbour in plane j - 1 (plane 3 of lane l - 1 for j = 0) and its right neighbour in plane j + 1 (plane 0 of lane l + 1)
-template <bool AND>
-__device__ __forceinline__ uint4 morph_row_x(const uint4 v)
-{
-    uint4 r;
-    if (AND) {
-        r.x = v.x & (v.w << 1 | 1u) & v.y; r.y = v.y & v.x & v.z; r.z = v.z & v.y & v.w; r.w = v.w & v.z & (v.x >> 1 | 0x80000000u);
-    } else {
-        r.x = v.x | (v.w << 1) | v.y; r.y = v.y | v.x | v.z; r.z = v.z | v.y | v.w; r.w = v.w | v.z | (v.x >> 1);
-    }
-    return r;
 }
 
 // Persistent, warp-specialised: warp 8 walks the CTA's tiles ahead of the others -- source box, expansion constants, row
@@ -450,15 +477,20 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
         const size_t step = (size_t)(NCONS / 32) * p.mask_pitch;
         const int nrow = min(TH, h - ty0);
         for (int ry = warp; ry < nrow; ry += NCONS / 32, dst += step) {
-            const uint4 d = D[ry + 2];
+            uint4 d = D[ry + 2];
+            if (p.morph) {
+                // the dilate's pass along y
+                const uint4 u = D[ry + 1], v = D[ry + 3];
+                d.x |= u.x | v.x; d.y |= u.y | v.y; d.z |= u.z | v.z; d.w |= u.w | v.w;
+            }
             const uint32_t r0 = __funnelshift_r(d.x, d.x, rot), r1 = __funnelshift_r(d.y, d.y, rot);
             const uint32_t r2 = __funnelshift_r(d.z, d.z, rot), r3 = __funnelshift_r(d.w, d.w, rot);
             const uint32_t o = prmt(prmt(r0, r1, 0x00c8u), prmt(r2, r3, 0x00c8u), 0x5410u);
-            if (ALIGNED && x + 3 < w) *reinterpret_cast<uint32_t *>(dst) = o;
+            if (ALIGNED && x + 3 < w) { *reinterpret_cast<uint32_t *>(dst) = o; local += __popc(o); }
             else {
 #pragma unroll
                 for (int j = 0; j < 4; j++)
-                    if (x + j < w) dst[j] = (uint8_t)(o >> (8 * j));
+                    if (x + j < w) { dst[j] = (uint8_t)(o >> (8 * j)); local += __popc((o >> (8 * j)) & 0xffu); }
             }
         }
     };
@@ -526,7 +558,10 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
                 }
                 const uint32_t w0 = __ballot_sync(0xffffffffu, mot[0]), w1 = __ballot_sync(0xffffffffu, mot[1]);
                 const uint32_t w2 = __ballot_sync(0xffffffffu, mot[2]), w3 = __ballot_sync(0xffffffffu, mot[3]);
-                if (lane == 0) W[ry] = make_uint4(w0 | ~ci0, w1 | ~ci1, w2 | ~ci2, w3 | ~ci3);
+                if (lane == 0) {
+                    const uint4 row = make_uint4(w0 | ~ci0, w1 | ~ci1, w2 | ~ci2, w3 | ~ci3);
+                    W[ry] = p.morph ? morph_row_x<true>(row) : row;
+                }
             }
         }
         consumer_sync();
@@ -534,32 +569,24 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
         // (the tile's scalars were copied to registers above; phases 2 and 3 only touch the bit planes)
         if (lane == 0) mbar_arrive(&empty[s]);
 
-        // ---- phase 2: erode then dilate on the bit planes; one thread per output row of the tile --------------------------------
-        if (tid < TH) {
-            const int r = tid + 2;                              // row of the computed region
+        // ---- phase 2: the erode's pass along y, then the dilate's pass along x; one thread per row (rows 1 .. TR - 2), on the two
+        // warps that own one row less of phase 3 ---------------------------------------------------------------------------------
+        if (tid >= 4 * 32 && tid < 4 * 32 + TR - 2) {
+            const int r = tid - 4 * 32 + 1;                     // row of the computed region
             uint4 o;
             if (p.morph && mode != 2) {
-                uint4 hx[5];
-#pragma unroll
-                for (int k = 0; k < 5; k++) hx[k] = morph_row_x<true>(W[r - 2 + k]);
-                uint4 e[3];
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    // eroded row r - 1 + k; outside the image it is the dilate identity (0)
-                    const int y = ty0 - 2 + r - 1 + k;
-                    const bool in = y >= 0 && y < h;
-                    e[k].x = in ? (hx[k].x & hx[k + 1].x & hx[k + 2].x & ci0) : 0u;
-                    e[k].y = in ? (hx[k].y & hx[k + 1].y & hx[k + 2].y & ci1) : 0u;
-                    e[k].z = in ? (hx[k].z & hx[k + 1].z & hx[k + 2].z & ci2) : 0u;
-                    e[k].w = in ? (hx[k].w & hx[k + 1].w & hx[k + 2].w & ci3) : 0u;
-                }
-                const uint4 d0 = morph_row_x<false>(e[0]), d1 = morph_row_x<false>(e[1]), d2 = morph_row_x<false>(e[2]);
-                o = make_uint4(d0.x | d1.x | d2.x, d0.y | d1.y | d2.y, d0.z | d1.z | d2.z, d0.w | d1.w | d2.w);
+                const uint4 a0 = W[r - 1], a1 = W[r], a2 = W[r + 1];
+                // eroded row r; outside the image it is the dilate identity (0)
+                const int y = ty0 - 2 + r;
+                const bool in = y >= 0 && y < h;
+                uint4 e;
+                e.x = in ? (a0.x & a1.x & a2.x & ci0) : 0u; e.y = in ? (a0.y & a1.y & a2.y & ci1) : 0u;
+                e.z = in ? (a0.z & a1.z & a2.z & ci2) : 0u; e.w = in ? (a0.w & a1.w & a2.w & ci3) : 0u;
+                o = morph_row_x<false>(e);
             } else o = W[r];
-            // only the tile's own columns (lanes 1 .. 30) inside the image count and are stored
-            o.x &= ci0 & 0x7ffffffeu; o.y &= ci1 & 0x7ffffffeu; o.z &= ci2 & 0x7ffffffeu; o.w &= ci3 & 0x7ffffffeu;
+            // only columns inside the image count and are stored
+            o.x &= ci0; o.y &= ci1; o.z &= ci2; o.w &= ci3;
             D[r] = o;
-            if (ty0 + tid < h) local += __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
         }
         // ---- phase 3 of the PREVIOUS tile (its planes were finished before the barrier above) -------------------------------------
         if (pb >= 0) phase3(Dp[(it - 1) & 1], ptx0, pty0, pb);
@@ -569,7 +596,7 @@ __global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, cons
     if (pb >= 0) phase3(Dp[(it - 1) & 1], ptx0, pty0, pb);
     if (p.stat_mask) {
         for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-        if (lane == 0 && local) atomicAdd(p.stat_mask, (unsigned long long)local);
+        if (lane == 0 && local) atomicAdd(p.stat_mask, (unsigned long long)(local >> 3));     // eight set bits per 0xff byte
     }
 }
 
