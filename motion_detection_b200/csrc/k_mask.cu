@@ -48,6 +48,9 @@
 #define PBH MD_MASK_PREV_BOX_H
 #define NCONS 256            // consumer threads (8 warps); warp 8 is the producer
 #define NSTAGE 2             // stages of the box ring
+#ifndef MASK_CTAS_PER_SM
+#define MASK_CTAS_PER_SM 3     // persistent CTAs per SM (register bound: 72 registers x 288 threads)
+#endif
 #define PREV_STAGE (PBW * PBH)
 #define PREV_AMAX (PBW * PBH - PBW - 2)      // largest index whose 2 x 2 footprint stays inside the staged box
 static_assert(PBW == 256, "the sample address is (row byte, column byte) of the fixed-point coordinates: the box pitch is 256");
@@ -418,7 +421,7 @@ __device__ __forceinline__ void mask_tile_setup(const MaskParams &p, MaskTile &t
 // tables, two TMA box loads per tile into a two-stage ring guarded by full / empty mbarriers -- while warps 0-7 sample and
 // threshold the tile that has landed (phase 1), erode + dilate it on bit planes (phase 2) and expand / store it (phase 3).
 template <bool ALIGNED>
-__global__ void __launch_bounds__(NCONS + 32, 3) k_mask(const MaskParams p, const __grid_constant__ MaskKernelMaps maps, int ntx, int nty,
+__global__ void __launch_bounds__(NCONS + 32, MASK_CTAS_PER_SM) k_mask(const MaskParams p, const __grid_constant__ MaskKernelMaps maps, int ntx, int nty,
                                                         int ntiles)
 {
     __shared__ __align__(128) uint8_t sPrev[NSTAGE][PREV_STAGE];
@@ -626,10 +629,10 @@ cudaError_t launch_mask(const MaskParams &p0, int pairs, const MaskTmaMaps *maps
     const int ntx = (p.w + TW - 1) / TW, nty = (p.h + TH - 1) / TH;
     const long long nt = (long long)ntx * nty * pairs;
     if (nt > 0x7fffffff) return cudaErrorInvalidValue;
-    // persistent CTAs: 3 per SM (register bound), every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+    // persistent CTAs: MASK_CTAS_PER_SM per SM (register bound), every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms < 1) sms = 148; }
-    const int grid = (int)(nt < (long long)sms * 3 ? nt : (long long)sms * 3);
+    const int grid = (int)(nt < (long long)sms * MASK_CTAS_PER_SM ? nt : (long long)sms * MASK_CTAS_PER_SM);
     if (aligned) k_mask<true><<<grid, NCONS + 32, 0, s>>>(p, km, ntx, nty, (int)nt);
     else k_mask<false><<<grid, NCONS + 32, 0, s>>>(p, km, ntx, nty, (int)nt);
     MD_COUNT_LAUNCH(1);
