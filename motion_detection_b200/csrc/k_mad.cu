@@ -167,6 +167,7 @@ void mad_free_workspace(void *w)
 extern "C" int md_find_outliers(md_ctx *ctx, const double *flow_dxdy, int32_t n, int32_t include_zeros, uint8_t *outlier,
                                 double *stats4, int mem)
 {
+    MD_NVTX("md_find_outliers");
     if (!ctx) return MD_ERR_INVALID;
     if (!flow_dxdy || !outlier || n < 1 || n > (1 << 26)) { ctx->err = "md_find_outliers: bad arguments"; return MD_ERR_INVALID; }
     if (cudaSetDevice(ctx->device) != cudaSuccess) return MD_ERR_CUDA;

@@ -353,6 +353,7 @@ extern "C" int md_fit_subspace(md_ctx *ctx, const float *traj, int32_t T, int32_
                                uint32_t seed, const int32_t *forced_cols, int32_t iters, float *residual, int32_t *best_cols,
                                uint8_t *outlier, int32_t *num_inliers, int mem)
 {
+    MD_NVTX("md_fit_subspace");
     if (!ctx) return MD_ERR_INVALID;
     const int n = 2 * F, d = 4 * num_motions;
     if (!traj || !residual || !best_cols || !outlier || T < 1 || F < 1 || n > SUB_MAXN || d < 1 || d > SUB_MAXN || d > n ||

@@ -495,6 +495,7 @@ static void fill_lk(md_ctx *ctx, LkParams &p, int prev_slot0, int next_slot0, co
 extern "C" int md_lk_flow(md_ctx *ctx, int slot_prev, int slot_next, const float *pts_in, int32_t npts, float *pts_out,
                           uint8_t *status, int mem)
 {
+    MD_NVTX("md_lk_flow (K2)");
     if (!ctx) return MD_ERR_INVALID;
     if (!pts_out || !status || npts < 1 || (size_t)npts > ctx->pts_cap || slot_prev < 0 || slot_next < 0 ||
         slot_prev >= ctx->g.nslots || slot_next >= ctx->g.nslots || (!pts_in && npts != ctx->P))
@@ -543,6 +544,7 @@ extern "C" int md_fit_egomotion(md_ctx *ctx, const float *src, const float *dst,
                                 int32_t npts, int mode, uint32_t seed, double *H9, int32_t *num_vectors, int32_t *inliers,
                                 uint8_t *inlier_mask, int mem)
 {
+    MD_NVTX("md_fit_egomotion (K3)");
     if (!ctx) return MD_ERR_INVALID;
     if (!src || !dst || (!status && !keep) || npts < 1 || (size_t)npts > ctx->pts_cap || mode < 0 || mode > 2)
         FAIL(MD_ERR_INVALID, "md_fit_egomotion: bad arguments (npts must be <= md_grid_size)");
@@ -593,6 +595,7 @@ static bool invert3_host(const double *S, double *D)
 extern "C" int md_motion_mask(md_ctx *ctx, const uint8_t *prev, const uint8_t *cur, int32_t pitch, const double *H9,
                               int32_t thresh, int32_t morph, uint8_t *mask, int32_t mask_pitch, int mem)
 {
+    MD_NVTX("md_motion_mask (K4)");
     if (!ctx) return MD_ERR_INVALID;
     const int w = ctx->cfg.width, h = ctx->cfg.height;
     if (!prev || !cur || !H9 || !mask || pitch < w || mask_pitch < w) FAIL(MD_ERR_INVALID, "md_motion_mask: bad arguments");
@@ -641,6 +644,7 @@ extern "C" int md_motion_mask(md_ctx *ctx, const uint8_t *prev, const uint8_t *c
 static int run_prep(md_ctx *ctx, int prev0, int p0, int p1, int slot0, int nframes, const uint8_t *frames, int channels, int fpitch,
                     long long fstride, cudaStream_t s)
 {
+    MD_NVTX("K1 pyramid + Scharr + phase planes + window sums");
     const PyrGeom &g = ctx->g;
     const int ns = g.nslots, nl = g.nlev;
     LkParams lp;
@@ -683,6 +687,7 @@ static int run_prep(md_ctx *ctx, int prev0, int p0, int p1, int slot0, int nfram
 // K2 for pairs [p0, p1) of the current batch (pyramids of the frames involved are already built) on stream s
 static int run_flow(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint8_t *d_status, cudaStream_t s, bool planes_done = false)
 {
+    MD_NVTX("K2 optical flow (LK / VarFlow)");
     const int P = ctx->P, ns = ctx->g.nslots, n = p1 - p0;
     if (ctx->cfg.flow_engine == MD_FLOW_VARFLOW) {
         // dense variational flow per pair, sampled at the grid points (the gray frames are the level-0 planes)
@@ -711,7 +716,7 @@ static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
     ep.blockcnt += (size_t)p0 * ep.nblk_scan; ep.kept_idx += (size_t)p0 * P; ep.M += p0;
     ep.hyp += (size_t)p0 * it * 9; ep.hyp_valid += (size_t)p0 * it; ep.counts += (size_t)p0 * it;
     ep.partial += (size_t)p0 * ep.nblk_acc * 24; ep.H += 9 * p0; ep.Hinv += 9 * p0; ep.inliers += p0; ep.valid += p0;
-    CK(launch_ego(ep, n, s));
+    { MD_NVTX("K3 egomotion fit"); CK(launch_ego(ep, n, s)); }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[3], s));
     if (want_mask) {
         MaskParams mp;
@@ -723,6 +728,7 @@ static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
         mp.thresh = ctx->cfg.diff_threshold; mp.morph = ctx->cfg.morph;
         mp.mask = d_mask + (size_t)p0 * mask_stride; mp.mask_pitch = mask_pitch; mp.mask_stride = mask_stride;
         mp.stat_mask = ctx->d_stats;
+        MD_NVTX("K4 warp + diff + threshold + morphology");
         CK(launch_mask(mp, n, &ctx->mask_maps, s));
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->ev[4], s));
@@ -745,6 +751,7 @@ static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
 
 extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outputs *out, int mem)
 {
+    MD_NVTX("md_process_batch");
     if (!ctx) return MD_ERR_INVALID;
     if (!fr || !out || !fr->data || (fr->channels != 1 && fr->channels != 3) || fr->count < 1 ||
         fr->pitch < ctx->cfg.width * fr->channels)
@@ -989,6 +996,7 @@ static int ensure_traj(md_ctx *ctx, int F)
 extern "C" int md_track_trajectories(md_ctx *ctx, const md_frames *fr, float *traj, int32_t *traj_len, float *last_prev,
                                      float *last_next, uint8_t *last_status, int mem)
 {
+    MD_NVTX("md_track_trajectories");
     if (!ctx) return MD_ERR_INVALID;
     if (!fr || !fr->data || !traj || !traj_len || (fr->channels != 1 && fr->channels != 3) || fr->count < 2 ||
         fr->count > ctx->g.nslots || fr->pitch < ctx->cfg.width * fr->channels || fr->chain)
@@ -1070,6 +1078,7 @@ extern "C" int md_window_reset(md_ctx *ctx)
 
 extern "C" int md_window_push(md_ctx *ctx, const uint8_t *frame, int32_t channels, int32_t pitch, int32_t *fill, int mem)
 {
+    MD_NVTX("md_window_push");
     if (!ctx) return MD_ERR_INVALID;
     if (!frame || (channels != 1 && channels != 3) || pitch < ctx->cfg.width * channels) FAIL(MD_ERR_INVALID, "md_window_push: bad frame");
     CK(cudaSetDevice(ctx->device));
@@ -1098,6 +1107,7 @@ static int live_cluster(md_ctx *ctx, LiveWs *ws, const int *n_dev, int n_max, do
 
 extern "C" int md_window_detect(md_ctx *ctx, const md_live_params *lp, md_live_result *res, int mem)
 {
+    MD_NVTX("md_window_detect");
     if (!ctx) return MD_ERR_INVALID;
     if (!lp || !res || lp->num_motions < 1) FAIL(MD_ERR_INVALID, "md_window_detect: bad arguments");
     const int F = 2 * lp->num_motions + 1, P = ctx->P, ns = ctx->g.nslots;

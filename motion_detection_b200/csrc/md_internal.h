@@ -223,6 +223,16 @@ cudaError_t vf_sample_grid(md_ctx *ctx, float2 *next, uint8_t *status, cudaStrea
 
 // kernels launched by this library, process wide (md_stats.kernel_launches): contexts may live on different threads
 extern std::atomic<long long> g_md_launches;
+// NVTX ranges (tracing): one host-side range per stage of the chain and per entry point; free when no tool is attached
+#include <nvtx3/nvToolsExt.h>
+struct MdNvtxRange {
+    explicit MdNvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~MdNvtxRange() { nvtxRangePop(); }
+};
+#define MD_NVTX_CAT2(a, b) a##b
+#define MD_NVTX_CAT(a, b) MD_NVTX_CAT2(a, b)
+#define MD_NVTX(name) MdNvtxRange MD_NVTX_CAT(md_nvtx_range_, __LINE__)(name)
+
 #define MD_COUNT_LAUNCH(n) (g_md_launches.fetch_add((n), std::memory_order_relaxed))
 
 // kernel launchers (each in its own .cu)
