@@ -341,9 +341,9 @@ SECONDARY = [
     ("c3_4k_lk", "configs[2] with the LK engine: 3840x2160, 6 pyramid levels", ["--width", "3840", "--height", "2160", "--batch", "8",
                                                                                 "--steps", "6", "--warmup", "3", "--cpu-baseline-seconds", "4"]),
     ("c3_4k_varflow", "configs[2] as written: 3840x2160, dense variational flow (VarFlow, max_level 4) + homography egomotion",
-     ["--width", "3840", "--height", "2160", "--flow-engine", "varflow", "--batch", "2", "--steps", "3", "--warmup", "3",
+     ["--width", "3840", "--height", "2160", "--flow-engine", "varflow", "--batch", "8", "--steps", "3", "--warmup", "3",
       "--cpu-baseline-seconds", "1"]),
-    ("varflow_1080p", "configs[1] with the dense variational flow engine", ["--flow-engine", "varflow", "--batch", "4", "--steps", "3",
+    ("varflow_1080p", "configs[1] with the dense variational flow engine", ["--flow-engine", "varflow", "--batch", "8", "--steps", "3",
                                                                             "--warmup", "3", "--cpu-baseline-seconds", "1"]),
     ("live_1080p", "configs[4]-style live path: imageCallback (window of 5 frames -> trajectories -> fitSubspace -> clusters)",
      ["--workload", "live", "--batch", "8", "--steps", "4", "--warmup", "3", "--cpu-baseline-seconds", "4"]),

@@ -163,7 +163,12 @@ static void free_ctx(md_ctx *ctx)
                     ctx->d_inliers, ctx->d_valid, ctx->d_hyp, ctx->d_partial, ctx->d_H, ctx->d_Hinv, ctx->d_stats,
                     ctx->d_traj, ctx->d_traj_len, ctx->d_phase, ctx->d_wsum};
     for (void *p : ptrs) if (p) cudaFree(p);
-    vf_free_workspace(ctx->vf_ws);
+    for (int i = 0; i < MD_VF_LANES; i++) {
+        vf_free_workspace(ctx->vf_ws[i]);
+        if (ctx->vf_stream[i]) cudaStreamDestroy(ctx->vf_stream[i]);
+        if (ctx->vf_ev[i]) cudaEventDestroy(ctx->vf_ev[i]);
+    }
+    if (ctx->vf_fork) cudaEventDestroy(ctx->vf_fork);
     sub_free_workspace(ctx->sub_ws);
     mad_free_workspace(ctx->mad_ws);
     live_free(ctx->live_ws);
@@ -690,12 +695,31 @@ static int run_flow(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
     MD_NVTX("K2 optical flow (LK / VarFlow)");
     const int P = ctx->P, ns = ctx->g.nslots, n = p1 - p0;
     if (ctx->cfg.flow_engine == MD_FLOW_VARFLOW) {
-        // dense variational flow per pair, sampled at the grid points (the gray frames are the level-0 planes)
-        for (int q = p0; q < p1; q++) {
-            const int rc = vf_compute_device(ctx, slot_plane(ctx, (prev0 + q) % ns, 0), slot_plane(ctx, (prev0 + q + 1) % ns, 0), ctx->g.lv[0].pitch);
-            if (rc != MD_OK) return rc;
-            CK(vf_sample_grid(ctx, d_next + (size_t)q * P, d_status + (size_t)q * P, s));
+        // dense variational flow per pair, sampled at the grid points (the gray frames are the level-0 planes).  The pairs are
+        // independent and one pair's wavefront occupies a single 16-CTA cluster, so up to MD_VF_LANES pairs run side by side,
+        // each on its own workspace and stream, forked from / joined into s.
+        const int lanes = n < MD_VF_LANES ? n : MD_VF_LANES;
+        if (lanes > 1) {
+            for (int k = 0; k < lanes; k++) {
+                if (!ctx->vf_stream[k]) CK(cudaStreamCreateWithFlags(&ctx->vf_stream[k], cudaStreamNonBlocking));
+                if (!ctx->vf_ev[k]) CK(cudaEventCreateWithFlags(&ctx->vf_ev[k], cudaEventDisableTiming));
+            }
+            if (!ctx->vf_fork) CK(cudaEventCreateWithFlags(&ctx->vf_fork, cudaEventDisableTiming));
+            CK(cudaEventRecord(ctx->vf_fork, s));
+            for (int k = 0; k < lanes; k++) CK(cudaStreamWaitEvent(ctx->vf_stream[k], ctx->vf_fork, 0));
         }
+        for (int q = p0; q < p1; q++) {
+            const int k = lanes > 1 ? (q - p0) % lanes : 0;
+            cudaStream_t sk = lanes > 1 ? ctx->vf_stream[k] : s;
+            const int rc = vf_compute_device(ctx, k, sk, slot_plane(ctx, (prev0 + q) % ns, 0), slot_plane(ctx, (prev0 + q + 1) % ns, 0), ctx->g.lv[0].pitch);
+            if (rc != MD_OK) return rc;
+            CK(vf_sample_grid(ctx, k, d_next + (size_t)q * P, d_status + (size_t)q * P, sk));
+        }
+        if (lanes > 1)
+            for (int k = 0; k < lanes; k++) {
+                CK(cudaEventRecord(ctx->vf_ev[k], ctx->vf_stream[k]));
+                CK(cudaStreamWaitEvent(s, ctx->vf_ev[k], 0));
+            }
     } else {
         LkParams lp;
         fill_lk(ctx, lp, (prev0 + p0) % ns, (prev0 + p0 + 1) % ns, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P, p0);

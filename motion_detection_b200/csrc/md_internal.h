@@ -206,7 +206,12 @@ struct md_ctx {
     void *sub_ws;         // fitSubspace workspace (k_subspace.cu)
     void *mad_ws;         // findOutliers workspace (k_mad.cu)
     void *live_ws;        // live-path workspace (md_api.cu: md_window_*)
-    void *vf_ws;          // VarFlow workspace (k_varflow.cu), allocated on the first md_varflow call
+    // VarFlow workspaces (k_varflow.cu), allocated on first use.  Slot 0 serves md_varflow; a batch on the variational engine runs
+    // up to MD_VF_LANES pairs at once, each on its own workspace and stream (a pair's Gauss-Seidel wavefront keeps one 16-CTA
+    // cluster busy, a ninth of the GPU)
+    void *vf_ws[8];
+    cudaStream_t vf_stream[8];
+    cudaEvent_t vf_ev[8], vf_fork;
     void *scratch;        // grow-only device scratch of the small host-memory entry points (md_gray_u8, md_cluster_vectors)
     size_t scratch_bytes;
     long long launches;   // kernels launched through this context's calls (md_stats.kernel_launches)
@@ -218,8 +223,9 @@ void sub_free_workspace(void *ws);
 void mad_free_workspace(void *ws);
 int sub_enqueue(md_ctx *ctx, const float *d_traj, int T, int F, int num_motions, double sigma, uint32_t seed,
                 const int32_t *forced_host, int iters, float *d_res, uint8_t *d_out, int *d_best, int *d_ninl);
-int vf_compute_device(md_ctx *ctx, const uint8_t *dA, const uint8_t *dB, int dpitch);
-cudaError_t vf_sample_grid(md_ctx *ctx, float2 *next, uint8_t *status, cudaStream_t s);
+#define MD_VF_LANES 8
+int vf_compute_device(md_ctx *ctx, int lane, cudaStream_t s, const uint8_t *dA, const uint8_t *dB, int dpitch);
+cudaError_t vf_sample_grid(md_ctx *ctx, int lane, float2 *next, uint8_t *status, cudaStream_t s);
 
 // kernels launched by this library, process wide (md_stats.kernel_launches): contexts may live on different threads
 extern std::atomic<long long> g_md_launches;
