@@ -76,7 +76,8 @@ typedef struct md_config {
     int32_t flow_engine;        /* md_flow_engine: which flow feeds the egomotion fit in md_process_batch */
     int32_t vf_grid_barrier;    /* test hook: 1 = run every Gauss-Seidel launch of md_varflow as the cooperative grid with the
                                    counting barrier (the path large levels take by themselves) instead of one cluster */
-    int32_t reserved[6];
+    int32_t cuda_graphs;        /* 1 (default) = md_process_batch captures the DAG of a repeated call into a CUDA graph and replays it */
+    int32_t reserved[5];
 } md_config;
 
 typedef struct md_ctx md_ctx;
@@ -115,6 +116,7 @@ typedef struct md_stats {
     int32_t reserved0;
     int64_t lk_iterations;      /* sum over tracked points and pyramid levels of the LK iterations executed (each = 1600 taps) */
     int64_t lk_levels;          /* sum over tracked points of the pyramid levels whose window was evaluated */
+    int64_t graph_replays;      /* md_process_batch calls served by a captured CUDA graph */
 } md_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------------------- */

@@ -39,7 +39,7 @@ class MdConfig(C.Structure):
         ("ransac_thresh", C.c_double), ("seed", C.c_uint32),
         ("vf_max_level", C.c_int32), ("vf_start_level", C.c_int32), ("vf_n1", C.c_int32), ("vf_n2", C.c_int32),
         ("vf_rho", C.c_float), ("vf_alpha", C.c_float), ("vf_sigma", C.c_float), ("vf_literal", C.c_int32),
-        ("flow_engine", C.c_int32), ("vf_grid_barrier", C.c_int32), ("reserved", C.c_int32 * 6),
+        ("flow_engine", C.c_int32), ("vf_grid_barrier", C.c_int32), ("cuda_graphs", C.c_int32), ("reserved", C.c_int32 * 5),
     ]
 
 
@@ -57,7 +57,7 @@ class MdOutputs(C.Structure):
 class MdStats(C.Structure):
     _fields_ = [("pairs", C.c_int64), ("mask_pixels", C.c_int64), ("tracked", C.c_int64), ("inliers", C.c_int64),
                 ("last_H", C.c_double * 9), ("kernel_launches", C.c_int64), ("device", C.c_int32), ("reserved0", C.c_int32),
-                ("lk_iterations", C.c_int64), ("lk_levels", C.c_int64)]
+                ("lk_iterations", C.c_int64), ("lk_levels", C.c_int64), ("graph_replays", C.c_int64)]
 
 
 class MdLiveParams(C.Structure):
@@ -363,7 +363,7 @@ class Context:
         self._ck(lib().md_stats_get(self._h, C.byref(st)))
         return dict(pairs=st.pairs, mask_pixels=st.mask_pixels, tracked=st.tracked, inliers=st.inliers,
                     last_H=np.array(st.last_H[:]).reshape(3, 3), device=st.device, kernel_launches=st.kernel_launches,
-                    lk_iterations=st.lk_iterations, lk_levels=st.lk_levels)
+                    lk_iterations=st.lk_iterations, lk_levels=st.lk_levels, graph_replays=st.graph_replays)
 
     def profile(self, enable=True):
         self._ck(lib().md_profile(self._h, 1 if enable else 0))

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(64) k_hypotheses(const EgoParams p)
             for (int k = 0; k < 4; k++) s_idx[k] = k;
         } else {
             GlibcRand st;
-            glibc_srand(st, p.seed0 + (uint32_t)b);
+            glibc_srand(st, p.seed0 + (uint32_t)b + (p.pair_ctr ? (uint32_t)*p.pair_ctr : 0u));
             for (int i = 0; i < 310; i++) (void)glibc_rand(st);
             for (int i = 0; i < nh * p.minimal; i++) s_idx[i] = glibc_rand(st) % M;
         }
@@ -492,6 +492,15 @@ cudaError_t launch_traj_step(float2 *pts_cur, const float2 *next, const uint8_t 
                              int P, int F, int w, int h, cudaStream_t s)
 {
     k_traj_step<<<(P + 255) / 256, 256, 0, s>>>(pts_cur, next, status, traj, len, P, F, w, h);
+    MD_COUNT_LAUNCH(1);
+    return cudaGetLastError();
+}
+
+// the context's pair counter lives on the device: bumped at the end of every batch (inside the captured graph as well)
+__global__ void k_advance_pairs(unsigned long long *ctr, int pairs) { *ctr += (unsigned long long)pairs; }
+cudaError_t launch_advance_pairs(unsigned long long *ctr, int pairs, cudaStream_t s)
+{
+    k_advance_pairs<<<1, 1, 0, s>>>(ctr, pairs);
     MD_COUNT_LAUNCH(1);
     return cudaGetLastError();
 }

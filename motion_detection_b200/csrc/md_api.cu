@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "md_internal.h"
 #include "tma.h"
@@ -50,6 +51,7 @@ extern "C" int md_config_default(md_config *c)
     c->vf_max_level = 4; c->vf_start_level = 0; c->vf_n1 = 2; c->vf_n2 = 2;      // cpp:422-425
     c->vf_rho = 2.8f; c->vf_alpha = 1400.f; c->vf_sigma = 1.5f;                  // cpp:427-429
     c->vf_literal = 1;
+    c->cuda_graphs = 1;
     return MD_OK;
 }
 
@@ -153,6 +155,8 @@ static int ensure_scratch(md_ctx *ctx, size_t bytes)
     return MD_OK;
 }
 
+static void graphs_free(void *p);
+
 static void free_ctx(md_ctx *ctx)
 {
     if (!ctx) return;
@@ -161,7 +165,8 @@ static void free_ctx(md_ctx *ctx)
     void *ptrs[] = {ctx->d_img, ctx->d_der, ctx->d_frames, ctx->d_mask, ctx->d_pts_in, ctx->d_next, ctx->d_status, ctx->d_keep,
                     ctx->d_inlier_mask, ctx->d_blockcnt, ctx->d_kept_idx, ctx->d_M, ctx->d_hyp_valid, ctx->d_counts,
                     ctx->d_inliers, ctx->d_valid, ctx->d_hyp, ctx->d_partial, ctx->d_H, ctx->d_Hinv, ctx->d_stats,
-                    ctx->d_traj, ctx->d_traj_len, ctx->d_phase, ctx->d_wsum};
+                    ctx->d_traj, ctx->d_traj_len, ctx->d_phase, ctx->d_wsum, ctx->d_pair_ctr};
+    graphs_free(ctx->graphs);
     for (void *p : ptrs) if (p) cudaFree(p);
     for (int i = 0; i < MD_VF_LANES; i++) {
         vf_free_workspace(ctx->vf_ws[i]);
@@ -177,6 +182,7 @@ static void free_ctx(md_ctx *ctx)
     for (int i = 0; i < 8; i++) { if (ctx->ev_k1[i]) cudaEventDestroy(ctx->ev_k1[i]); if (ctx->ev_lk[i]) cudaEventDestroy(ctx->ev_lk[i]); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_out) cudaEventDestroy(ctx->ev_out);
     for (int i = 0; i < 4; i++) if (ctx->ev_lv[i]) cudaEventDestroy(ctx->ev_lv[i]);
     for (int i = 0; i < 2; i++) if (ctx->aux_lv[i]) cudaStreamDestroy(ctx->aux_lv[i]);
     if (ctx->aux_pyr) cudaStreamDestroy(ctx->aux_pyr);
@@ -225,7 +231,8 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
         sok = sok && cudaStreamCreateWithPriority(&ctx->aux_pyr, cudaStreamNonBlocking, hi) == cudaSuccess &&
               cudaStreamCreateWithPriority(&ctx->aux_post, cudaStreamNonBlocking, hi) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming) == cudaSuccess;
     }
     for (int i = 0; i < 8 && sok; i++)
         sok = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
@@ -287,10 +294,12 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
     A((void **)&ctx->d_H, sizeof(double) * 9 * B);
     A((void **)&ctx->d_Hinv, sizeof(double) * 9 * B);
     A((void **)&ctx->d_stats, sizeof(unsigned long long) * 136);
+    A((void **)&ctx->d_pair_ctr, sizeof(unsigned long long));
     if (ok) {
         // derivative planes keep a ZERO frame forever (derivBorder = BORDER_CONSTANT); image frames are rewritten per build
         ok = cudaMemsetAsync(ctx->d_der, 0, g.slot_der_elems * sizeof(short2) * g.nslots, ctx->stream) == cudaSuccess &&
              cudaMemsetAsync(ctx->d_stats, 0, sizeof(unsigned long long) * 136, ctx->stream) == cudaSuccess &&
+             cudaMemsetAsync(ctx->d_pair_ctr, 0, sizeof(unsigned long long), ctx->stream) == cudaSuccess &&
              cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     }
     if (!ok) { free_ctx(ctx); return MD_ERR_NOMEM; }
@@ -325,6 +334,8 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
         ctx->pipe_first = e ? atoi(e) : 0;
         e = getenv("MD_TRACE");
         ctx->trace_calls = e ? atoi(e) : 0;
+        e = getenv("MD_GRAPHS");
+        if (e) ctx->cfg.cuda_graphs = atoi(e) != 0;
     }
     ctx->stats.device = device;
     *out = ctx;
@@ -534,6 +545,7 @@ static void fill_ego(md_ctx *ctx, EgoParams &p, const float2 *pts_in, int P, con
     p.mode = mode; p.iters = ctx->cfg.ransac_iters; p.minimal = mode == MD_EGO_RANSAC_AFFINE ? 3 : 4;
     p.thr2 = ctx->cfg.ransac_thresh * ctx->cfg.ransac_thresh;
     p.seed0 = seed0;
+    p.pair_ctr = nullptr;
     p.w = ctx->cfg.width; p.h = ctx->cfg.height;
     p.nblk_scan = (P + 2047) / 2048;
     p.nblk_acc = (P + 255) / 256 < 64 ? (P + 255) / 256 : 64;
@@ -736,7 +748,8 @@ static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
     const int P = ctx->P, ns = ctx->g.nslots, n = p1 - p0, it = ctx->cfg.ransac_iters;
     EgoParams ep;
     fill_ego(ctx, ep, nullptr, P, d_next + (size_t)p0 * P, d_status + (size_t)p0 * P, d_keep + (size_t)p0 * P, 0, ctx->cfg.ego_mode,
-             ctx->cfg.seed + (uint32_t)ctx->pair_counter + (uint32_t)p0, nullptr, nullptr, nullptr);
+             ctx->cfg.seed + (uint32_t)p0, nullptr, nullptr, nullptr);
+    ep.pair_ctr = ctx->d_pair_ctr;
     ep.blockcnt += (size_t)p0 * ep.nblk_scan; ep.kept_idx += (size_t)p0 * P; ep.M += p0;
     ep.hyp += (size_t)p0 * it * 9; ep.hyp_valid += (size_t)p0 * it; ep.counts += (size_t)p0 * it;
     ep.partial += (size_t)p0 * ep.nblk_acc * 24; ep.H += 9 * p0; ep.Hinv += 9 * p0; ep.inliers += p0; ep.valid += p0;
@@ -773,21 +786,13 @@ static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
 #define MD_PIPE_CHUNKS_DEVICE 2   // device-resident frames: measured 4 193 pairs/s with 2 even chunks, 4 146 with 3, 4 060 with 4, 3 675 with 6
 #define MD_PIPE_CHUNKS 6      // host buffers, 32 pairs: measured e2e 3 297 / 3 750 / 3 906 / 3 953 / 4 003 pairs/s with 3 / 4 / 5 / 6 / 8 chunks; a short first chunk (its K1 / H2D is exposed), even middle chunks, a short last chunk (its K3 / K4 / D2H is)
 
-extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outputs *out, int mem)
+// Enqueues one batch (frames in ring slots prev0 ...) on the context's stream and its side streams; no allocation, no host
+// synchronisation, every side stream joined back into the context's stream: the body can run eagerly or under stream capture.
+static int batch_enqueue(md_ctx *ctx, const md_frames *fr, const md_outputs *out, int mem, int prev0, bool serial)
 {
-    MD_NVTX("md_process_batch");
-    if (!ctx) return MD_ERR_INVALID;
-    if (!fr || !out || !fr->data || (fr->channels != 1 && fr->channels != 3) || fr->count < 1 ||
-        fr->pitch < ctx->cfg.width * fr->channels)
-        FAIL(MD_ERR_INVALID, "md_process_batch: bad frame descriptor");
     const int pairs = fr->chain ? fr->count : fr->count - 1;
-    if (pairs < 1 || pairs > ctx->cfg.max_batch) FAIL(MD_ERR_INVALID, "md_process_batch: pairs must be in [1, max_batch]");
-    if (fr->chain && !ctx->have_cached) FAIL(MD_ERR_STATE, "md_process_batch: chain=1 without a cached previous frame");
-    if (out->mask && out->mask_pitch < ctx->cfg.width) FAIL(MD_ERR_INVALID, "md_process_batch: mask_pitch too small");
-    CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int w = ctx->cfg.width, h = ctx->cfg.height, P = ctx->P, ns = ctx->g.nslots;
-    const int prev0 = ctx->slot_base;
     const int new0 = fr->chain ? (prev0 + 1) % ns : prev0;
     const bool host = mem != MD_MEM_DEVICE;
     const bool want_mask = out->mask != nullptr;
@@ -802,8 +807,6 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
     int mpitch = ctx->fpitch;
     long long mstride = (long long)ctx->fpitch * h;
     if (host) {
-        r = ensure_frames(ctx, fr->channels);
-        if (r != MD_OK) return r;
         df = ctx->d_frames; dp = ctx->fpitch * fr->channels; ds = (long long)dp * h;
     } else {
         if (out->next_pts) d_next = (float2 *)out->next_pts;
@@ -816,7 +819,6 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
     int bounds[12];                   // at most 8 chunks (the per-chunk events)
     int nch = 0;
     bounds[0] = 0;
-    const bool serial = ctx->profile || pairs < 2 || ctx->cfg.flow_engine == MD_FLOW_VARFLOW;
     if (serial) { nch = 1; bounds[1] = pairs; }
     else if (pairs < 8) { nch = 2; bounds[1] = pairs / 2; bounds[2] = pairs; }
     else {
@@ -866,7 +868,7 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
         return MD_OK;
     };
 
-    const bool trace = ctx->trace_calls > 0 && !serial;
+    const bool trace = ctx->trace_calls > 0 && !serial && !ctx->capturing;
     cudaEvent_t tev[8][6];            // per chunk: K1 begin, K1+planes end, LK begin, LK end, post begin, post end
     cudaEvent_t tev0 = nullptr;
     if (trace) {
@@ -879,6 +881,12 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
         CK(cudaEventRecord(ctx->ev_fork, s));
         CK(cudaStreamWaitEvent(s_pyr, ctx->ev_fork, 0));
         CK(cudaStreamWaitEvent(s_post, ctx->ev_fork, 0));
+    }
+    if (host) {
+        // the H2D stream forks from the context's stream as well: the staging buffer may still be read by work queued there, and
+        // under capture every stream of the DAG has to descend from the capturing one
+        if (serial) CK(cudaEventRecord(ctx->ev_fork, s));
+        CK(cudaStreamWaitEvent(ctx->copy_in, ctx->ev_fork, 0));
     }
     int fdone = 0, pprev0 = 0, pprev1 = 0;
     for (int i = 0; i < nch; i++) {
@@ -951,13 +959,152 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
         CK(cudaStreamWaitEvent(ctx->copy_out, ctx->ev_comp[nch - 1], 0));
         r = d2h(pprev0, pprev1);
         if (r != MD_OK) return r;
-        CK(cudaStreamSynchronize(ctx->copy_out));
-        CK(cudaStreamSynchronize(s));
+        // the copies join the context's stream: the caller (md_process_batch) synchronises it once
+        CK(cudaEventRecord(ctx->ev_out, ctx->copy_out));
+        CK(cudaStreamWaitEvent(s, ctx->ev_out, 0));
     } else {
         if (out->num_vectors) CK(cudaMemcpyAsync(out->num_vectors, ctx->d_M, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
         if (out->H) CK(cudaMemcpyAsync(out->H, ctx->d_H, sizeof(double) * 9 * pairs, cudaMemcpyDeviceToDevice, s));
         if (out->inliers) CK(cudaMemcpyAsync(out->inliers, ctx->d_inliers, sizeof(int) * pairs, cudaMemcpyDeviceToDevice, s));
     }
+    CK(launch_advance_pairs(ctx->d_pair_ctr, pairs, s));
+    return MD_OK;
+}
+
+// ---- captured batch graphs ---------------------------------------------------------------------------------------------------
+// A batch is ~60 kernel launches and ~40 event operations over seven streams.  The second time a call with the same buffers,
+// shapes and ring position arrives, its whole DAG is captured (cudaStreamBeginCapture on the context's stream; the side streams
+// join the capture through their event waits) and from then on replayed with ONE cudaGraphLaunch: no per-kernel launch latency
+// between the dependent small kernels at the head and the tail of a batch, no host launch jitter.  What varies from call to call
+// is kept out of the kernel parameters: the ring position is constant (the last frame's pyramid is moved to slot 0 before a
+// chained call), the RANSAC seeds come from the pair counter on the device.
+struct BatchKey {
+    const void *data; int channels, pitch; long long fstride; int count, chain, mem, prev0;
+    const void *o[7]; int mask_pitch; long long mask_stride;
+    const void *stream;
+    bool operator==(const BatchKey &k) const
+    {
+        if (data != k.data || channels != k.channels || pitch != k.pitch || fstride != k.fstride || count != k.count || chain != k.chain ||
+            mem != k.mem || prev0 != k.prev0 || mask_pitch != k.mask_pitch || mask_stride != k.mask_stride || stream != k.stream)
+            return false;
+        for (int i = 0; i < 7; i++) if (o[i] != k.o[i]) return false;
+        return true;
+    }
+};
+struct BatchGraph { BatchKey key; cudaGraphExec_t exec; long long launches; unsigned long long stamp; };
+struct GraphCache {
+    std::vector<BatchKey> seen, failed;      // seen once (eager) / could not be captured (e.g. pageable host buffers): stay eager
+    std::vector<BatchGraph> graphs;
+    unsigned long long clock = 0;
+};
+#define MD_GRAPH_CACHE 16
+
+static void graphs_free(void *p)
+{
+    GraphCache *gc = static_cast<GraphCache *>(p);
+    if (!gc) return;
+    for (auto &g : gc->graphs) cudaGraphExecDestroy(g.exec);
+    delete gc;
+}
+
+extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outputs *out, int mem)
+{
+    MD_NVTX("md_process_batch");
+    if (!ctx) return MD_ERR_INVALID;
+    if (!fr || !out || !fr->data || (fr->channels != 1 && fr->channels != 3) || fr->count < 1 ||
+        fr->pitch < ctx->cfg.width * fr->channels)
+        FAIL(MD_ERR_INVALID, "md_process_batch: bad frame descriptor");
+    const int pairs = fr->chain ? fr->count : fr->count - 1;
+    if (pairs < 1 || pairs > ctx->cfg.max_batch) FAIL(MD_ERR_INVALID, "md_process_batch: pairs must be in [1, max_batch]");
+    if (fr->chain && !ctx->have_cached) FAIL(MD_ERR_STATE, "md_process_batch: chain=1 without a cached previous frame");
+    if (out->mask && out->mask_pitch < ctx->cfg.width) FAIL(MD_ERR_INVALID, "md_process_batch: mask_pitch too small");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int ns = ctx->g.nslots;
+    const bool host = mem != MD_MEM_DEVICE;
+    if (host) { int r0 = ensure_frames(ctx, fr->channels); if (r0 != MD_OK) return r0; }
+    // The ring position is the same for every call: an unchained batch rewrites every slot it uses, a chained one finds the
+    // previous call's last pyramid in slot 0 (two device copies of one slot, ~16 MB at 1080p, when it is not there already).
+    if (fr->chain && ctx->slot_base != 0) {
+        const PyrGeom &g = ctx->g;
+        CK(cudaMemcpyAsync(ctx->d_img, ctx->d_img + (size_t)ctx->slot_base * g.slot_img_bytes, g.slot_img_bytes, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(ctx->d_der, ctx->d_der + (size_t)ctx->slot_base * g.slot_der_elems, g.slot_der_elems * sizeof(short2),
+                           cudaMemcpyDeviceToDevice, s));
+    }
+    const int prev0 = 0;
+    ctx->slot_base = 0;
+    const bool serial = ctx->profile || pairs < 2 || ctx->cfg.flow_engine == MD_FLOW_VARFLOW;
+
+    int r = MD_OK;
+    bool done = false;
+    const bool graph_ok = ctx->cfg.cuda_graphs && !ctx->profile && ctx->trace_calls <= 0 && ctx->cfg.flow_engine != MD_FLOW_VARFLOW;
+    if (graph_ok) {
+        if (!ctx->graphs) ctx->graphs = new (std::nothrow) GraphCache();
+        GraphCache *gc = static_cast<GraphCache *>(ctx->graphs);
+        BatchKey key;
+        memset(&key, 0, sizeof key);
+        key.data = fr->data; key.channels = fr->channels; key.pitch = fr->pitch; key.fstride = fr->frame_stride; key.count = fr->count;
+        key.chain = fr->chain; key.mem = mem; key.prev0 = prev0;
+        key.o[0] = out->next_pts; key.o[1] = out->status; key.o[2] = out->keep; key.o[3] = out->H; key.o[4] = out->num_vectors;
+        key.o[5] = out->inliers; key.o[6] = out->mask; key.mask_pitch = out->mask_pitch; key.mask_stride = out->mask_stride;
+        key.stream = (const void *)s;
+        BatchGraph *hit = nullptr;
+        if (gc) for (auto &g : gc->graphs) if (g.key == key) { hit = &g; break; }
+        if (gc && !hit) {
+            bool seen = false;
+            for (auto &k : gc->seen) if (k == key) { seen = true; break; }
+            bool failed = false;
+            for (auto &k : gc->failed) if (k == key) { failed = true; break; }
+            if (failed) {
+            } else if (!seen) {
+                // first sight of these buffers: run eagerly (this also allocates the phase planes etc. outside any capture)
+                if (gc->seen.size() >= 64) gc->seen.erase(gc->seen.begin());
+                gc->seen.push_back(key);
+            } else {
+                const long long l0 = g_md_launches.load(std::memory_order_relaxed);
+                cudaGraph_t graph = nullptr;
+                cudaGraphExec_t exec = nullptr;
+                if (cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+                    ctx->capturing = 1;
+                    const int rc = batch_enqueue(ctx, fr, out, mem, prev0, serial);
+                    ctx->capturing = 0;
+                    const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+                    if (rc == MD_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                        if (gc->graphs.size() >= MD_GRAPH_CACHE) {
+                            size_t old = 0;
+                            for (size_t i = 1; i < gc->graphs.size(); i++) if (gc->graphs[i].stamp < gc->graphs[old].stamp) old = i;
+                            cudaGraphExecDestroy(gc->graphs[old].exec);
+                            gc->graphs.erase(gc->graphs.begin() + old);
+                        }
+                        BatchGraph bg;
+                        bg.key = key; bg.exec = exec; bg.launches = g_md_launches.load(std::memory_order_relaxed) - l0; bg.stamp = 0;
+                        gc->graphs.push_back(bg);
+                        hit = &gc->graphs.back();
+                    } else {
+                        (void)cudaGetLastError();     // capture failed (pageable host buffers, a foreign capture ...): stay eager
+                        if (exec) cudaGraphExecDestroy(exec);
+                        if (gc->failed.size() >= 64) gc->failed.erase(gc->failed.begin());
+                        gc->failed.push_back(key);
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                    // the launches counted while capturing did not run; the replay below counts them
+                    g_md_launches.fetch_sub(g_md_launches.load(std::memory_order_relaxed) - l0, std::memory_order_relaxed);
+                } else (void)cudaGetLastError();
+            }
+        }
+        if (hit) {
+            hit->stamp = ++gc->clock;
+            CK(cudaGraphLaunch(hit->exec, s));
+            MD_COUNT_LAUNCH(hit->launches);
+            ctx->stats.graph_replays++;
+            done = true;
+        }
+    }
+    if (!done) {
+        r = batch_enqueue(ctx, fr, out, mem, prev0, serial);
+        if (r != MD_OK) return r;
+    }
+    if (host) CK(cudaStreamSynchronize(s));
     ctx->slot_base = (prev0 + pairs) % ns;
     ctx->have_cached = 1;
     ctx->win_fill = 0;               // the ring now belongs to the batch API

@@ -106,7 +106,9 @@ struct EgoParams {
     double min_vec;
     int mode, iters, minimal;
     double thr2;
-    uint32_t seed0;          // pair b uses seed0 + b
+    uint32_t seed0;          // pair b uses seed0 + b (+ *pair_ctr when given: the context's count of pairs processed so far, on the device
+                             // so that a captured graph of the batch replays with fresh seeds)
+    const unsigned long long *pair_ctr;
     int w, h;
     int nblk_scan;           // blocks per pair for keep/compact (2048 items each)
     int nblk_acc;            // blocks per pair for the normal-equation accumulation
@@ -157,7 +159,8 @@ struct md_ctx {
     cudaStream_t copy_in, copy_out;     // H2D / D2H streams of the pipelined host-memory path
     cudaEvent_t ev_in[8], ev_comp[8];
     cudaStream_t aux_pyr, aux_post;     // side streams of the kernel pipeline (K1 / K3+K4 beside LK), higher priority
-    cudaEvent_t ev_k1[8], ev_lk[8], ev_fork, ev_join;
+    cudaEvent_t ev_k1[8], ev_lk[8], ev_fork, ev_join, ev_out;
+    int capturing;                      // batch_enqueue runs under stream capture
     cudaStream_t aux_lv[2];             // level groups of the phase planes / window sums (launch_lk_planes)
     cudaEvent_t ev_lv[4];
     std::string err;
@@ -170,6 +173,8 @@ struct md_ctx {
     int slot_base;        // slot holding frame 0 of the current batch
     int have_cached;      // slot_base holds a valid pyramid of the last frame of the previous batch
     uint64_t pair_counter;
+    unsigned long long *d_pair_ctr;      // device copy of pair_counter (k_hypotheses reads it, k_advance_pairs bumps it)
+    void *graphs;                        // cache of captured batch graphs (md_api.cu)
 
     // staging for host-memory calls / plain frames
     uint8_t *d_frames;    // [(max_batch+1)][h][fpitch*channels], allocated on first host-memory call
@@ -247,6 +252,7 @@ cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot
                            int channels, int fpitch, long long fstride, cudaStream_t s);
 cudaError_t launch_lk(const LkParams &p, const LkTmaMaps *maps, const LkPhaseMaps *pmaps, int pairs, cudaStream_t s);
 cudaError_t launch_ego(const EgoParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_advance_pairs(unsigned long long *ctr, int pairs, cudaStream_t s);
 cudaError_t launch_mask(const MaskParams &p, int pairs, const MaskTmaMaps *maps, cudaStream_t s);
 bool mask_encode_maps(MaskTmaMaps *m, const uint8_t *prev, const uint8_t *cur, int w, int h, int pitch, long long stride, int nframes);
 cudaError_t launch_compact_trajectories(const float2 *traj, const int32_t *len, int P, int F, int *blockcnt, int *idx, int *total,
