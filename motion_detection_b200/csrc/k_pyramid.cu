@@ -2,7 +2,8 @@
 //
 // Replaces cv::cvtColor(CV_BGR2GRAY) (common/src/optical_flow_calculator.cpp:50-51) and
 // cv::buildOpticalFlowPyramid(gray, pyr, Size(40,40), 5, true) (cpp:67,170):
-//   level l+1 = pyrDown(level l): separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8, size (w+1)/2;
+//   level l+1 = pyrDown(level l): separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8, size (w+1)/2
+//   (shared-memory tiled, 16-byte loads);
 //   per level Scharr derivative planes (int16 x2), image planes padded REFLECT_101 by the window size,
 //   derivative planes padded with zeros.
 // Integer arithmetic throughout: results are bit-exact with the CPU oracle.
@@ -68,52 +69,101 @@ __global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ fram
 }
 
 // ---- level l -> l+1: pyrDown straight into the padded plane (frame pixels computed at reflected coordinates) -----
+// One pixel of the padded destination plane at padded coordinates (px, py): the general path (REFLECT_101 frame, ragged edges).
+__device__ __forceinline__ uint32_t pyrdown_px(const uint8_t *sp, int spitch, int ox, int oy)
+{
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint8_t *r = sp + (ptrdiff_t)(2 * oy + j - 2) * spitch + 2 * ox - 2;
+        const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
+        acc += kj * (r[0] + 4 * r[1] + 6 * r[2] + 4 * r[3] + r[4]);
+    }
+    return (uint32_t)((acc + 128) >> 8);
+}
+
+// Shared-memory tiled: a CTA owns a PD_TW x PD_TH tile of the padded destination plane.  Interior tiles (every output inside the
+// level) stage the (2 PD_TW + 3) x (2 PD_TH + 3) source patch with aligned 16-byte loads, run the horizontal [1 4 6 4 1] pass
+// once per source row into 16-bit sums (4 outputs per thread from three 32-bit shared loads), then the vertical pass from 8-byte
+// shared loads with one coalesced 32-bit store per 4 outputs: 4.9 source bytes and ~26 instructions per output instead of 13.75
+// byte loads and ~50.  Tiles that touch the REFLECT_101 frame take the per-pixel path (the source's own frame already holds the
+// reflected taps; the destination's frame pixels are computed at reflected coordinates, no second border pass).
+#define PD_TW 128
+#define PD_TH 16
+#define PD_SW (2 * PD_TW + 32)         // staged source row: 16-byte aligned window around 2 ox0 - 2 .. 2 ox0 + 2 PD_TW + 1
+#define PD_SH (2 * PD_TH + 3)
 __global__ void __launch_bounds__(256) k_pyrdown(uint8_t *__restrict__ img, size_t slot_bytes, int slot0, int nslots,
                                                  LevelGeom S, LevelGeom D, int padx, int pady)
 {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    int py = blockIdx.y;
-    int f = blockIdx.z;
-    if (q * 4 >= D.pitch) return;
+    __shared__ __align__(16) uint8_t sS[PD_SH][PD_SW];
+    __shared__ __align__(8) uint16_t sH[PD_SH][PD_TW];
+    const int px0 = blockIdx.x * PD_TW, py0 = blockIdx.y * PD_TH;
+    const int f = blockIdx.z;
     uint8_t *base = img + (size_t)((slot0 + f) % nslots) * slot_bytes;
     const uint8_t *sp = base + S.img_off + (size_t)pady * S.pitch + padx;   // source interior origin
     uint8_t *dp = base + D.img_off;
-    int oy = reflect101(py - pady, D.h);
-    int px0 = q * 4 - padx;
-    uint32_t v = 0;
-    if (px0 >= 0 && px0 + 3 < D.w) {
-        // fast path: 4 interior outputs share an 11-column source strip
-        int acc[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int j = 0; j < 5; j++) {
-            const uint8_t *r = sp + (ptrdiff_t)(2 * oy + j - 2) * S.pitch + 2 * px0 - 2;
-            int c[11];
-#pragma unroll
-            for (int i = 0; i < 11; i++) c[i] = r[i];
-            const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
-#pragma unroll
-            for (int o = 0; o < 4; o++)
-                acc[o] += kj * (c[2 * o] + 4 * c[2 * o + 1] + 6 * c[2 * o + 2] + 4 * c[2 * o + 3] + c[2 * o + 4]);
+    const int ox0 = px0 - padx, oy0 = py0 - pady;
+    const bool interior = ox0 >= 0 && ox0 + PD_TW <= D.w && oy0 >= 0 && oy0 + PD_TH <= D.h && ((padx | S.pitch) & 15) == 0;
+    if (interior) {
+        // ---- stage: source rows 2 oy0 - 2 .. 2 oy0 + 2 PD_TH, columns from the 16-byte boundary at or below 2 ox0 - 2
+        const int c0 = (2 * ox0 - 2) & ~15;            // padx is a multiple of 16: the boundary is one in memory as well
+        const int skew = 2 * ox0 - 2 - c0;             // 14 (ox0 is a multiple of 128 minus padx = a multiple of 64)
+        const uint8_t *src = sp + (ptrdiff_t)(2 * oy0 - 2) * S.pitch + c0;
+        for (int i = threadIdx.x; i < PD_SH * (PD_SW / 16); i += 256) {
+            const int r = i / (PD_SW / 16), c = i - r * (PD_SW / 16);
+            *reinterpret_cast<uint4 *>(&sS[r][16 * c]) = __ldg(reinterpret_cast<const uint4 *>(src + (ptrdiff_t)r * S.pitch + 16 * c));
         }
+        __syncthreads();
+        // ---- horizontal pass: 4 outputs (source bytes skew + 8 q .. + 10) per thread-iteration
+        for (int i = threadIdx.x; i < PD_SH * (PD_TW / 4); i += 256) {
+            const int r = i / (PD_TW / 4), q = i - r * (PD_TW / 4);
+            const int o = skew + 8 * q;                // even; the three words around it cover 11 bytes whatever o & 3 is
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(&sS[r][o & ~3]);
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3];
+            const int sh = (o & 3) * 8;
+            const uint32_t a = __funnelshift_r(w0, w1, sh), b = __funnelshift_r(w1, w2, sh), c = __funnelshift_r(w2, w3, sh);
+            int p[11];
 #pragma unroll
-        for (int o = 0; o < 4; o++) v |= (uint32_t)((acc[o] + 128) >> 8) << (8 * o);
-    } else {
+            for (int k = 0; k < 4; k++) { p[k] = (a >> (8 * k)) & 0xff; p[4 + k] = (b >> (8 * k)) & 0xff; }
+            p[8] = c & 0xff; p[9] = (c >> 8) & 0xff; p[10] = (c >> 16) & 0xff;
+            uint32_t h[4];
 #pragma unroll
-        for (int o = 0; o < 4; o++) {
-            int px = px0 + o;
-            if (px < -padx || px >= D.w + padx) continue;
-            int ox = reflect101(px, D.w);
-            int acc = 0;
+            for (int k = 0; k < 4; k++) h[k] = (uint32_t)(p[2 * k] + 4 * p[2 * k + 1] + 6 * p[2 * k + 2] + 4 * p[2 * k + 3] + p[2 * k + 4]);
+            *reinterpret_cast<uint2 *>(&sH[r][4 * q]) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+        }
+        __syncthreads();
+        // ---- vertical pass + store
+        for (int i = threadIdx.x; i < PD_TH * (PD_TW / 4); i += 256) {
+            const int r = i / (PD_TW / 4), q = i - r * (PD_TW / 4);
+            uint32_t lo = 0, hi = 0;                   // two packed 16-bit sums each (max 255 * 256 < 65536)
 #pragma unroll
             for (int j = 0; j < 5; j++) {
-                const uint8_t *r = sp + (ptrdiff_t)(2 * oy + j - 2) * S.pitch + 2 * ox - 2;
-                const int kj = (j == 0 || j == 4) ? 1 : ((j == 2) ? 6 : 4);
-                acc += kj * (r[0] + 4 * r[1] + 6 * r[2] + 4 * r[3] + r[4]);
+                const uint2 v = *reinterpret_cast<const uint2 *>(&sH[2 * r + j][4 * q]);
+                const uint32_t kj = (j == 0 || j == 4) ? 1u : ((j == 2) ? 6u : 4u);
+                lo += kj * v.x; hi += kj * v.y;
             }
-            v |= (uint32_t)((acc + 128) >> 8) << (8 * o);
+            // (sum + 128) >> 8 per half: the sums stay below 65536, so the halves do not carry into each other
+            lo += 0x00800080u; hi += 0x00800080u;
+            const uint32_t v = ((lo >> 8) & 0xffu) | ((lo >> 16) & 0xff00u) | (((hi >> 8) & 0xffu) << 16) | ((hi >> 24) << 24);
+            *reinterpret_cast<uint32_t *>(dp + (size_t)(py0 + r) * D.pitch + px0 + 4 * q) = v;
         }
+        return;
     }
-    *reinterpret_cast<uint32_t *>(dp + (size_t)py * D.pitch + q * 4) = v;
+    // ---- tiles on the frame / ragged edges: per-pixel path
+    for (int i = threadIdx.x; i < PD_TH * (PD_TW / 4); i += 256) {
+        const int r = i / (PD_TW / 4), q = i - r * (PD_TW / 4);
+        const int py = py0 + r;
+        if (py >= D.rows || px0 + 4 * q >= D.pitch) continue;
+        const int oy = reflect101(py - pady, D.h);
+        uint32_t v = 0;
+#pragma unroll
+        for (int o = 0; o < 4; o++) {
+            const int px = ox0 + 4 * q + o;
+            if (px < -padx || px >= D.w + padx) continue;
+            v |= pyrdown_px(sp, S.pitch, reflect101(px, D.w), oy) << (8 * o);
+        }
+        *reinterpret_cast<uint32_t *>(dp + (size_t)py * D.pitch + px0 + 4 * q) = v;
+    }
 }
 
 // ---- Scharr planes (calcScharrDeriv): Ix = t0[x+1]-t0[x-1], t0 = 3(up+down)+10 mid; Iy = 3(t1[x-1]+t1[x+1])+10 t1[x] ---
@@ -177,7 +227,7 @@ cudaError_t launch_pyramid_down(const PyrGeom &g, uint8_t *img, int slot0, int n
 {
     for (int l = l0 < 1 ? 1 : l0; l <= l1 && l < g.nlev; l++) {
         const LevelGeom &D = g.lv[l];
-        dim3 grid((D.pitch / 4 + 255) / 256, D.rows, nframes);
+        dim3 grid((D.pitch + PD_TW - 1) / PD_TW, (D.rows + PD_TH - 1) / PD_TH, nframes);
         k_pyrdown<<<grid, 256, 0, s>>>(img, g.slot_img_bytes, slot0, g.nslots, g.lv[l - 1], D, g.padx, g.pady);
         MD_COUNT_LAUNCH(1);
     }

@@ -334,6 +334,13 @@ extern "C" int md_create(const md_config *cfg, int device, md_ctx **out)
         ctx->pipe_first = e ? atoi(e) : 0;
         e = getenv("MD_TRACE");
         ctx->trace_calls = e ? atoi(e) : 0;
+        e = getenv("MD_PIPE_BOUNDS");
+        ctx->pipe_nbounds = 0;
+        while (e && *e && ctx->pipe_nbounds < 8) {
+            ctx->pipe_bounds[ctx->pipe_nbounds++] = atoi(e);
+            e = strchr(e, ',');
+            if (e) e++;
+        }
         e = getenv("MD_GRAPHS");
         if (e) ctx->cfg.cuda_graphs = atoi(e) != 0;
     }
@@ -820,6 +827,12 @@ static int batch_enqueue(md_ctx *ctx, const md_frames *fr, const md_outputs *out
     int nch = 0;
     bounds[0] = 0;
     if (serial) { nch = 1; bounds[1] = pairs; }
+    else if (ctx->pipe_nbounds > 0 && !host) {
+        // MD_PIPE_BOUNDS="2,8,32": explicit chunk ends (tuning aid); ends beyond the batch are clipped, the batch end is appended
+        for (int i = 0; i < ctx->pipe_nbounds && nch < 7; i++)
+            if (ctx->pipe_bounds[i] > bounds[nch] && ctx->pipe_bounds[i] < pairs) { bounds[nch + 1] = ctx->pipe_bounds[i]; nch++; }
+        bounds[++nch] = pairs;
+    }
     else if (pairs < 8) { nch = 2; bounds[1] = pairs / 2; bounds[2] = pairs; }
     else {
         const int tuned = ctx->pipe_chunks;        // MD_PIPE_CHUNKS=<2..8> in the environment overrides the default (tuning aid)

@@ -220,6 +220,7 @@ struct md_ctx {
     void *scratch;        // grow-only device scratch of the small host-memory entry points (md_gray_u8, md_cluster_vectors)
     size_t scratch_bytes;
     long long launches;   // kernels launched through this context's calls (md_stats.kernel_launches)
+    int pipe_bounds[8], pipe_nbounds;           // MD_PIPE_BOUNDS
     int pipe_chunks, pipe_first, trace_calls;   // MD_PIPE_CHUNKS / MD_PIPE_FIRST / MD_TRACE, read once in md_create
 };
 
