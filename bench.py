@@ -534,13 +534,13 @@ def main():
                              "source": "ncu smsp__inst_executed.sum of k_lk_phase / tracked points (profiles/r01_lk_phase_ncu_full_v2.txt); the time is the whole K2 stage (planes + window sums + LK), so this is a lower bound of the LK kernel's own 80 %"}
 
     # ---- e2e: C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
-    e2e = None
-    if not a.no_e2e:
+    def measure_e2e(packed):
         ctx2 = capi.Context(width=w, height=h, max_batch=B, pixel_step=a.pixel_step, min_vector_size=0.2, seed=1, device=local,
-                            flow_engine=engine)
+                            flow_engine=engine, mask_packed=1 if packed else 0)
+        mrow = (w + 7) // 8 if packed else w
         pin_frames = torch.empty((B + 1, h, w), dtype=torch.uint8).pin_memory()
         pin_frames.copy_(host)
-        pin = dict(mask=torch.empty((B, h, w), dtype=torch.uint8).pin_memory(),
+        pin = dict(mask=torch.empty((B, h, mrow), dtype=torch.uint8).pin_memory(),
                    nxt=torch.empty((B, P, 2), dtype=torch.float32).pin_memory(),
                    st=torch.empty((B, P), dtype=torch.uint8).pin_memory(),
                    keep=torch.empty((B, P), dtype=torch.uint8).pin_memory(),
@@ -548,7 +548,7 @@ def main():
                    nv=torch.empty((B,), dtype=torch.int32).pin_memory(),
                    inl=torch.empty((B,), dtype=torch.int32).pin_memory())
         houts = capi.MdOutputs(pin["nxt"].data_ptr(), pin["st"].data_ptr(), pin["keep"].data_ptr(), pin["H"].data_ptr(),
-                               pin["nv"].data_ptr(), pin["inl"].data_ptr(), pin["mask"].data_ptr(), w, w * h)
+                               pin["nv"].data_ptr(), pin["inl"].data_ptr(), pin["mask"].data_ptr(), mrow, mrow * h)
         # Chained stream: the context keeps the pyramid of the last frame, every step pushes B NEW frames.  The clip
         # is played forward (f1..fB) and backward (fB-1..f0) alternately so that every pair is a real consecutive pair.
         pin_fwd = pin_frames[1:]
@@ -563,7 +563,7 @@ def main():
             nstep[0] += 1
             ctx2.raw_process_batch(src.data_ptr(), 1, w, frame_bytes, B, True, houts, capi.MD_MEM_HOST)
 
-        for _ in range(a.warmup + (a.warmup % 2)):      # an even number of warm-up steps: the timed loop starts forward
+        for _ in range(max(a.warmup, 3) + (max(a.warmup, 3) % 2)):      # an even number of warm-up steps: the timed loop starts forward
             hstep()
         barrier()
         t0 = time.perf_counter()
@@ -575,10 +575,20 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         h2d = B * frame_bytes
-        d2h = B * (frame_bytes + P * 8 + P + P + 72 + 4 + 4)
-        e2e = {"value": world * B * a.steps / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        d2h = B * (mrow * h + P * 8 + P + P + 72 + 4 + 4)
+        res = {"value": world * B * a.steps / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "graph_replays": ctx2.stats()["graph_replays"]}
         assert int(pin["inl"].min()) > 0
         ctx2.close()
+        return res
+
+    e2e = None
+    e2e_packed = None
+    if not a.no_e2e:
+        e2e = measure_e2e(False)
+        if not a.lean and not vf:
+            # the same with md_config.mask_packed (1 bit per mask pixel on the way back: the u8 mask is 91 % of the D2H bytes)
+            e2e_packed = measure_e2e(True)
 
     # ---- two camera streams on this GPU (two contexts, two CUDA streams): the head and tail of one stream's batch are filled by
     # the other stream's LK.  An extra figure; `value` above stays the single-stream number.
@@ -663,6 +673,7 @@ def main():
             "mpx_per_s": value * N / 1e6,
             "roofline": roofline, "lk_work": lk_taps, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "stream_stats": gathered, "two_streams_per_gpu": multi, "host_pinning": pinned,
+            "e2e_packed_mask": e2e_packed, "graph_replays": st["graph_replays"],
         }
         assert line["config"]["grid_points"] == P
     ctx.close()

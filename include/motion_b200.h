@@ -77,7 +77,10 @@ typedef struct md_config {
     int32_t vf_grid_barrier;    /* test hook: 1 = run every Gauss-Seidel launch of md_varflow as the cooperative grid with the
                                    counting barrier (the path large levels take by themselves) instead of one cluster */
     int32_t cuda_graphs;        /* 1 (default) = md_process_batch captures the DAG of a repeated call into a CUDA graph and replays it */
-    int32_t reserved[5];
+    int32_t mask_packed;        /* 1 = md_process_batch writes the mask as 1 bit per pixel (bit x & 7 of byte x >> 3, LSB first, row pitch
+                                   md_outputs.mask_pitch >= (width + 7) / 8 bytes): an eighth of the device-to-host bytes.  0 (default) =
+                                   one byte per pixel, 0 / 255, like the reference's cv::Mat */
+    int32_t reserved[4];
 } md_config;
 
 typedef struct md_ctx md_ctx;

@@ -39,7 +39,7 @@ class MdConfig(C.Structure):
         ("ransac_thresh", C.c_double), ("seed", C.c_uint32),
         ("vf_max_level", C.c_int32), ("vf_start_level", C.c_int32), ("vf_n1", C.c_int32), ("vf_n2", C.c_int32),
         ("vf_rho", C.c_float), ("vf_alpha", C.c_float), ("vf_sigma", C.c_float), ("vf_literal", C.c_int32),
-        ("flow_engine", C.c_int32), ("vf_grid_barrier", C.c_int32), ("cuda_graphs", C.c_int32), ("reserved", C.c_int32 * 5),
+        ("flow_engine", C.c_int32), ("vf_grid_barrier", C.c_int32), ("cuda_graphs", C.c_int32), ("mask_packed", C.c_int32), ("reserved", C.c_int32 * 4),
     ]
 
 
@@ -237,9 +237,17 @@ class Context:
                    keep=np.zeros((pairs, self.P), np.uint8), H=np.zeros((pairs, 3, 3), np.float64),
                    num_vectors=np.zeros(pairs, np.int32), inliers=np.zeros(pairs, np.int32),
                    mask=np.zeros((pairs, self.h, self.w), np.uint8) if want_mask else None)
+        mpitch, mstride = self.w, self.w * self.h
+        if want_mask and self.cfg.mask_packed:
+            # 1 bit per pixel on the wire; handed back both packed ("mask_bits") and expanded to 0 / 255
+            mpitch = (self.w + 7) // 8
+            mstride = mpitch * self.h
+            res["mask_bits"] = np.zeros((pairs, self.h, mpitch), np.uint8)
         out = MdOutputs(_ptr(res["next"]), _ptr(res["status"]), _ptr(res["keep"]), _ptr(res["H"]), _ptr(res["num_vectors"]),
-                        _ptr(res["inliers"]), _ptr(res["mask"]), self.w, self.w * self.h)
+                        _ptr(res["inliers"]), _ptr(res["mask_bits"] if "mask_bits" in res else res["mask"]), mpitch, mstride)
         self._ck(lib().md_process_batch(self._h, C.byref(fr), C.byref(out), MD_MEM_HOST))
+        if "mask_bits" in res:
+            res["mask"] = np.unpackbits(res["mask_bits"], axis=2, bitorder="little")[:, :, :self.w] * np.uint8(255)
         return res
 
     def raw_process_batch(self, frames_ptr, channels, pitch, frame_stride, count, chain, outputs, mem):

@@ -473,12 +473,31 @@ __global__ void __launch_bounds__(NCONS + 32, MASK_CTAS_PER_SM) k_mask(const Mas
     // that the bit becomes the sign bit of byte 0 lets PRMT's sign replication write 0x00 / 0xff.
     const int rot = (lane - 7) & 31;
     auto phase3 = [&](const uint4 *D, int tx0, int ty0, int b) {
-        if (lane < 1 || lane > TW / 4) return;
         const int x = tx0 - 4 + 4 * lane;
+        const int nrow = min(TH, h - ty0);
+        if (p.packed) {
+            // 1 bit per pixel: a lane's run is a nibble, an odd lane and its right neighbour make the byte at x / 8 (the tile starts at
+            // a multiple of 120 pixels = 15 bytes)
+            uint8_t *dst = p.mask + (size_t)b * p.mask_stride + (size_t)(ty0 + warp) * p.mask_pitch + (x >> 3);
+            const size_t step = (size_t)(NCONS / 32) * p.mask_pitch;
+            for (int ry = warp; ry < nrow; ry += NCONS / 32, dst += step) {
+                uint4 d = D[ry + 2];
+                if (p.morph) {
+                    const uint4 u = D[ry + 1], v = D[ry + 3];
+                    d.x |= u.x | v.x; d.y |= u.y | v.y; d.z |= u.z | v.z; d.w |= u.w | v.w;
+                }
+                uint32_t nib = ((d.x >> lane) & 1u) | (((d.y >> lane) & 1u) << 1) | (((d.z >> lane) & 1u) << 2) | (((d.w >> lane) & 1u) << 3);
+                if (lane < 1 || lane > TW / 4) nib = 0;
+                const uint32_t right = __shfl_down_sync(0xffffffffu, nib, 1);
+                local += 8 * __popc(nib);
+                if ((lane & 1) && lane <= TW / 4 && x < w) *dst = (uint8_t)(nib | (right << 4));
+            }
+            return;
+        }
+        if (lane < 1 || lane > TW / 4) return;
         if (x >= w) return;
         uint8_t *dst = p.mask + (size_t)b * p.mask_stride + (size_t)(ty0 + warp) * p.mask_pitch + x;
         const size_t step = (size_t)(NCONS / 32) * p.mask_pitch;
-        const int nrow = min(TH, h - ty0);
         for (int ry = warp; ry < nrow; ry += NCONS / 32, dst += step) {
             uint4 d = D[ry + 2];
             if (p.morph) {

@@ -769,7 +769,7 @@ static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
         mp.pitch = ctx->g.lv[0].pitch; mp.stride = (long long)ctx->g.slot_img_bytes;
         mp.nslots = ns; mp.prev_slot0 = (prev0 + p0) % ns; mp.cur_slot0 = (prev0 + p0 + 1) % ns;
         mp.w = ctx->cfg.width; mp.h = ctx->cfg.height; mp.Hinv = ctx->d_Hinv + 9 * p0; mp.valid = ctx->d_valid + p0;
-        mp.thresh = ctx->cfg.diff_threshold; mp.morph = ctx->cfg.morph;
+        mp.thresh = ctx->cfg.diff_threshold; mp.morph = ctx->cfg.morph; mp.packed = ctx->cfg.mask_packed ? 1 : 0;
         mp.mask = d_mask + (size_t)p0 * mask_stride; mp.mask_pitch = mask_pitch; mp.mask_stride = mask_stride;
         mp.stat_mask = ctx->d_stats;
         MD_NVTX("K4 warp + diff + threshold + morphology");
@@ -811,8 +811,11 @@ static int batch_enqueue(md_ctx *ctx, const md_frames *fr, const md_outputs *out
     long long ds = fr->frame_stride;
     float2 *d_next = ctx->d_next;
     uint8_t *d_status = ctx->d_status, *d_keep = ctx->d_keep, *d_mask = ctx->d_mask;
-    int mpitch = ctx->fpitch;
-    long long mstride = (long long)ctx->fpitch * h;
+    // staging layout of the masks in host mode: byte rows of the frame pitch, or packed rows ((w + 7) / 8 bytes, 16-byte aligned)
+    const int packed = ctx->cfg.mask_packed ? 1 : 0;
+    const int mrow = packed ? (w + 7) / 8 : w;                 // payload bytes per mask row
+    int mpitch = packed ? align_up(mrow, 16) : ctx->fpitch;
+    long long mstride = (long long)mpitch * h;
     if (host) {
         df = ctx->d_frames; dp = ctx->fpitch * fr->channels; ds = (long long)dp * h;
     } else {
@@ -871,11 +874,11 @@ static int batch_enqueue(md_ctx *ctx, const md_frames *fr, const md_outputs *out
         if (out->inliers) CK(cudaMemcpyAsync(out->inliers + p0, ctx->d_inliers + p0, sizeof(int) * n, cudaMemcpyDeviceToHost, so));
         if (out->mask) {
             if (out->mask_stride == (long long)out->mask_pitch * h)
-                CK(cudaMemcpy2DAsync(out->mask + p0 * out->mask_stride, out->mask_pitch, ctx->d_mask + p0 * mstride, ctx->fpitch, w,
+                CK(cudaMemcpy2DAsync(out->mask + p0 * out->mask_stride, out->mask_pitch, ctx->d_mask + p0 * mstride, mpitch, mrow,
                                      (size_t)h * n, cudaMemcpyDeviceToHost, so));
             else
                 for (int b = p0; b < p1; b++)
-                    CK(cudaMemcpy2DAsync(out->mask + b * out->mask_stride, out->mask_pitch, ctx->d_mask + b * mstride, ctx->fpitch, w, h,
+                    CK(cudaMemcpy2DAsync(out->mask + b * out->mask_stride, out->mask_pitch, ctx->d_mask + b * mstride, mpitch, mrow, h,
                                          cudaMemcpyDeviceToHost, so));
         }
         return MD_OK;
@@ -1030,7 +1033,8 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
     const int pairs = fr->chain ? fr->count : fr->count - 1;
     if (pairs < 1 || pairs > ctx->cfg.max_batch) FAIL(MD_ERR_INVALID, "md_process_batch: pairs must be in [1, max_batch]");
     if (fr->chain && !ctx->have_cached) FAIL(MD_ERR_STATE, "md_process_batch: chain=1 without a cached previous frame");
-    if (out->mask && out->mask_pitch < ctx->cfg.width) FAIL(MD_ERR_INVALID, "md_process_batch: mask_pitch too small");
+    if (out->mask && out->mask_pitch < (ctx->cfg.mask_packed ? (ctx->cfg.width + 7) / 8 : ctx->cfg.width))
+        FAIL(MD_ERR_INVALID, "md_process_batch: mask_pitch too small");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t s = ctx->stream;
     const int ns = ctx->g.nslots;

@@ -149,6 +149,7 @@ struct MaskParams {
     int mask_pitch;
     long long mask_stride;
     unsigned long long *stat_mask;   // nullable
+    int packed;              // 1 = the mask leaves as 1 bit per pixel (LSB first), mask_pitch in bytes of packed rows
     int use_tma;             // set by launch_mask: 1 = the tensor maps are usable (TMA-staged fast path)
 };
 

@@ -185,3 +185,19 @@ def test_mask_fast_path_random_homographies(capi, oracle, size):
             assert np.array_equal(got, ref), (size, H.tolist(), thresh, int((got != ref).sum()))
         got = ctx.motion_mask(prev, cur, H, thresh=60, morph=False)
         assert np.array_equal(got, oracle.motion_mask(prev, cur, H, thresh=60, morph=False)), (size, H.tolist(), "raw")
+
+
+@pytest.mark.parametrize("size", [(320, 240), (641, 479), (1920, 1080)])
+def test_packed_mask_output_equals_byte_mask(capi, size):
+    """md_config.mask_packed: the same mask as 1 bit per pixel (LSB first), an eighth of the bytes on the way back to the host."""
+    w, h = size
+    frames, _ = synth.sequence(w, h, 4, seed=31, blobs=3)
+    a = _ctx(capi, w, h, max_batch=3, seed=5, diff_threshold=40)
+    b = _ctx(capi, w, h, max_batch=3, seed=5, diff_threshold=40, mask_packed=1)
+    ra, rb = a.process_batch(frames), b.process_batch(frames)
+    assert ra["mask"].any()
+    assert rb["mask_bits"].shape == (3, h, (w + 7) // 8)
+    assert np.array_equal(ra["mask"], rb["mask"])
+    assert a.stats()["mask_pixels"] == b.stats()["mask_pixels"] == int((ra["mask"] > 0).sum())
+    for k in ("next", "status", "H", "inliers"):
+        assert np.array_equal(ra[k], rb[k]), k
