@@ -239,6 +239,19 @@ int md_cluster_points(md_ctx *ctx, const float *pts, int32_t n, double distance_
 int md_cluster_vectors(md_ctx *ctx, const double *vec4, int32_t n, double distance_threshold, double angular_threshold,
                        int32_t *labels, int32_t *num_clusters_all, int mem);
 
+/* ---- OpticalFlowVisualizer::showOpticalFlowVectors (common/src/optical_flow_visualizer.cpp:23-71; node.cpp:83,101) --------------- */
+/* out = image (1 or 3 interleaved channels, width x height of the context) with one anti-aliased arrow per flow vector that passes
+ * the reference's test (|dx| or |dy| > min_vector_size, both < 5 * pixel_step; :37), drawn like cv::line(..., colour, 1, CV_AA):
+ * shaft start -> end, two 3-pixel head strokes at +-45 degrees, in the reference's visiting order (overlapping arrows blend in
+ * that order).  The vectors are EITHER vec4 [n][4] f64 = (x, y, dx, dy), the non-empty elements of the flow field row by row
+ * (rows outer, columns inner), OR -- vec4 == NULL -- one pair's next_pts [P][2] / status [P] / keep [P] as md_process_batch wrote
+ * them (the field of optical_flow_calculator.cpp:78-117 is formed on the device; nothing has to visit the host to be drawn).
+ * pixel_step and min_vector_size are the context's.  colour[channels].  *drawn (nullable, same memory space as the buffers) =
+ * arrows that passed the test.  MD_MEM_DEVICE: stream ordered, image / out may not alias. */
+int md_draw_flow(md_ctx *ctx, const uint8_t *image, int32_t channels, int32_t pitch, const double *vec4, int32_t n,
+                 const float *next_pts, const uint8_t *status, const uint8_t *keep, const uint8_t *colour, uint8_t *out,
+                 int32_t out_pitch, int32_t *drawn, int mem);
+
 /* ---- OutlierDetector::fitSubspace (common/src/outlier_detector.cpp:236-331) ------------------------------------ */
 /* traj [T][F][2]; forced_cols NULL (rand() % T after srand(seed)) or [iters][4*num_motions] host indices.
  * residual[T] f32, best_cols[4*num_motions] i32, outlier[T] u8 (residual > threshold, :318-324). */

@@ -25,7 +25,7 @@ SYMBOLS = [
     "md_pyramid_read", "md_pyramid_read_deriv", "md_lk_flow", "md_fit_egomotion", "md_motion_mask",
     "md_process_batch", "md_process_pair", "md_track_trajectories", "md_fit_subspace", "md_varflow", "md_stats_get",
     "md_stats_reset", "md_profile", "md_profile_read", "md_live_params_default", "md_window_reset", "md_window_push",
-    "md_window_detect", "md_cluster_points", "md_find_outliers", "md_cluster_vectors",
+    "md_window_detect", "md_cluster_points", "md_find_outliers", "md_cluster_vectors", "md_draw_flow",
 ]
 
 
@@ -349,6 +349,25 @@ class Context:
         self._ck(lib().md_cluster_vectors(self._h, _ptr(vec4), n, C.c_double(distance_threshold), C.c_double(angular_threshold),
                                           _ptr(labels), C.byref(nall), MD_MEM_HOST))
         return labels[:n], nall.value
+
+    def draw_flow(self, image, vec4=None, next_pts=None, status=None, keep=None, colour=(255, 0, 0)):
+        """showOpticalFlowVectors: image [h][w] or [h][w][3]; either vec4 [n][4] (row-major field elements) or one pair's
+        next_pts / status / keep.  Returns (image with arrows, arrows drawn)."""
+        image = np.ascontiguousarray(image, np.uint8)
+        ch = 3 if image.ndim == 3 else 1
+        out = np.empty_like(image)
+        col = np.ascontiguousarray(np.array(colour, np.uint8).reshape(-1)[:ch])
+        drawn = C.c_int32()
+        if vec4 is not None:
+            vec4 = np.ascontiguousarray(vec4, np.float64).reshape(-1, 4)
+            vp, n = _ptr(vec4) if len(vec4) else C.c_void_p(8), len(vec4)
+            a = b = c = None
+        else:
+            vp, n = None, 0
+            a = np.ascontiguousarray(next_pts, np.float32); b = np.ascontiguousarray(status, np.uint8); c = np.ascontiguousarray(keep, np.uint8)
+        self._ck(lib().md_draw_flow(self._h, _ptr(image), ch, self.w * ch, vp, n, _ptr(a), _ptr(b), _ptr(c), _ptr(col), _ptr(out),
+                                    self.w * ch, C.byref(drawn), MD_MEM_HOST))
+        return out, drawn.value
 
     def find_outliers(self, dxdy, include_zeros=False):
         dxdy = np.ascontiguousarray(dxdy, np.float64).reshape(-1, 2)

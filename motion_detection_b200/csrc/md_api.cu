@@ -1414,6 +1414,59 @@ extern "C" int md_cluster_vectors(md_ctx *ctx, const double *vec4, int32_t n, do
 }
 
 // ---- statistics --------------------------------------------------------------------------------------------------------
+// ---- OpticalFlowVisualizer::showOpticalFlowVectors (k_draw.cu) ------------------------------------------------------------------
+extern "C" int md_draw_flow(md_ctx *ctx, const uint8_t *image, int32_t channels, int32_t pitch, const double *vec4, int32_t n,
+                            const float *next_pts, const uint8_t *status, const uint8_t *keep, const uint8_t *colour, uint8_t *out,
+                            int32_t out_pitch, int32_t *drawn, int mem)
+{
+    MD_NVTX("md_draw_flow");
+    if (!ctx) return MD_ERR_INVALID;
+    const int w = ctx->cfg.width, h = ctx->cfg.height;
+    const bool grid = vec4 == nullptr;
+    if (!image || !out || !colour || (channels != 1 && channels != 3) || pitch < w * channels || out_pitch < w * channels ||
+        (grid ? (!next_pts || !status || !keep) : n < 0))
+        FAIL(MD_ERR_INVALID, "md_draw_flow: bad arguments (a Vec4d list, or next_pts + status + keep of one pair)");
+    if (grid) n = ctx->P;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const bool host = mem != MD_MEM_DEVICE;
+    const size_t segb = draw_segs_bytes(n), boxb = ((size_t)n * sizeof(int4) + 255) / 256 * 256;
+    const size_t row = (size_t)w * channels, imgb = (row * h + 255) / 256 * 256;
+    const size_t vecb = host ? (grid ? ((size_t)n * 10 + 255) / 256 * 256 : ((size_t)n * 32 + 255) / 256 * 256) : 0;
+    { int r = ensure_scratch(ctx, segb + boxb + 256 + vecb + (host ? 2 * imgb : 0)); if (r != MD_OK) return r; }
+    uint8_t *base = (uint8_t *)ctx->scratch;
+    void *segs = base, *abox = base + segb;
+    int *d_drawn = (int *)(base + segb + boxb);
+    uint8_t *d_vec = base + segb + boxb + 256, *d_in = d_vec + vecb, *d_out = d_in + imgb;
+    const uint8_t *src = image;
+    uint8_t *dst = out;
+    int sp = pitch, dp = out_pitch;
+    const double *dv = vec4;
+    const float2 *dn = (const float2 *)next_pts;
+    const uint8_t *dst_status = status, *dst_keep = keep;
+    if (host) {
+        CK(cudaMemcpy2DAsync(d_in, row, image, pitch, row, h, cudaMemcpyHostToDevice, s));
+        src = d_in; dst = d_out; sp = dp = (int)row;
+        if (grid) {
+            CK(cudaMemcpyAsync(d_vec, next_pts, (size_t)n * 8, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_vec + (size_t)n * 8, status, n, cudaMemcpyHostToDevice, s));
+            CK(cudaMemcpyAsync(d_vec + (size_t)n * 9, keep, n, cudaMemcpyHostToDevice, s));
+            dn = (const float2 *)d_vec; dst_status = d_vec + (size_t)n * 8; dst_keep = d_vec + (size_t)n * 9;
+        } else if (n > 0) {
+            CK(cudaMemcpyAsync(d_vec, vec4, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+            dv = (const double *)d_vec;
+        }
+    }
+    CK(launch_draw_flow(src, channels, sp, dst, dp, w, h, n, ctx->cfg.pixel_step, ctx->cfg.min_vector_size, dv, dn, dst_status, dst_keep,
+                        ctx->gx, ctx->gy, colour, segs, abox, d_drawn, s));
+    if (host) {
+        CK(cudaMemcpy2DAsync(out, out_pitch, d_out, row, row, h, cudaMemcpyDeviceToHost, s));
+        if (drawn) CK(cudaMemcpyAsync(drawn, d_drawn, sizeof(int), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    } else if (drawn) CK(cudaMemcpyAsync(drawn, d_drawn, sizeof(int), cudaMemcpyDeviceToDevice, s));
+    return MD_OK;
+}
+
 extern "C" int md_stats_get(md_ctx *ctx, md_stats *out)
 {
     if (!ctx || !out) return MD_ERR_INVALID;

@@ -254,6 +254,10 @@ cudaError_t launch_pyramid(const PyrGeom &g, uint8_t *img, short2 *der, int slot
                            int channels, int fpitch, long long fstride, cudaStream_t s);
 cudaError_t launch_lk(const LkParams &p, const LkTmaMaps *maps, const LkPhaseMaps *pmaps, int pairs, cudaStream_t s);
 cudaError_t launch_ego(const EgoParams &p, int pairs, cudaStream_t s);
+cudaError_t launch_draw_flow(const uint8_t *src, int channels, int spitch, uint8_t *dst, int dpitch, int w, int h, int n, int ps, double min_vec,
+                             const double *vec4, const float2 *next, const uint8_t *status, const uint8_t *keep, int gx, int gy,
+                             const uint8_t *colour, void *segs, void *abox, int *drawn, cudaStream_t s);
+size_t draw_segs_bytes(int n);
 cudaError_t launch_advance_pairs(unsigned long long *ctr, int pairs, cudaStream_t s);
 cudaError_t launch_mask(const MaskParams &p, int pairs, const MaskTmaMaps *maps, cudaStream_t s);
 bool mask_encode_maps(MaskTmaMaps *m, const uint8_t *prev, const uint8_t *cur, int w, int h, int pitch, long long stride, int nframes);

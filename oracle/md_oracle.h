@@ -51,6 +51,12 @@ int orc_find_outliers(const double *dxdy, int n, int include_zeros, uint8_t *out
 int orc_bounding_boxes(const float *pts, int n, const int32_t *labels, int nclusters, int min_size, int32_t *boxes,
                        int32_t *sizes, int32_t *ids);
 
+/* md_oracle_draw.c */
+void orc_line_aa(uint8_t *img, int w, int h, int pitch, int nch, int px1, int py1, int px2, int py2, const uint8_t *colour);
+int orc_arrow_segments(const double *elem, int pixel_step, double min_vector_size, int *seg);
+int orc_draw_flow(const uint8_t *src, int w, int h, int nch, int pitch, const double *vec4, int n, int pixel_step,
+                  double min_vector_size, const uint8_t *colour, uint8_t *dst, int dpitch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -375,6 +375,52 @@ def find_outliers(dxdy, include_zeros=False):
 _REF = {}
 
 
+def line_aa(img, p1, p2, colour):
+    """cv::line(img, p1, p2, colour, 1, CV_AA, 0) in place; img [h][w] or [h][w][3] uint8."""
+    assert img.dtype == np.uint8 and img.flags.c_contiguous
+    h, w = img.shape[:2]
+    nch = 1 if img.ndim == 2 else img.shape[2]
+    col = np.ascontiguousarray(np.array(colour, np.uint8).reshape(-1)[:nch])
+    lib().orc_line_aa(img.ctypes.data_as(u8p), w, h, w * nch, nch, int(p1[0]), int(p1[1]), int(p2[0]), int(p2[1]), col.ctypes.data_as(u8p))
+    return img
+
+
+def arrow_segments(elem, pixel_step, min_vector_size):
+    seg = np.zeros(12, np.int32)
+    e = np.ascontiguousarray(elem, np.float64)
+    ok = lib().orc_arrow_segments(e.ctypes.data_as(f64p), int(pixel_step), C.c_double(min_vector_size), seg.ctypes.data_as(i32p))
+    return seg.reshape(3, 4) if ok else None
+
+
+def draw_flow(image, vec4, pixel_step=10, min_vector_size=0.2, colour=(255, 0, 0)):
+    """OpticalFlowVisualizer::showOpticalFlowVectors (optical_flow_visualizer.cpp:23-71): vec4 [n][4] = the non-empty elements
+    of the flow field in row-major (y outer, x inner) order.  Returns (image with arrows, number of arrows drawn)."""
+    image = np.ascontiguousarray(image, np.uint8)
+    h, w = image.shape[:2]
+    nch = 1 if image.ndim == 2 else image.shape[2]
+    vec4 = np.ascontiguousarray(vec4, np.float64).reshape(-1, 4)
+    col = np.ascontiguousarray(np.array(colour, np.uint8).reshape(-1)[:nch])
+    out = np.empty_like(image)
+    n = lib().orc_draw_flow(image.ctypes.data_as(u8p), w, h, nch, w * nch, vec4.ctypes.data_as(f64p), len(vec4), int(pixel_step),
+                            C.c_double(min_vector_size), col.ctypes.data_as(u8p), out.ctypes.data_as(u8p), w * nch)
+    return out, n
+
+
+def flow_field_row_major(pts, nxt, status, keep):
+    """The flow-field elements (optical_flow_calculator.cpp:78-117) of the grid points, in the order showOpticalFlowVectors meets
+    them: row-major over the image (y outer, x inner)."""
+    pts = np.asarray(pts, np.float32); nxt = np.asarray(nxt, np.float32)
+    d = (nxt - pts).astype(np.float64)
+    vec = np.zeros((len(pts), 4), np.float64)
+    ok = np.asarray(status) != 0
+    kp = ok & (np.asarray(keep) != 0)
+    vec[ok, 0] = pts[ok, 0]; vec[ok, 1] = pts[ok, 1]
+    vec[~ok, 0] = -1.0; vec[~ok, 1] = -1.0
+    vec[kp, 2] = d[kp, 0]; vec[kp, 3] = d[kp, 1]
+    order = np.lexsort((pts[:, 0], pts[:, 1]))
+    return vec[order]
+
+
 def ref_lib(name):
     """'varflow' (common/src/VarFlow.cpp) or 'cluster' (flow_clusterer.cpp + vector_cluster.cpp + point_cluster.cpp);
     None when oracle/_ref was not built (no /root/reference at build time)."""

@@ -188,3 +188,26 @@ def varflow(A, B, max_level=4, n1=2, n2=2, rho=2.8, alpha=1400.0, sigma=1.5, lit
         else:
             break
     return U[0], V[0]
+
+
+def show_optical_flow_vectors(image, vec4, pixel_step, min_vector_size, colour):
+    """OpticalFlowVisualizer::showOpticalFlowVectors (common/src/optical_flow_visualizer.cpp:23-71) with cv2.line itself; vec4 =
+    the field's elements in the order the reference's double loop meets them."""
+    out = image.copy()
+    f32 = np.float32
+    n = 0
+    for e in np.asarray(vec4, np.float64).reshape(-1, 4):
+        if not ((abs(e[2]) > min_vector_size or abs(e[3]) > min_vector_size) and abs(e[2]) < pixel_step * 5 and abs(e[3]) < pixel_step * 5):
+            continue
+        sx, sy = f32(e[0]), f32(e[1])
+        ex, ey = f32(np.float64(sx) + e[2]), f32(np.float64(sy) + e[3])
+        back = np.float64(np.arctan2(f32(sy - ey), f32(sx - ex), dtype=f32))          # atan2 on float arguments
+        pts = [(sx, sy), (ex, ey)]
+        for ang in (back + np.pi / 4.0, back - np.pi / 4.0):
+            pts.append((f32(np.float64(ex) + 3.0 * np.cos(ang)), f32(np.float64(ey) + 3.0 * np.sin(ang))))
+        ip = [(int(np.rint(p[0])), int(np.rint(p[1]))) for p in pts]                   # Point2f -> Point: cvRound
+        cv2.line(out, ip[0], ip[1], colour, 1, cv2.LINE_AA, 0)
+        cv2.line(out, ip[1], ip[2], colour, 1, cv2.LINE_AA, 0)
+        cv2.line(out, ip[1], ip[3], colour, 1, cv2.LINE_AA, 0)
+        n += 1
+    return out, n

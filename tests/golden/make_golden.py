@@ -65,6 +65,25 @@ def main():
     x2 = (rng.random((32, 48)) * 100).astype(np.float32)
     out["prim_in2"] = x2
     out["prim_resize_half"] = cv2.resize(x2, (24, 16), interpolation=cv2.INTER_LINEAR)
+    # cv::line(..., 1, CV_AA): random segments (some clipped by the image), 3 channels and 1 channel, drawn one after another
+    rng = np.random.default_rng(77)
+    img3 = rng.integers(0, 256, (60, 80, 3), dtype=np.uint8)
+    img1 = rng.integers(0, 256, (60, 80), dtype=np.uint8)
+    segs = np.stack([rng.integers(-20, 100, 40), rng.integers(-20, 80, 40), rng.integers(-20, 100, 40), rng.integers(-20, 80, 40)], axis=1).astype(np.int32)
+    cols = rng.integers(0, 256, (40, 3), dtype=np.uint8)
+    out["aa_img3"], out["aa_img1"], out["aa_segs"], out["aa_cols"] = img3.copy(), img1.copy(), segs, cols
+    for s_, c_ in zip(segs, cols):
+        cv2.line(img3, (int(s_[0]), int(s_[1])), (int(s_[2]), int(s_[3])), tuple(int(v) for v in c_), 1, cv2.LINE_AA, 0)
+        cv2.line(img1, (int(s_[0]), int(s_[1])), (int(s_[2]), int(s_[3])), (int(c_[0]),), 1, cv2.LINE_AA, 0)
+    out["aa_out3"], out["aa_out1"] = img3, img1
+    # showOpticalFlowVectors on a small field (arrows long enough to overlap their neighbours)
+    fimg = rng.integers(0, 256, (90, 120, 3), dtype=np.uint8)
+    gy, gx = np.mgrid[0:90:10, 0:120:10]
+    vec = np.stack([gx.ravel(), gy.ravel(), rng.normal(6, 9, gx.size), rng.normal(-3, 9, gx.size)], axis=1).astype(np.float64)
+    vec[::7, 2:] = 0.0
+    out["flowdraw_img"], out["flowdraw_vec"] = fimg, vec
+    out["flowdraw_out"], nd = cvref.show_optical_flow_vectors(fimg, vec, 10, 0.2, (255, 0, 0))
+    out["flowdraw_n"] = np.int32(nd)
     out["cv2_version"] = np.array(cv2.__version__)
     path = os.path.join(HERE, "golden_cv2.npz")
     np.savez_compressed(path, **out)

@@ -168,3 +168,23 @@ def test_find_outliers_against_numpy_statistics():
     # no participating vector: nothing is flagged (vals.empty() return, outlier_detector.cpp:142-145)
     out, st = O.find_outliers(np.zeros((10, 2)), False)
     assert out.sum() == 0
+
+
+def test_line_aa_golden(oracle):
+    """cv::line(..., 1, CV_AA) -- OpenCV's LineAA restated in oracle/md_oracle_draw.c -- against frozen cv2 output: 40 segments
+    drawn one after another (clipped ones included), 3 channels and 1 channel."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_cv2.npz"))
+    img3, img1 = g["aa_img3"].copy(), g["aa_img1"].copy()
+    for s, c in zip(g["aa_segs"], g["aa_cols"]):
+        oracle.line_aa(img3, (s[0], s[1]), (s[2], s[3]), c)
+        oracle.line_aa(img1, (s[0], s[1]), (s[2], s[3]), c[:1])
+    assert np.array_equal(img3, g["aa_out3"])
+    assert np.array_equal(img1, g["aa_out1"])
+
+
+def test_show_optical_flow_vectors_golden(oracle):
+    """OpticalFlowVisualizer::showOpticalFlowVectors (optical_flow_visualizer.cpp:23-71): arrows of a 12 x 9 field, overlapping."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_cv2.npz"))
+    out, n = oracle.draw_flow(g["flowdraw_img"], g["flowdraw_vec"], 10, 0.2, (255, 0, 0))
+    assert n == int(g["flowdraw_n"]) and n > 50
+    assert np.array_equal(out, g["flowdraw_out"])

@@ -94,3 +94,34 @@ def test_fit_subspace_matches_numpy_svd(oracle):
     assert n == best and list(cols) == bcols
     assert np.abs(res - bres).max() < 1e-4
     assert abs(thr - 0.25 * 0.115) < 1e-12      # chi-square p99 table entry 2 (outlier_detector.cpp:22)
+
+
+def test_line_aa_exact(oracle):
+    """oracle.line_aa == cv2.line(..., 1, LINE_AA) on random segments, also partly / wholly outside the image, 1 and 3 channels."""
+    rng = np.random.default_rng(11)
+    for t in range(1500):
+        shp = (40, 50, 3) if t % 2 else (40, 50)
+        img = rng.integers(0, 256, shp, dtype=np.uint8)
+        ref, got = img.copy(), img.copy()
+        p1 = (int(rng.integers(-30, 80)), int(rng.integers(-30, 70)))
+        p2 = (p1[0] + int(rng.integers(-45, 46)), p1[1] + int(rng.integers(-45, 46)))
+        col = tuple(int(c) for c in rng.integers(0, 256, 3))
+        cv2.line(ref, p1, p2, col, 1, cv2.LINE_AA, 0)
+        oracle.line_aa(got, p1, p2, col)
+        assert np.array_equal(ref, got), (p1, p2, col)
+
+
+@pytest.mark.parametrize("channels", [1, 3])
+def test_show_optical_flow_vectors_exact(oracle, channels):
+    rng = np.random.default_rng(5 + channels)
+    w, h, ps = 200, 150, 10
+    img = rng.integers(0, 256, (h, w, 3) if channels == 3 else (h, w), dtype=np.uint8)
+    gy, gx = np.mgrid[0:h:ps, 0:w:ps]
+    vec = np.stack([gx.ravel(), gy.ravel(), rng.normal(4, 14, gx.size), rng.normal(-2, 14, gx.size)], axis=1).astype(np.float64)
+    vec[::5, 2:] = 0.0                     # vectors below min_vector_size
+    vec[3::11, :2] = -1.0; vec[3::11, 2:] = 0.0      # failed points
+    col = (10, 200, 90) if channels == 3 else (200,)
+    ref, n = cvref.show_optical_flow_vectors(img, vec, ps, 0.2, col)
+    got, m = oracle.draw_flow(img, vec, ps, 0.2, col)
+    assert n == m and n > 100
+    assert np.array_equal(ref, got)
