@@ -129,7 +129,8 @@ class ClockSampler(threading.Thread):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("MD_BENCH_SAMPLER_MS", "20")],
+                                         stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
         except Exception:
@@ -460,7 +461,11 @@ def main():
     launches = st1["kernel_launches"] - l0
     lk_work = (st1["lk_iterations"] - st0["lk_iterations"], st1["lk_levels"] - st0["lk_levels"])
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ms_ranks = [ms]
     if world > 1:
+        tl = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(tl, t)
+        ms_ranks = [float(x.item()) for x in tl]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * B * a.steps / (ms_max * 1e-3)
@@ -674,6 +679,7 @@ def main():
             "roofline": roofline, "lk_work": lk_taps, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "stream_stats": gathered, "two_streams_per_gpu": multi, "host_pinning": pinned,
             "e2e_packed_mask": e2e_packed, "graph_replays": st["graph_replays"],
+            "ms_per_step_by_rank": [m / a.steps for m in ms_ranks],
         }
         assert line["config"]["grid_points"] == P
     ctx.close()
