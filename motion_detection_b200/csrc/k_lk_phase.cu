@@ -28,10 +28,10 @@ struct PhParams {
     const uint8_t *img;
     const short2 *der;
     int16_t *ph;
-    long long *wsum;
+    LkLevelRec *wsum;
     int prev_slot0, pair0;
     int P, ps, gx, gy;
-    float half;
+    float half, min_eig;
 };
 
 // One thread = 8 consecutive plane pixels x 4 rows of one (class, pair): aligned 8-byte / 32-byte loads of the padded
@@ -186,16 +186,29 @@ __global__ void __launch_bounds__(256) k_window_sums(const PhParams q, int level
             }
         }
         __syncthreads();
-        const int per_row = (i1 - i0) * 5;
+        // one thread per point: its five window sums (40 column sums each, int64), then the level scalars k_lk_phase needs --
+        // the f32 matrix entries, the minimum-eigenvalue / determinant test of calcOpticalFlowPyrLK and 1 / det, evaluated
+        // once here instead of by every lane of the point's warp
+        const int per_row = i1 - i0;
         for (int e = threadIdx.x; e < gn * per_row; e += blockDim.x) {
-            const int g = e / per_row, e2 = e - g * per_row;
-            const int pi = e2 / 5, t = e2 - pi * 5;
-            const int *v = &ws_col[g][t][ox0 + pi * step - c_lo];
-            long long sum = 0;
-#pragma unroll 8
-            for (int c = 0; c < 40; c++) sum += v[c];
+            const int g = e / per_row, pi = e - g * per_row;
+            const int *v = &ws_col[g][0][ox0 + pi * step - c_lo];
+            long long sum[5] = {0, 0, 0, 0, 0};
+#pragma unroll 4
+            for (int c = 0; c < 40; c++) {
+#pragma unroll
+                for (int t = 0; t < 5; t++) sum[t] += v[t * (WS_COLS + 8) + c];
+            }
+            const float FLT_SCALE = 1.f / (1 << 20);
+            LkLevelRec rec;
+            rec.A11 = (float)sum[0] * FLT_SCALE; rec.A12 = (float)sum[1] * FLT_SCALE; rec.A22 = (float)sum[2] * FLT_SCALE;
+            float D;
+            rec.Dinv = lk_min_eig_ok(rec.A11, rec.A12, rec.A22, 40, q.min_eig, D) ? D : 0.f;
+            rec.C1 = sum[3]; rec.C2 = sum[4];
             const int kx = kx0 + (i0 + pi) * ncx, ky = ky0 + (jg + g) * ncx;
-            q.wsum[((((size_t)(q.pair0 + b) * q.g.nlev + level) * q.P) + (size_t)kx * q.gy + ky) * 5 + t] = sum;
+            LkLevelRec *o = q.wsum + (((size_t)(q.pair0 + b) * q.g.nlev + level) * q.P) + (size_t)kx * q.gy + ky;
+            *reinterpret_cast<float4 *>(o) = make_float4(rec.A11, rec.A12, rec.A22, rec.Dinv);
+            *reinterpret_cast<longlong2 *>(&o->C1) = make_longlong2(rec.C1, rec.C2);
         }
     }
 }
@@ -216,20 +229,60 @@ struct PhTile {
     static constexpr int JX_MAX = MD_LK_J_BOX_W - (WIN + 1) - 3;
 };
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 : (WARPS <= 4 ? 3 : (WARPS <= 7 ? 2 : 1))) k_lk_phase(const LkParams p, const __grid_constant__ LkPhaseMaps maps)
+// register fill of a lane's 10 x 5 block of the Ix / Iy window from the staged phase tile (rows unrolled by recursion: the row
+// offsets are immediates of the shared-memory loads)
+template <int R>
+__device__ __forceinline__ void lkp_fill_rows(uint32_t aX, int sh, int (&Xpk)[PhTile::TH][PhTile::NP], int (&Ypk)[PhTile::TH][PhTile::NP])
+{
+    using T = PhTile;
+    constexpr int NP = T::NP;
+    uint32_t wx[NP + 1], wy[NP + 1];
+    wx[0] = lds_u32<(R * T::PW + 0) * 4>(aX); wx[1] = lds_u32<(R * T::PW + 1) * 4>(aX); wx[2] = lds_u32<(R * T::PW + 2) * 4>(aX);
+    wx[3] = lds_u32<(R * T::PW + 3) * 4>(aX); wx[4] = lds_u32<(R * T::PW + 4) * 4>(aX); wx[5] = lds_u32<(R * T::PW + 5) * 4>(aX);
+    constexpr int YO = T::PLANE_WORDS * 4;
+    wy[0] = lds_u32<YO + (R * T::PW + 0) * 4>(aX); wy[1] = lds_u32<YO + (R * T::PW + 1) * 4>(aX); wy[2] = lds_u32<YO + (R * T::PW + 2) * 4>(aX);
+    wy[3] = lds_u32<YO + (R * T::PW + 3) * 4>(aX); wy[4] = lds_u32<YO + (R * T::PW + 4) * 4>(aX); wy[5] = lds_u32<YO + (R * T::PW + 5) * 4>(aX);
+    static_assert(NP == 5, "six words per row and plane");
+#pragma unroll
+    for (int i = 0; i < NP; i++) {
+        Xpk[R][i] = (int)__funnelshift_r(wx[i], wx[i + 1], sh);
+        Ypk[R][i] = (int)__funnelshift_r(wy[i], wy[i + 1], sh);
+    }
+    if constexpr (R + 1 < T::TH) lkp_fill_rows<R + 1>(aX, sh, Xpk, Ypk);
+}
+// the tap rows of one LK iteration
+template <int R>
+__device__ __forceinline__ void lkp_iter_rows(uint32_t rowa, int sh, const RowWords &r0, int wtop, int wbot, const int (&Xpk)[PhTile::TH][PhTile::NP],
+                                              const int (&Ypk)[PhTile::TH][PhTile::NP], int &b1lo, int &b1hi, int &b2lo, int &b2hi)
+{
+    using T = PhTile;
+    const RowWords r1 = load_row_a<(R + 1) * T::JP * 4>(rowa, sh);
+    TapLoop<0, T::TW>::template iter2<T::NP>(r0, r1, wtop, wbot, Xpk[R], Ypk[R], b1lo, b1hi, b2lo, b2hi);
+    if constexpr (R + 1 < T::TH) lkp_iter_rows<R + 1>(rowa, sh, r1, wtop, wbot, Xpk, Ypk, b1lo, b1hi, b2lo, b2hi);
+}
+
+// exactly one lane of the (converged) warp
+__device__ __forceinline__ bool lkp_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
+// One warp per CTA; a CTA tracks NPTS consecutive grid points (one grid column segment: neighbouring windows, shared L2 lines) one
+// after the other, so the barrier setup, the kernel parameters and the first window request are paid once per NPTS points and
+// the top-level window of point k + 1 is in flight while point k iterates on level 0.  One-warp CTAs keep the scheduling dynamic:
+// a CTA's shared memory goes back to the SM as soon as its own points are done.
+template <int NPTS>
+__global__ void __launch_bounds__(32, 18) k_lk_phase(const LkParams p, const __grid_constant__ LkPhaseMaps maps)
 {
     using T = PhTile;
     constexpr int WIN = T::WIN, TW = T::TW, TH = T::TH, NP = T::NP;
     extern __shared__ __align__(1024) uint8_t lkp_sm_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int k = blockIdx.x * WARPS + warp;
+    const int lane = threadIdx.x;
     const int b = blockIdx.y;
-    if (k >= p.P) return;
-    uint8_t *wbase = lkp_sm_raw + (size_t)warp * T::WARP_BYTES;
-    uint32_t *tP = reinterpret_cast<uint32_t *>(wbase + T::P_OFF);
-    uint32_t *tJ = reinterpret_cast<uint32_t *>(wbase + T::J_OFF);
-    uint64_t *barP = reinterpret_cast<uint64_t *>(wbase + T::BAR_OFF), *barJ = barP + 1;
+    const int k0 = blockIdx.x * NPTS, k1 = min(p.P, k0 + NPTS);
+    uint64_t *barP = reinterpret_cast<uint64_t *>(lkp_sm_raw + T::BAR_OFF), *barJ = barP + 1;
     const int lx = lane & 3, ly = lane >> 2;
     if (lane == 0) {
         mbar_init(barP, 1);
@@ -237,142 +290,145 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS == 1 ? 18 : WARPS == 2 ? 8 :
         mbar_fence_init();
     }
     __syncwarp();
+    // shared-window addresses of the tiles and barriers, computed once and kept opaque (the compiler otherwise re-derives the window
+    // base from SR_CgaCtaId at every use)
+    uint32_t sm0 = smem_u32(lkp_sm_raw);
+    asm volatile("" : "+r"(sm0));
+    const uint32_t aP = sm0 + T::P_OFF, aJ = sm0 + T::J_OFF, aBarP = sm0 + T::BAR_OFF, aBarJ = aBarP + 8;
     uint32_t phP = 0, phJ = 0;
-
-    const int gxi = p.ps * (k / p.gy), gyi = p.ps * (k % p.gy);       // the grid point (cpp:56-64: x outer, y inner)
-    const float2 pt = make_float2((float)gxi, (float)gyi);
+    const int top = p.g.nlev - 1;
     const int slotJ = (p.next_slot0 + b) % p.g.nslots;
     const float half = (WIN - 1) * 0.5f;
     const float FLT_SCALE = 1.f / (1 << 20);
-    float2 nxt = make_float2(0.f, 0.f);
-    int st = 1;
-    int n_iters = 0, n_levels = 0;              // measurement: work actually done for this point
+    unsigned n_iters = 0, n_levels = 0;         // measurement: work actually done by this CTA's points
 
-    // request the window (I, Ix, Iy planes of the point's phase class) of `level`
-    auto issue_P = [&](int level) {
+    // request the window (Ix, Iy planes of the point's phase class) of grid point kk at `level`; nothing is requested (and nothing
+    // will be waited for) when the window lies outside the level
+    auto issue_P = [&](int kk, int level) {
+        const int gxi = p.ps * (kk / p.gy), gyi = p.ps * (kk % p.gy);
         const float scale = lk_level_scale(level);
-        const float ppx = __fsub_rn(pt.x * scale, half), ppy = __fsub_rn(pt.y * scale, half);
+        const float ppx = __fsub_rn((float)gxi * scale, half), ppy = __fsub_rn((float)gyi * scale, half);
         const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
         if (ipx < -WIN || ipx >= p.g.lv[level].w || ipy < -WIN || ipy >= p.g.lv[level].h) return;
-        if (lane == 0) {
-            const int msk = (1 << level) - 1, sh = p.pg.lv[level].shift;
-            const int cls = ((gyi & msk) >> sh) * p.pg.lv[level].ncx + ((gxi & msk) >> sh);
-            mbar_expect_tx(barP, T::P_BYTES);
-            tma_load_5d(tP, &maps.ph[level], (ipx + MD_PH_MARGIN) & ~7, ipy + MD_PH_MARGIN, 1, cls, p.ph_pair0 + b, barP);
+        const int msk = (1 << level) - 1, sh = p.pg.lv[level].shift;
+        const int cls = ((gyi & msk) >> sh) * p.pg.lv[level].ncx + ((gxi & msk) >> sh);
+        if (lkp_elect_one()) {
+            mbar_expect_tx_a(aBarP, T::P_BYTES);
+            tma_load_5d_a(aP, &maps.ph[level], (ipx + MD_PH_MARGIN) & ~7, ipy + MD_PH_MARGIN, 1, cls, p.ph_pair0 + b, aBarP);
         }
     };
-    issue_P(p.g.nlev - 1);
+    // the window after (k, level) in processing order: the next finer level of k, or the top level of k + 1
+    auto issue_next_P = [&](int k, int level) {
+        if (level > 0) issue_P(k, level - 1);
+        else if (k + 1 < k1) issue_P(k + 1, top);
+    };
+    if (k0 < k1) issue_P(k0, top);
 
-    for (int level = p.g.nlev - 1; level >= 0; level--) {
-        const int Lw = p.g.lv[level].w, Lh = p.g.lv[level].h;
-        const float scale = lk_level_scale(level);
-        float ppx = pt.x * scale, ppy = pt.y * scale;
-        LkIterState s;
-        if (level == p.g.nlev - 1) { s.npx = ppx; s.npy = ppy; }
-        else { s.npx = nxt.x * 2.f; s.npy = nxt.y * 2.f; }
-        nxt = make_float2(s.npx, s.npy);
-        ppx = __fsub_rn(ppx, half); ppy = __fsub_rn(ppy, half);
-        const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
-        if (ipx < -WIN || ipx >= Lw || ipy < -WIN || ipy >= Lh) {
-            if (level == 0) st = 0;
-            else issue_P(level - 1);
-            continue;
-        }
-        // ---- request the next-frame tile around the initial guess; it lands while the window sums are formed ---------
-        s.npx = __fsub_rn(s.npx, half); s.npy = __fsub_rn(s.npy, half);
-        int tx0 = 0, ty0 = 0;
-        bool j_ok = false;
-        {
-            const int inx = __float2int_rd(s.npx), iny = __float2int_rd(s.npy);
-            if (!(inx < -WIN || inx >= Lw || iny < -WIN || iny >= Lh)) {
-                tx0 = ((inx - MD_LK_J_MARGIN_X + p.g.padx) & ~15) - p.g.padx; ty0 = iny - MD_LK_J_MARGIN_Y;
-                j_ok = true;
-                __syncwarp();      // every lane is done with the J tile of the previous level
-                if (lane == 0) {
-                    mbar_expect_tx(barJ, T::J_BYTES);
-                    tma_load_3d(tJ, &maps.imgJ[level], tx0 + p.g.padx, ty0 + p.g.pady, slotJ, barJ);
-                }
-            }
-        }
+    for (int k = k0; k < k1; k++) {
+        const int gxi = p.ps * (k / p.gy), gyi = p.ps * (k % p.gy);       // the grid point (cpp:56-64: x outer, y inner)
+        const float2 pt = make_float2((float)gxi, (float)gyi);
+        float2 nxt = make_float2(0.f, 0.f);
+        int st = 1;
+        const LkLevelRec *recs = p.wsum + ((size_t)(p.ph_pair0 + b) * p.g.nlev) * p.P + k;
 
-        // ---- derivative window from the phase planes into registers; the window sums come precomputed ---------------
-        mbar_wait(barP, phP); phP ^= 1;
-        int Xpk[TH][NP], Ypk[TH][NP];
-        {
-            const int e0 = ((ipx + MD_PH_MARGIN) & 7) + TW * lx;       // first tap column of this lane inside the box
-            const int sh = (e0 & 1) * 16;
-            const uint32_t *pX = tP + (TH * ly) * T::PW + (e0 >> 1), *pY = pX + T::PLANE_WORDS;
-#pragma unroll
-            for (int r = 0; r < TH; r++) {
-                uint32_t wx[NP + 1], wy[NP + 1];
-#pragma unroll
-                for (int i = 0; i <= NP; i++) { wx[i] = pX[r * T::PW + i]; wy[i] = pY[r * T::PW + i]; }
-#pragma unroll
-                for (int i = 0; i < NP; i++) {
-                    Xpk[r][i] = (int)__funnelshift_r(wx[i], wx[i + 1], sh);
-                    Ypk[r][i] = (int)__funnelshift_r(wy[i], wy[i + 1], sh);
-                }
-            }
-        }
-        const long long *ws = p.wsum + ((((size_t)(p.ph_pair0 + b) * p.g.nlev + level) * p.P) + k) * 5;
-        const long long s11 = __ldg(ws), s12 = __ldg(ws + 1), s22 = __ldg(ws + 2), C1 = __ldg(ws + 3), C2 = __ldg(ws + 4);
-        __syncwarp();                       // the phase tile is consumed: prefetch the next level's
-        if (level > 0) issue_P(level - 1);
-        if (j_ok) { mbar_wait(barJ, phJ); phJ ^= 1; }
-
-        const float A11 = (float)s11 * FLT_SCALE;
-        const float A12 = (float)s12 * FLT_SCALE;
-        const float A22 = (float)s22 * FLT_SCALE;
-        float D;
-        if (!lk_min_eig_ok(A11, A12, A22, WIN, p.min_eig, D)) {
-            if (level == 0) st = 0;
-            continue;
-        }
-        s.pdx = 0.f; s.pdy = 0.f;
-        n_levels++;
-        for (int j = 0; j < p.max_iters; j++) {
-            const int inx = __float2int_rd(s.npx), iny = __float2int_rd(s.npy);
-            if (inx < -WIN || inx >= Lw || iny < -WIN || iny >= Lh) {
+        for (int level = top; level >= 0; level--) {
+            const int Lw = p.g.lv[level].w, Lh = p.g.lv[level].h;
+            const float scale = lk_level_scale(level);
+            float ppx = pt.x * scale, ppy = pt.y * scale;
+            LkIterState s;
+            if (level == top) { s.npx = ppx; s.npy = ppy; }
+            else { s.npx = nxt.x * 2.f; s.npy = nxt.y * 2.f; }
+            nxt = make_float2(s.npx, s.npy);
+            ppx = __fsub_rn(ppx, half); ppy = __fsub_rn(ppy, half);
+            const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
+            if (ipx < -WIN || ipx >= Lw || ipy < -WIN || ipy >= Lh) {
                 if (level == 0) st = 0;
-                break;
+                issue_next_P(k, level);
+                continue;
             }
-            int w00, w01, w10, w11;
-            lk_weights(__fsub_rn(s.npx, (float)inx), __fsub_rn(s.npy, (float)iny), w00, w01, w10, w11);
-            n_iters++;
-            // ---- restage the J tile when the window drifts out of it (warp-uniform, rare) -----------------------------
-            if (inx < tx0 || inx - tx0 > T::JX_MAX || iny < ty0 || iny - ty0 > 2 * MD_LK_J_MARGIN_Y) {
-                tx0 = ((inx - MD_LK_J_MARGIN_X + p.g.padx) & ~15) - p.g.padx; ty0 = iny - MD_LK_J_MARGIN_Y;
-                __syncwarp();
-                if (lane == 0) {
-                    mbar_expect_tx(barJ, T::J_BYTES);
-                    tma_load_3d(tJ, &maps.imgJ[level], tx0 + p.g.padx, ty0 + p.g.pady, slotJ, barJ);
+            // the level scalars (k_window_sums); they land while the window is copied into registers
+            const LkLevelRec *rec = recs + (size_t)level * p.P;
+            const float4 A = __ldg(reinterpret_cast<const float4 *>(rec));
+            const longlong2 C = __ldg(reinterpret_cast<const longlong2 *>(&rec->C1));
+            // ---- request the next-frame tile around the initial guess; it lands while the window is copied ------------------
+            s.npx = __fsub_rn(s.npx, half); s.npy = __fsub_rn(s.npy, half);
+            int tx0 = 0, ty0 = 0;
+            bool j_ok = false;
+            {
+                const int inx = __float2int_rd(s.npx), iny = __float2int_rd(s.npy);
+                if (!(inx < -WIN || inx >= Lw || iny < -WIN || iny >= Lh)) {
+                    tx0 = ((inx - MD_LK_J_MARGIN_X + p.g.padx) & ~15) - p.g.padx; ty0 = iny - MD_LK_J_MARGIN_Y;
+                    j_ok = true;
+                    __syncwarp();      // every lane is done with the J tile of the previous level
+                    if (lkp_elect_one()) {
+                        mbar_expect_tx_a(aBarJ, T::J_BYTES);
+                        tma_load_3d_a(aJ, &maps.imgJ[level], tx0 + p.g.padx, ty0 + p.g.pady, slotJ, aBarJ);
+                    }
                 }
-                mbar_wait(barJ, phJ); phJ ^= 1;
             }
-            const int c0 = (inx - tx0) + TW * lx, wb = c0 >> 2, sh = (c0 & 3) * 8;
-            const uint32_t *rowp = tJ + ((iny - ty0) + TH * ly) * T::JP;
-            const int wtop = (int)__byte_perm((uint32_t)w00, (uint32_t)w01, 0x5410);
-            const int wbot = (int)__byte_perm((uint32_t)w10, (uint32_t)w11, 0x5410);
-            int b1lo = 0, b1hi = 0, b2lo = 0, b2hi = 0;
-            RowWords r0 = load_row(rowp, wb, sh);
-#pragma unroll
-            for (int r = 0; r < TH; r++) {
-                const RowWords r1 = load_row(rowp + (r + 1) * T::JP, wb, sh);
-                TapLoop<0, TW>::template iter2<NP>(r0, r1, wtop, wbot, Xpk[r], Ypk[r], b1lo, b1hi, b2lo, b2hi);
-                r0 = r1;
+
+            // ---- derivative window from the phase planes into registers ----------------------------------------------------
+            mbar_wait_a(aBarP, phP); phP ^= 1;
+            int Xpk[TH][NP], Ypk[TH][NP];
+            {
+                const int e0 = ((ipx + MD_PH_MARGIN) & 7) + TW * lx;       // first tap column of this lane inside the box
+                const int sh = (e0 & 1) * 16;
+                const uint32_t aX = aP + ((TH * ly) * T::PW + (e0 >> 1)) * 4;
+                lkp_fill_rows<0>(aX, sh, Xpk, Ypk);
             }
-            const int b1 = b1hi * 256 + b1lo, b2 = b2hi * 256 + b2lo;
-            // sum (J - I) Ix = sum J Ix - sum I Ix, exactly, in 64-bit integers; one rounding to f32
-            const float fb1 = (float)(warp_sum_exact_i64(b1) - C1) * FLT_SCALE;
-            const float fb2 = (float)(warp_sum_exact_i64(b2) - C2) * FLT_SCALE;
-            if (lk_update(A11, A12, A22, D, fb1, fb2, half, j, p.eps2, s, nxt)) break;
+            __syncwarp();                       // the phase tile is consumed: prefetch the next window
+            issue_next_P(k, level);
+            if (j_ok) { mbar_wait_a(aBarJ, phJ); phJ ^= 1; }
+
+            const float A11 = A.x, A12 = A.y, A22 = A.z, D = A.w;
+            const long long C1 = C.x, C2 = C.y;
+            if (D == 0.f) {                     // minimum-eigenvalue / determinant test failed (k_window_sums)
+                if (level == 0) st = 0;
+                continue;
+            }
+            s.pdx = 0.f; s.pdy = 0.f;
+            n_levels++;
+            for (int j = 0; j < p.max_iters; j++) {
+                const int inx = __float2int_rd(s.npx), iny = __float2int_rd(s.npy);
+                if (inx < -WIN || inx >= Lw || iny < -WIN || iny >= Lh) {
+                    if (level == 0) st = 0;
+                    break;
+                }
+                int w00, w01, w10, w11;
+                lk_weights(__fsub_rn(s.npx, (float)inx), __fsub_rn(s.npy, (float)iny), w00, w01, w10, w11);
+                n_iters++;
+                // ---- restage the J tile when the window drifts out of it (warp-uniform, rare) -------------------------------
+                if (inx < tx0 || inx - tx0 > T::JX_MAX || iny < ty0 || iny - ty0 > 2 * MD_LK_J_MARGIN_Y) {
+                    tx0 = ((inx - MD_LK_J_MARGIN_X + p.g.padx) & ~15) - p.g.padx; ty0 = iny - MD_LK_J_MARGIN_Y;
+                    __syncwarp();
+                    if (lkp_elect_one()) {
+                        mbar_expect_tx_a(aBarJ, T::J_BYTES);
+                        tma_load_3d_a(aJ, &maps.imgJ[level], tx0 + p.g.padx, ty0 + p.g.pady, slotJ, aBarJ);
+                    }
+                    mbar_wait_a(aBarJ, phJ); phJ ^= 1;
+                }
+                const int c0 = (inx - tx0) + TW * lx, wb = c0 >> 2, sh = (c0 & 3) * 8;
+                const uint32_t rowa = aJ + (((iny - ty0) + TH * ly) * T::JP + wb) * 4;
+                const int wtop = (int)__byte_perm((uint32_t)w00, (uint32_t)w01, 0x5410);
+                const int wbot = (int)__byte_perm((uint32_t)w10, (uint32_t)w11, 0x5410);
+                int b1lo = 0, b1hi = 0, b2lo = 0, b2hi = 0;
+                lkp_iter_rows<0>(rowa, sh, load_row_a<0>(rowa, sh), wtop, wbot, Xpk, Ypk, b1lo, b1hi, b2lo, b2hi);
+                const int b1 = b1hi * 256 + b1lo, b2 = b2hi * 256 + b2lo;
+                // sum (J - I) Ix = sum J Ix - sum I Ix, exactly, in 64-bit integers; one rounding to f32
+                const float fb1 = (float)(warp_sum_exact_i64(b1) - C1) * FLT_SCALE;
+                const float fb2 = (float)(warp_sum_exact_i64(b2) - C2) * FLT_SCALE;
+                if (lk_update(A11, A12, A22, D, fb1, fb2, half, j, p.eps2, s, nxt)) break;
+            }
+        }
+        if (lane == 0) {
+            p.next[(size_t)b * p.P + k] = nxt;
+            p.status[(size_t)b * p.P + k] = (uint8_t)st;
         }
     }
-    if (lane == 0) {
-        p.next[(size_t)b * p.P + k] = nxt;
-        p.status[(size_t)b * p.P + k] = (uint8_t)st;
-        // 64 striped counter pairs: one hot address would serialise the atomics of every finishing warp
-        if (p.stat_iters) { unsigned long long *c = p.stat_iters + 2 * (k & 63); atomicAdd(c, (unsigned long long)n_iters); atomicAdd(c + 1, (unsigned long long)n_levels); }
+    // 64 striped counter pairs: one hot address would serialise the atomics of every finishing warp
+    if (lane == 0 && p.stat_iters) {
+        unsigned long long *c = p.stat_iters + 2 * (blockIdx.x & 63);
+        atomicAdd(c, (unsigned long long)n_iters); atomicAdd(c + 1, (unsigned long long)n_levels);
     }
 }
 
@@ -383,7 +439,7 @@ cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1
     PhParams q;
     q.g = p.g; q.pg = p.pg; q.img = p.img; q.der = p.der; q.ph = p.ph; q.prev_slot0 = p.prev_slot0; q.pair0 = p.ph_pair0;
     q.wsum = p.wsum; q.P = p.P; q.ps = p.ps; q.gy = p.gy; q.gx = p.P / p.gy;
-    q.half = (p.win - 1) * 0.5f;
+    q.half = (p.win - 1) * 0.5f; q.min_eig = p.min_eig;
     for (int l = l0; l <= l1 && l < p.g.nlev; l++) {
         const PhaseLevel &PL = p.pg.lv[l];
         const int step = p.ps >> PL.shift;
@@ -408,21 +464,20 @@ cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pair
         cudaError_t e0 = launch_lk_planes(p, pairs, s);
         if (e0 != cudaSuccess) return e0;
     }
-    static int warps_env = -1;
-    if (warps_env < 0) { const char *e = getenv("MD_LK_WARPS"); warps_env = e ? atoi(e) : 0; }
-    auto go = [&](auto kern, int WARPS) {
-        const size_t smem = (size_t)WARPS * PhTile::WARP_BYTES + 128;
+    static int npts_env = -1;
+    if (npts_env < 0) { const char *e = getenv("MD_LK_NPTS"); npts_env = e ? atoi(e) : 0; }
+    auto go = [&](auto kern, int NPTS) {
+        const size_t smem = (size_t)PhTile::WARP_BYTES + 128;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        dim3 grid((p.P + WARPS - 1) / WARPS, pairs);
-        kern<<<grid, WARPS * 32, smem, s>>>(p, *maps);
+        dim3 grid((p.P + NPTS - 1) / NPTS, pairs);
+        kern<<<grid, 32, smem, s>>>(p, *maps);
         MD_COUNT_LAUNCH(1);
         return cudaGetLastError();
     };
-    // One warp per CTA (14 CTAs per SM): a CTA's shared memory is released as soon as its point is done instead of when the
-    // slowest of several points is.  Measured on the default bench (LK ms per 16 pairs): 14 warps per CTA 4.59, 7: 3.92,
-    // 4: 3.94, 2: 3.74, 1: 3.54.  MD_LK_WARPS=2|7 selects the other builds (tuning aid).
-    if (warps_env == 7) return go(k_lk_phase<7>, 7);
-    if (warps_env == 2) return go(k_lk_phase<2>, 2);
-    return go(k_lk_phase<1>, 1);
+    // points per one-warp CTA (MD_LK_NPTS = 1 | 4 | 16 selects the other builds: tuning aid)
+    if (npts_env == 1) return go(k_lk_phase<1>, 1);
+    if (npts_env == 4) return go(k_lk_phase<4>, 4);
+    if (npts_env == 16) return go(k_lk_phase<16>, 16);
+    return go(k_lk_phase<8>, 8);
 }

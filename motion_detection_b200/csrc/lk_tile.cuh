@@ -32,6 +32,27 @@ __device__ __forceinline__ RowWords load_row(const uint32_t *row, int wb, int sh
     r.s[2] = r.a[2] >> 8;
     return r;
 }
+// the same from a 32-bit shared-window byte address (word wb of the row at `row`); volatile: ordered after the mbarrier wait
+template <int OFF>
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int ROW_OFF>
+__device__ __forceinline__ RowWords load_row_a(uint32_t addr, int sh)
+{
+    const uint32_t w0 = lds_u32<ROW_OFF>(addr), w1 = lds_u32<ROW_OFF + 4>(addr), w2 = lds_u32<ROW_OFF + 8>(addr), w3 = lds_u32<ROW_OFF + 12>(addr);
+    RowWords r;
+    r.a[0] = __funnelshift_r(w0, w1, sh);
+    r.a[1] = __funnelshift_r(w1, w2, sh);
+    r.a[2] = __funnelshift_r(w2, w3, sh);
+    r.s[0] = __funnelshift_r(r.a[0], r.a[1], 8);
+    r.s[1] = __funnelshift_r(r.a[1], r.a[2], 8);
+    r.s[2] = r.a[2] >> 8;
+    return r;
+}
 // sum over the pixel pair (i, i+1) of a row: wpair.lo * p[i] + wpair.hi * p[i+1] + c   (i compile-time)
 template <int I>
 __device__ __forceinline__ int row_pair(const RowWords &r, int wpair, int c)

@@ -124,7 +124,7 @@ static bool ensure_phase(md_ctx *ctx)
     for (int l = 0; l < ctx->g.nlev; l++)
         if ((ctx->cfg.pixel_step >> pg.lv[l].shift) > 470) return false;              // k_window_sums: one lattice step must fit its 512-column block
     if (cudaMalloc((void **)&ctx->d_phase, bytes) != cudaSuccess) { cudaGetLastError(); ctx->d_phase = nullptr; return false; }
-    if (cudaMalloc((void **)&ctx->d_wsum, sizeof(long long) * 5 * (size_t)ctx->P * ctx->g.nlev * ctx->cfg.max_batch) != cudaSuccess) {
+    if (cudaMalloc((void **)&ctx->d_wsum, sizeof(LkLevelRec) * (size_t)ctx->P * ctx->g.nlev * ctx->cfg.max_batch) != cudaSuccess) {
         cudaGetLastError();
         cudaFree(ctx->d_phase); ctx->d_phase = nullptr; ctx->d_wsum = nullptr;
         return false;

@@ -74,6 +74,11 @@ struct alignas(64) LkPhaseMaps {
     int valid;
 };
 
+// Per (pair, level, grid point) scalars of the LK normal equations, written by k_window_sums and read by k_lk_phase: the f32 matrix
+// entries (window sums * 2^-20), the reciprocal determinant (0 = the level fails calcOpticalFlowPyrLK's minimum-eigenvalue / determinant
+// test and is skipped) and the exact integer sums of I * Ix, I * Iy.  32 bytes, two 16-byte loads.
+struct alignas(16) LkLevelRec { float A11, A12, A22, Dinv; long long C1, C2; };
+
 struct LkParams {
     PyrGeom g;
     const uint8_t *img;      // slot 0 image arena
@@ -90,7 +95,7 @@ struct LkParams {
     // grid mode with phase planes (pts_in == nullptr): pair b uses arena ph + b * pg.pair_elems
     PhaseGeom pg;
     int16_t *ph;
-    long long *wsum;         // [max_batch][nlev][P][5] window sums A11, A12, A22, sum I*Ix, sum I*Iy (k_window_sums)
+    LkLevelRec *wsum;        // [max_batch][nlev][P] per-point level scalars (k_window_sums)
     int ph_pair0;            // pair b of this launch uses arena ph_pair0 + b
     int ph_ready;            // 1 = the planes were already computed (launch_lk_planes on another stream)
     unsigned long long *stat_iters;   // [64][2] nullable, striped: iterations executed, levels iterated (summed over points)
@@ -207,7 +212,7 @@ struct md_ctx {
     int mask_user_pitch;
     PhaseGeom pg;
     int16_t *d_phase;     // [max_batch] pair arenas of phase planes, allocated on the first grid-mode LK call
-    long long *d_wsum;    // [max_batch][nlev][P][5] per-point window sums
+    LkLevelRec *d_wsum;   // [max_batch][nlev][P] per-point level scalars
     int phase_state;      // 0 = not tried, 1 = ready, -1 = not used (not worth it / allocation failed)
     void *sub_ws;         // fitSubspace workspace (k_subspace.cu)
     void *mad_ws;         // findOutliers workspace (k_mad.cu)

@@ -89,6 +89,29 @@ __device__ __forceinline__ void tma_load_5d(void *smem_dst, const CUtensorMap *m
     asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
 }
+// the same primitives on 32-bit shared-window addresses the caller computed once (smem_u32) and keeps in a register
+__device__ __forceinline__ void mbar_expect_tx_a(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d_a(uint32_t smem_dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_dst), "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_a(uint32_t smem_dst, const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(smem_dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(bar) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");

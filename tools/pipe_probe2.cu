@@ -10,10 +10,11 @@
 constexpr int TW = 10, TH = 5, NP = 5, JP = 20;
 
 // variants of TapLoop::iter2 (two taps per step)
-template <int MODE, int I>
+template <int MODEX, int I>
 __device__ __forceinline__ void pair_step(const RowWords &r0, const RowWords &r1, int wtop, int wbot, const int (&Xpk)[NP], const int (&Ypk)[NP],
                                           int &b1lo, int &b1hi, int &b2lo, int &b2hi)
 {
+    constexpr int MODE = MODEX >= 10 ? 0 : MODEX;
     const int v0 = row_pair<I>(r1, wbot, row_pair<I>(r0, wtop, 1 << (W_BITS - 5 - 1)));
     const int v1 = row_pair<I + 1>(r1, wbot, row_pair<I + 1>(r0, wtop, 1 << (W_BITS - 5 - 1)));
     const int xp = Xpk[I >> 1], yp = Ypk[I >> 1];
@@ -55,7 +56,9 @@ __global__ void __launch_bounds__(32, 18) probe(uint32_t *out, long long *clk, u
     int wtop = seed | 0x00010001, wbot = (seed >> 3) | 0x00020002;
     int b1lo = 0, b1hi = 0, b2lo = 0, b2hi = 0;
     int inx = seed & 15, iny = 1;
+    uint32_t ex[4] = {seed, seed * 3, seed * 5, seed * 7};
     __syncwarp();
+    unsigned long long g0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
     const long long t0 = clock64();
     for (int it = 0; it < iters; it++) {
         const int c0 = inx + TW * lx, wb = c0 >> 2, sh = (c0 & 3) * 8;
@@ -67,11 +70,29 @@ __global__ void __launch_bounds__(32, 18) probe(uint32_t *out, long long *clk, u
             row_step<MODE>(r0, r1, wtop, wbot, Xpk[r], Ypk[r], b1lo, b1hi, b2lo, b2hi);
             r0 = r1;
         }
+        if (MODE == 10) {
+#pragma unroll
+            for (int e = 0; e < 100; e++) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(ex[e & 3]) : "r"(wtop), "r"(wbot));
+        }
+        if (MODE == 11) {
+#pragma unroll
+            for (int e = 0; e < 50; e++) ex[e & 3] ^= tJ[(iny + e) * 3 + lane];
+        }
+        if (MODE == 12) {
+#pragma unroll
+            for (int e = 0; e < 50; e++) asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(ex[e & 3]) : "r"(wtop), "r"(wbot));
+        }
+        if (MODE == 13) {
+#pragma unroll
+            for (int e = 0; e < 100; e++) asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(ex[e & 3]) : "r"(wtop), "r"(wbot));
+        }
         inx = (inx + (b1lo & 1) + 1) & 15; iny = (b2hi & 1) + 1;
         wtop += b1hi & 1; wbot ^= b2lo & 2;
     }
     const long long t1 = clock64();
-    out[blockIdx.x * 32 + lane] = b1lo + b1hi + b2lo + b2hi;
+    unsigned long long g1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    if (lane == 0 && blockIdx.x == 0) clk[148 * 32] = (long long)(g1 - g0);
+    out[blockIdx.x * 32 + lane] = b1lo + b1hi + b2lo + b2hi + ex[0] + ex[1] + ex[2] + ex[3];
     if (lane == 0) clk[blockIdx.x] = t1 - t0;
 }
 
@@ -89,14 +110,20 @@ void run(const char *name, int instr, uint32_t *out, long long *clk, int ctas_pe
     for (int i = 0; i < blocks; i++) avg += (double)h[i];
     avg /= blocks;
     const double its = (double)iters * ctas_per_sm / 4.0;                  // warp iterations per SM sub-partition
+    long long ns; cudaMemcpy(&ns, clk + 148 * 32, 8, cudaMemcpyDeviceToHost);
+    printf("[%.0f MHz] ", 1e3 * (double)h[0] / (double)ns);
     printf("%-44s warps/SM %2d  %7.1f clk / iteration / SMSP  (~%d instr -> IPC %.3f)\n", name, ctas_per_sm, avg / its, instr, instr * its / avg);
 }
 
 int main()
 {
     uint32_t *out; long long *clk;
-    cudaMalloc(&out, 148 * 32 * 32 * 4); cudaMalloc(&clk, 148 * 32 * 8);
-    for (int wps : {4, 8, 16, 18}) {
+    cudaMalloc(&out, 148 * 32 * 32 * 4); cudaMalloc(&clk, (148 * 32 + 1) * 8);
+    for (int wps : {8, 18}) {
+        run<10>("current + 100 LOP3", 60 + 375, out, clk, wps);
+        run<13>("current + 100 SHF", 60 + 375, out, clk, wps);
+        run<11>("current + 50 LDS + 50 LOP3", 60 + 375, out, clk, wps);
+        run<12>("current + 50 IMAD", 60 + 325, out, clk, wps);
         run<0>("current: 4 IDP + 2 SHF + PRMT + 4 IDP", 60 + 275, out, clk, wps);
         run<1>("4 IDP + PRMT + AND + 4 IDP", 60 + 250, out, clk, wps);
         run<2>("4 IDP + PRMT + 4 IDP (bound, wrong result)", 60 + 225, out, clk, wps);
