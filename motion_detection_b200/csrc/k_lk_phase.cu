@@ -304,8 +304,7 @@ __global__ void __launch_bounds__(32, 18) k_lk_phase(const LkParams p, const __g
 
     // request the window (Ix, Iy planes of the point's phase class) of grid point kk at `level`; nothing is requested (and nothing
     // will be waited for) when the window lies outside the level
-    auto issue_P = [&](int kk, int level) {
-        const int gxi = p.ps * (kk / p.gy), gyi = p.ps * (kk % p.gy);
+    auto issue_P = [&](int gxi, int gyi, int level) {
         const float scale = lk_level_scale(level);
         const float ppx = __fsub_rn((float)gxi * scale, half), ppy = __fsub_rn((float)gyi * scale, half);
         const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
@@ -318,20 +317,24 @@ __global__ void __launch_bounds__(32, 18) k_lk_phase(const LkParams p, const __g
         }
     };
     // the window after (k, level) in processing order: the next finer level of k, or the top level of k + 1
+    // the grid point (cpp:56-64: x outer, y inner) and its successor in the CTA, stepped without divisions
+    int kx = k0 / p.gy, ky = k0 - kx * p.gy;
+    int gxi = p.ps * kx, gyi = p.ps * ky, gxn, gyn;
     auto issue_next_P = [&](int k, int level) {
-        if (level > 0) issue_P(k, level - 1);
-        else if (k + 1 < k1) issue_P(k + 1, top);
+        if (level > 0) issue_P(gxi, gyi, level - 1);
+        else if (k + 1 < k1) issue_P(gxn, gyn, top);
     };
-    if (k0 < k1) issue_P(k0, top);
+    if (k0 < k1) issue_P(gxi, gyi, top);
 
-    for (int k = k0; k < k1; k++) {
-        const int gxi = p.ps * (k / p.gy), gyi = p.ps * (k % p.gy);       // the grid point (cpp:56-64: x outer, y inner)
+    for (int k = k0; k < k1; k++, gxi = gxn, gyi = gyn) {
+        if (++ky == p.gy) { ky = 0; gxn = gxi + p.ps; gyn = 0; }
+        else { gxn = gxi; gyn = gyi + p.ps; }
         const float2 pt = make_float2((float)gxi, (float)gyi);
         float2 nxt = make_float2(0.f, 0.f);
         int st = 1;
-        const LkLevelRec *recs = p.wsum + ((size_t)(p.ph_pair0 + b) * p.g.nlev) * p.P + k;
+        const LkLevelRec *rec = p.wsum + ((size_t)(p.ph_pair0 + b) * p.g.nlev + top) * p.P + k;      // the level scalars (k_window_sums)
 
-        for (int level = top; level >= 0; level--) {
+        for (int level = top; level >= 0; level--, rec -= p.P) {
             const int Lw = p.g.lv[level].w, Lh = p.g.lv[level].h;
             const float scale = lk_level_scale(level);
             float ppx = pt.x * scale, ppy = pt.y * scale;
@@ -346,8 +349,7 @@ __global__ void __launch_bounds__(32, 18) k_lk_phase(const LkParams p, const __g
                 issue_next_P(k, level);
                 continue;
             }
-            // the level scalars (k_window_sums); they land while the window is copied into registers
-            const LkLevelRec *rec = recs + (size_t)level * p.P;
+            // the level scalars land while the window is copied into registers
             const float4 A = __ldg(reinterpret_cast<const float4 *>(rec));
             const longlong2 C = __ldg(reinterpret_cast<const longlong2 *>(&rec->C1));
             // ---- request the next-frame tile around the initial guess; it lands while the window is copied ------------------
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(32, 18) k_lk_phase(const LkParams p, const __g
                 const int wbot = (int)__byte_perm((uint32_t)w10, (uint32_t)w11, 0x5410);
                 int b1lo = 0, b1hi = 0, b2lo = 0, b2hi = 0;
                 lkp_iter_rows<0>(rowa, sh, load_row_a<0>(rowa, sh), wtop, wbot, Xpk, Ypk, b1lo, b1hi, b2lo, b2hi);
-                const int b1 = b1hi * 256 + b1lo, b2 = b2hi * 256 + b2lo;
+                const int b1 = iter2_total(b1lo, b1hi), b2 = iter2_total(b2lo, b2hi);
                 // sum (J - I) Ix = sum J Ix - sum I Ix, exactly, in 64-bit integers; one rounding to f32
                 const float fb1 = (float)(warp_sum_exact_i64(b1) - C1) * FLT_SCALE;
                 const float fb2 = (float)(warp_sum_exact_i64(b2) - C2) * FLT_SCALE;

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) k_lk_tma(const LkParam
             const uint32_t *rowp = tJ + ((iny - ty0) + TH * ly) * T::JP;
             const int wtop = (int)__byte_perm((uint32_t)w00, (uint32_t)w01, 0x5410);
             const int wbot = (int)__byte_perm((uint32_t)w10, (uint32_t)w11, 0x5410);
-            int b1lo = -c1, b1hi = 0, b2lo = -c2, b2hi = 0;
+            int b1lo = 0, b1hi = 0, b2lo = 0, b2hi = 0;
             RowWords r0 = load_row(rowp, wb, sh);
 #pragma unroll
             for (int r = 0; r < TH; r++) {
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS) k_lk_tma(const LkParam
                 TapLoop<0, TW>::template iter2<NP>(r0, r1, wtop, wbot, Xpk[r], Ypk[r], b1lo, b1hi, b2lo, b2hi);
                 r0 = r1;
             }
-            const int b1 = b1hi * 256 + b1lo, b2 = b2hi * 256 + b2lo;
+            const int b1 = iter2_total(b1lo, b1hi) - c1, b2 = iter2_total(b2lo, b2hi) - c2;      // sum (J - I) Ix of this lane's taps
             const float fb1 = warp_sum_exact_f32(b1) * FLT_SCALE;
             const float fb2 = warp_sum_exact_f32(b2) * FLT_SCALE;
             if (lk_update(A11, A12, A22, D, fb1, fb2, half, j, p.eps2, s, nxt)) break;

@@ -98,17 +98,18 @@ struct TapLoop {
         b2 += q * ((I & 1) ? (yp >> 16) : (int)(short)yp);
         if constexpr (I + 1 < TW) TapLoop<I + 1, TW>::template iter<NP>(r0, r1, wtop, wbot, Xpk, Ypk, b1, b2);
     }
-    // Same sums, two taps at a time, without unpacking the s16 pairs: q = v >> 9 with v < 2^22, so with u = v >> 1 the low
-    // 8 bits of q are byte 1 of u and the high 5 bits are byte 2 of u.  One PRMT gathers (ql_i, ql_i+1, qh_i, qh_i+1) and
-    // dp2a.lo / dp2a.hi against the packed (Ix_i, Ix_i+1) give sum ql*Ix and sum qh*Ix:  sum q*Ix = 256 * hi + lo.
+    // Same sums, two taps at a time, without unpacking the s16 pairs and without shifting the samples: q = v >> 9 with v < 2^22, so
+    // byte 2 of v is q >> 7 and byte 1 of v is 2 * (q & 127) + (bit 8 of v).  One PRMT gathers (v0.b1, v1.b1, v0.b2, v1.b2), one AND
+    // clears the two stray bits, and dp2a.lo / dp2a.hi against the packed (Ix_i, Ix_i+1) give lo = sum 2 (q & 127) Ix (even) and
+    // hi = sum (q >> 7) Ix:  sum q * Ix = 128 * hi + lo / 2, exactly.
     template <int NP>
     static __device__ __forceinline__ void iter2(const RowWords &r0, const RowWords &r1, int wtop, int wbot, const int (&Xpk)[NP],
                                                  const int (&Ypk)[NP], int &b1lo, int &b1hi, int &b2lo, int &b2hi)
     {
         static_assert((I & 1) == 0, "pairs start at even taps");
-        const int u0 = row_pair<I>(r1, wbot, row_pair<I>(r0, wtop, 1 << (W_BITS - 5 - 1))) >> 1;
-        const int u1 = row_pair<I + 1>(r1, wbot, row_pair<I + 1>(r0, wtop, 1 << (W_BITS - 5 - 1))) >> 1;
-        const uint32_t qb = __byte_perm((uint32_t)u0, (uint32_t)u1, 0x6251);
+        const int v0 = row_pair<I>(r1, wbot, row_pair<I>(r0, wtop, 1 << (W_BITS - 5 - 1)));
+        const int v1 = row_pair<I + 1>(r1, wbot, row_pair<I + 1>(r0, wtop, 1 << (W_BITS - 5 - 1)));
+        const uint32_t qb = __byte_perm((uint32_t)v0, (uint32_t)v1, 0x6251) & 0xfffffefeu;
         const int xp = Xpk[I >> 1], yp = Ypk[I >> 1];
         b1lo = dp2a_lo(xp, qb, b1lo); b1hi = dp2a_hi(xp, qb, b1hi);
         b2lo = dp2a_lo(yp, qb, b2lo); b2hi = dp2a_hi(yp, qb, b2hi);
@@ -127,6 +128,9 @@ struct RowStore {
         } else if constexpr (R + 1 < TH) RowStore<R + 1, TH, NP>::put(r, Xpk, Ypk, Xr, Yr);
     }
 };
+
+// sum q * Ix from the two accumulators of TapLoop::iter2
+__device__ __forceinline__ int iter2_total(int lo, int hi) { return hi * 128 + (lo >> 1); }
 
 // exact warp sum of per-lane int32 partial sums (|v| < 2^31): two REDUX adds on the 16-bit halves, one rounding to f32
 __device__ __forceinline__ long long warp_sum_exact_i64(int v)
