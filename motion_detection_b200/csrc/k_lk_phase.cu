@@ -231,24 +231,26 @@ struct PhTile {
 
 // register fill of a lane's 10 x 5 block of the Ix / Iy window from the staged phase tile (rows unrolled by recursion: the row
 // offsets are immediates of the shared-memory loads)
-template <int R>
-__device__ __forceinline__ void lkp_fill_rows(uint32_t aX, int sh, int (&Xpk)[PhTile::TH][PhTile::NP], int (&Ypk)[PhTile::TH][PhTile::NP])
+template <int R, bool ODD>
+__device__ __forceinline__ void lkp_fill_rows(uint32_t aX, int (&Xpk)[PhTile::TH][PhTile::NP], int (&Ypk)[PhTile::TH][PhTile::NP])
 {
     using T = PhTile;
-    constexpr int NP = T::NP;
+    constexpr int NP = T::NP, NW = ODD ? NP + 1 : NP, YO = T::PLANE_WORDS * 4;
+    static_assert(NP == 5, "five tap pairs per row and plane");
     uint32_t wx[NP + 1], wy[NP + 1];
     wx[0] = lds_u32<(R * T::PW + 0) * 4>(aX); wx[1] = lds_u32<(R * T::PW + 1) * 4>(aX); wx[2] = lds_u32<(R * T::PW + 2) * 4>(aX);
-    wx[3] = lds_u32<(R * T::PW + 3) * 4>(aX); wx[4] = lds_u32<(R * T::PW + 4) * 4>(aX); wx[5] = lds_u32<(R * T::PW + 5) * 4>(aX);
-    constexpr int YO = T::PLANE_WORDS * 4;
+    wx[3] = lds_u32<(R * T::PW + 3) * 4>(aX); wx[4] = lds_u32<(R * T::PW + 4) * 4>(aX);
     wy[0] = lds_u32<YO + (R * T::PW + 0) * 4>(aX); wy[1] = lds_u32<YO + (R * T::PW + 1) * 4>(aX); wy[2] = lds_u32<YO + (R * T::PW + 2) * 4>(aX);
-    wy[3] = lds_u32<YO + (R * T::PW + 3) * 4>(aX); wy[4] = lds_u32<YO + (R * T::PW + 4) * 4>(aX); wy[5] = lds_u32<YO + (R * T::PW + 5) * 4>(aX);
-    static_assert(NP == 5, "six words per row and plane");
+    wy[3] = lds_u32<YO + (R * T::PW + 3) * 4>(aX); wy[4] = lds_u32<YO + (R * T::PW + 4) * 4>(aX);
+    if constexpr (NW > NP) { wx[5] = lds_u32<(R * T::PW + 5) * 4>(aX); wy[5] = lds_u32<YO + (R * T::PW + 5) * 4>(aX); }
 #pragma unroll
     for (int i = 0; i < NP; i++) {
-        Xpk[R][i] = (int)__funnelshift_r(wx[i], wx[i + 1], sh);
-        Ypk[R][i] = (int)__funnelshift_r(wy[i], wy[i + 1], sh);
+        if constexpr (ODD) {       // the window starts on the odd element of a word: pairs straddle two words
+            Xpk[R][i] = (int)__byte_perm(wx[i], wx[i + 1], 0x5432);
+            Ypk[R][i] = (int)__byte_perm(wy[i], wy[i + 1], 0x5432);
+        } else { Xpk[R][i] = (int)wx[i]; Ypk[R][i] = (int)wy[i]; }
     }
-    if constexpr (R + 1 < T::TH) lkp_fill_rows<R + 1>(aX, sh, Xpk, Ypk);
+    if constexpr (R + 1 < T::TH) lkp_fill_rows<R + 1, ODD>(aX, Xpk, Ypk);
 }
 // the tap rows of one LK iteration
 template <int R>
@@ -374,9 +376,9 @@ __global__ void __launch_bounds__(32, 18) k_lk_phase(const LkParams p, const __g
             int Xpk[TH][NP], Ypk[TH][NP];
             {
                 const int e0 = ((ipx + MD_PH_MARGIN) & 7) + TW * lx;       // first tap column of this lane inside the box
-                const int sh = (e0 & 1) * 16;
                 const uint32_t aX = aP + ((TH * ly) * T::PW + (e0 >> 1)) * 4;
-                lkp_fill_rows<0>(aX, sh, Xpk, Ypk);
+                if ((ipx + MD_PH_MARGIN) & 1) lkp_fill_rows<0, true>(aX, Xpk, Ypk);       // warp-uniform: 10 lx is even
+                else lkp_fill_rows<0, false>(aX, Xpk, Ypk);
             }
             __syncwarp();                       // the phase tile is consumed: prefetch the next window
             issue_next_P(k, level);

@@ -9,7 +9,7 @@
 #define REPS 64
 
 template <int MODE>
-__global__ void __launch_bounds__(256) probe(uint32_t *out, long long *clk, uint32_t seed, int iters)
+__global__ void __launch_bounds__(512) probe(uint32_t *out, long long *clk, uint32_t seed, int iters)
 {
     uint32_t a[CHAINS], b[CHAINS];
 #pragma unroll
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(256) probe(uint32_t *out, long long *clk, uint
                 if (MODE == 11) { float f = __uint_as_float(a[i]), g = __uint_as_float(b[i]);
                                   asm volatile("fma.rn.f32 %0, %1, %2, %0;" : "+f"(f) : "f"(g), "f"(g)); a[i] = __float_as_uint(f);
                                   asm volatile("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(b[i]) : "r"(w), "r"(a[(i + 1) % CHAINS])); }
-                if (MODE == 12) { asm volatile("mul.wide.u32 %0, %1, %2;" : "=l"(*(unsigned long long *)&a[i & ~1]) : "r"(w), "r"(b[i])); }
+                if (MODE == 12) { asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(w), "r"(b[i])); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b[i]) : "r"(a[(i + 1) % CHAINS]), "r"(w)); asm volatile("shf.r.wrap.b32 %0, %0, %1, %2;" : "+r"(b[i]) : "r"(a[(i + 2) % CHAINS]), "r"(w)); }
             }
         }
     }
@@ -76,7 +76,7 @@ int main()
 {
     uint32_t *out; long long *clk;
     cudaMalloc(&out, 148 * 1024 * 4); cudaMalloc(&clk, 148 * 8);
-    for (int wps : {8, 16}) {
+    for (int wps : {4, 8, 16}) {
         run<0>("IDP.2A", 1, out, clk, wps);
         run<5>("IDP.4A", 1, out, clk, wps);
         run<3>("IMAD", 1, out, clk, wps);
@@ -89,7 +89,7 @@ int main()
         run<10>("IMAD + SHF", 2, out, clk, wps);
         run<11>("FFMA + IDP.2A", 2, out, clk, wps);
         run<8>("4 IDP.2A + SHF", 5, out, clk, wps);
-        run<12>("IMAD.WIDE (mul.wide.u32)", 1, out, clk, wps);
+        run<12>("IMAD + LOP3 + SHF", 3, out, clk, wps);
     }
     return 0;
 }
