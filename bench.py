@@ -5,7 +5,8 @@ A "step" is one pass of the hot path (pyramid -> LK -> egomotion fit -> fused wa
 batch of `--batch` frame pairs of the 1920x1080 synthetic sequence with global affine camera motion plus moving blobs
 (BASELINE.json configs[1], SURVEY.md 8d "C2").  `value` = pairs/s with the frames already resident in HBM; `e2e` = the
 same metric through the C ABI with HOST (pinned) buffers, H2D of the frames and D2H of masks/flow/H inside the timed
-region.  N > 1: one process per GPU (torchrun), independent camera streams per rank (seed 1234 + rank), no collective
+region.  N > 1: one process per GPU (torchrun), independent camera streams per rank (every rank its own copy of the same synthetic sequence: LK work is data dependent, so
+only identical content keeps the per-GPU work of a weak-scaling run fixed), no collective
 on the frame path; NCCL only for the barrier / max-over-ranks / stats gather.
 
   python bench.py --gpus 1 --steps 20 --warmup 3
@@ -110,8 +111,10 @@ def pin_to_gpu_cores(local, world):
 
 
 def make_frames(a, rank, n):
+    """Every rank gets its own copy of the SAME sequence: the LK iteration count depends on the image content (r02: the seed
+    1234 + 1 sequence needs 4.6 % more GPU time than seed 1234 on the same GPU, which read as a flat scaling loss at N >= 2)."""
     from motion_detection_b200 import synth
-    frames, _ = synth.sequence(a.width, a.height, n, seed=1234 + rank)
+    frames, _ = synth.sequence(a.width, a.height, n, seed=1234)
     return frames
 
 
@@ -121,12 +124,19 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
+        try:                         # the physical GPU, whatever CUDA_VISIBLE_DEVICES maps `index` to
+            import torch
+            self.index = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+        except Exception:
+            pass
         self.rows = []
         self.proc = None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        if os.environ.get("MD_BENCH_NO_SAMPLER"):        # diagnostic runs only: does the polling itself disturb the GPU?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                           "--format=csv,noheader,nounits", "-lms", os.environ.get("MD_BENCH_SAMPLER_MS", "20")],
