@@ -40,32 +40,59 @@ cudaError_t launch_gray(const uint8_t *src3, int src_pitch, int w, int h, uint8_
 }
 
 // ---- level 0: plain frame (gray or 8UC3) -> padded plane with REFLECT_101 frame --------------------------------
-// One thread writes 4 consecutive padded pixels as one 32-bit store (padded rows are 128-byte aligned).
+// One thread writes 16 consecutive padded pixels as one 16-byte store (padded rows are 128-byte aligned, padx is a multiple of
+// 16).  Groups that lie inside the image read their source with aligned 16-byte loads when the frame's base and pitch allow it
+// (ALIGNED, decided by the host); groups that touch the REFLECT_101 frame take the per-pixel path.
 template <int CH>
-__global__ void __launch_bounds__(256) k_level0(const uint8_t *__restrict__ frames, int fpitch, long long fstride,
-                                                uint8_t *__restrict__ img, size_t slot_bytes, int slot0, int nslots,
-                                                LevelGeom L, int padx, int pady)
+__device__ __forceinline__ uint32_t level0_px4(const uint8_t *row, int px, int w, int padx)
 {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;      // group of 4 padded columns
-    int py = blockIdx.y;
-    int f = blockIdx.z;
-    if (q * 4 >= L.pitch) return;
-    const uint8_t *src = frames + (size_t)f * fstride;
-    uint8_t *plane = img + (size_t)((slot0 + f) % nslots) * slot_bytes + L.img_off;
-    int sy = reflect101(py - pady, L.h);
-    const uint8_t *row = src + (size_t)sy * fpitch;
     uint32_t v = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        int px = q * 4 + i - padx;
         uint32_t g = 0;
-        if (px >= -padx && px < L.w + padx) {
-            int sx = reflect101(px, L.w);
+        if (px + i >= -padx && px + i < w + padx) {
+            const int sx = reflect101(px + i, w);
             g = CH == 1 ? row[sx] : gray_px(row + 3 * sx);
         }
         v |= g << (8 * i);
     }
-    *reinterpret_cast<uint32_t *>(plane + (size_t)py * L.pitch + q * 4) = v;
+    return v;
+}
+__device__ __forceinline__ uint32_t gray_word4(uint32_t a, uint32_t b, uint32_t c)      // 12 source bytes -> 4 gray pixels
+{
+    const uint32_t g0 = ((a & 0xffu) * 3735u + ((a >> 8) & 0xffu) * 19235u + ((a >> 16) & 0xffu) * 9798u + (1u << 14)) >> 15;
+    const uint32_t g1 = ((a >> 24) * 3735u + (b & 0xffu) * 19235u + ((b >> 8) & 0xffu) * 9798u + (1u << 14)) >> 15;
+    const uint32_t g2 = (((b >> 16) & 0xffu) * 3735u + (b >> 24) * 19235u + (c & 0xffu) * 9798u + (1u << 14)) >> 15;
+    const uint32_t g3 = (((c >> 8) & 0xffu) * 3735u + ((c >> 16) & 0xffu) * 19235u + (c >> 24) * 9798u + (1u << 14)) >> 15;
+    return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+}
+template <int CH, bool ALIGNED>
+__global__ void __launch_bounds__(128) k_level0(const uint8_t *__restrict__ frames, int fpitch, long long fstride,
+                                                uint8_t *__restrict__ img, size_t slot_bytes, int slot0, int nslots,
+                                                LevelGeom L, int padx, int pady)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;      // group of 16 padded columns
+    const int py = blockIdx.y;
+    const int f = blockIdx.z;
+    if (q * 16 >= L.pitch) return;
+    const uint8_t *src = frames + (size_t)f * fstride;
+    uint8_t *plane = img + (size_t)((slot0 + f) % nslots) * slot_bytes + L.img_off;
+    const int sy = reflect101(py - pady, L.h);
+    const uint8_t *row = src + (size_t)sy * fpitch;
+    const int px = q * 16 - padx;
+    uint4 v;
+    if (ALIGNED && px >= 0 && px + 16 <= L.w) {
+        if (CH == 1) v = __ldg(reinterpret_cast<const uint4 *>(row + px));
+        else {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(row + 3 * px)), b = __ldg(reinterpret_cast<const uint4 *>(row + 3 * px + 16)),
+                        c = __ldg(reinterpret_cast<const uint4 *>(row + 3 * px + 32));
+            v = make_uint4(gray_word4(a.x, a.y, a.z), gray_word4(a.w, b.x, b.y), gray_word4(b.z, b.w, c.x), gray_word4(c.y, c.z, c.w));
+        }
+    } else {
+        v = make_uint4(level0_px4<CH>(row, px, L.w, padx), level0_px4<CH>(row, px + 4, L.w, padx), level0_px4<CH>(row, px + 8, L.w, padx),
+                       level0_px4<CH>(row, px + 12, L.w, padx));
+    }
+    *reinterpret_cast<uint4 *>(plane + (size_t)py * L.pitch + q * 16) = v;
 }
 
 // ---- level l -> l+1: pyrDown straight into the padded plane (frame pixels computed at reflected coordinates) -----
@@ -214,11 +241,14 @@ cudaError_t launch_pyramid_level0(const PyrGeom &g, uint8_t *img, int slot0, int
                                   int fpitch, long long fstride, cudaStream_t s)
 {
     const LevelGeom &L = g.lv[0];
-    dim3 grid((L.pitch / 4 + 255) / 256, L.rows, nframes);
-    if (channels == 1)
-        k_level0<1><<<grid, 256, 0, s>>>(frames, fpitch, fstride, img, g.slot_img_bytes, slot0, g.nslots, L, g.padx, g.pady);
-    else
-        k_level0<3><<<grid, 256, 0, s>>>(frames, fpitch, fstride, img, g.slot_img_bytes, slot0, g.nslots, L, g.padx, g.pady);
+    dim3 grid((L.pitch / 16 + 127) / 128, L.rows, nframes);
+    // 16-byte source loads need a 16-byte aligned base, pitch and frame stride (and padx a multiple of 16: column groups of the
+    // padded plane then start on multiples of 16 source pixels)
+    const bool al = (((uintptr_t)frames | (uintptr_t)fpitch | (uintptr_t)fstride | (uintptr_t)g.padx) & 15) == 0;
+#define MD_L0(CH, AL) k_level0<CH, AL><<<grid, 128, 0, s>>>(frames, fpitch, fstride, img, g.slot_img_bytes, slot0, g.nslots, L, g.padx, g.pady)
+    if (channels == 1) { if (al) MD_L0(1, true); else MD_L0(1, false); }
+    else { if (al) MD_L0(3, true); else MD_L0(3, false); }
+#undef MD_L0
     MD_COUNT_LAUNCH(1);
     return cudaGetLastError();
 }
