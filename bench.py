@@ -534,19 +534,27 @@ def main():
                 "note": "LK with a 40x40 window is ALU/shared-memory bound by construction (1600 taps x levels x iterations "
                         "per point); its HBM fraction is small by design, see stages[] for the HBM-bound kernels (K1, K4)"}
 
-    # LK is bound by instruction issue, not by bytes: report that roofline beside the HBM one.  Instructions per tracked point
-    # come from the committed ncu capture (profiles/traffic.json "k_lk_warp_instr_per_point"); the time is measured here.
+    # LK is bound by instruction issue, not by bytes: report that roofline beside the HBM one.  Warp instructions per tracked point =
+    # static instruction counts per SASS region of k_lk_phase (profiles/traffic.json "k_lk_instr_model", from the committed ncu
+    # source-page capture) x the iterations per point COUNTED ON THE DEVICE in this run's timed region; the time is measured here.
     try:
-        ipp = json.load(open(tp)).get("k_lk_warp_instr_per_point")
+        tj = json.load(open(tp))
+        model, ipp_ncu = tj.get("k_lk_instr_model"), tj.get("k_lk_warp_instr_per_point")
     except Exception:
-        ipp = None
-    if ipp and a.pixel_step == 10 and (w, h) == (1920, 1080):
+        model, ipp_ncu = None, None
+    if model and lk_taps and a.pixel_step == 10 and (w, h) == (1920, 1080) and not vf:
+        nlev = getattr(ctx, "levels", 5)
+        ipp = model["per_point"] + model["per_level_visited"] * nlev + model["per_iteration"] * lk_taps["iterations_per_point"]
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         peak_issue = 148 * 4 * sm_mhz * 1e6                       # one warp instruction per scheduler per clock
         ach = ipp * P * B / (stage_ms[1] * 1e-3)
         roofline["issue"] = {"bound": "instruction issue (148 SMs x 4 schedulers x SM clock)", "achieved": ach / 1e9, "peak": peak_issue / 1e9,
                              "unit": "G warp-instr/s", "frac": ach / peak_issue, "warp_instr_per_point": ipp,
-                             "source": "ncu smsp__inst_executed.sum of k_lk_phase / tracked points (profiles/r01_lk_phase_ncu_full_v2.txt); the time is the whole K2 stage (planes + window sums + LK), so this is a lower bound of the LK kernel's own 80 %"}
+                             "warp_instr_per_point_ncu": ipp_ncu,
+                             "thread_instr_per_window_tap": 32.0 * ipp / (1600.0 * lk_taps["iterations_per_point"]),
+                             "source": "k_lk_phase only: per-region static SASS counts (profiles/r02_k2_ncu_full.txt) x iterations per point "
+                                       "counted on the device in this run; the time is the whole K2 stage (planes + window sums + LK), "
+                                       "so frac is a lower bound of the LK kernel's own issue utilisation (79 % under ncu)"}
 
     # ---- e2e: C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
     def measure_e2e(packed):
