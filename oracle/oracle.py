@@ -422,8 +422,8 @@ def flow_field_row_major(pts, nxt, status, keep):
 
 
 def ref_lib(name):
-    """'varflow' (common/src/VarFlow.cpp) or 'cluster' (flow_clusterer.cpp + vector_cluster.cpp + point_cluster.cpp);
-    None when oracle/_ref was not built (no /root/reference at build time)."""
+    """'varflow' (common/src/VarFlow.cpp), 'cluster' (flow_clusterer.cpp + vector_cluster.cpp + point_cluster.cpp) or 'ofc'
+    (optical_flow_calculator.cpp); None when oracle/_ref was not built (no /root/reference at build time)."""
     if name not in _REF:
         so = os.path.join(_HERE, "_ref", "lib%s_ref.so" % name)
         if not os.path.exists(so) and os.path.exists("/root/reference/common/src/VarFlow.cpp"):
@@ -476,3 +476,68 @@ def clusters_from_labels(items, labels, ncl, min_size=5):
     ids = [i for i in range(ncl) if cnt[i] > min_size]
     mem = np.concatenate([items[labels == i] for i in ids]) if ids else items[:0]
     return cnt[ids].astype(np.int32), mem
+
+
+# ---- the reference's own OpticalFlowCalculator (oracle/_ref/libofc_ref.so: common/src/optical_flow_calculator.cpp unmodified, the
+# cv:: calls it makes forwarded to the primitives above by oracle/ref_shim_ofc) ------------------------------------------------
+def _bgr(img):
+    img = np.ascontiguousarray(img, np.uint8)
+    if img.ndim == 2:
+        img = np.repeat(img[..., None], 3, axis=2)
+    return np.ascontiguousarray(img)
+
+
+def ref_calculate_optical_flow(img1, img2, pixel_step=10, min_vector_size=1.0):
+    """OpticalFlowCalculator::calculateOpticalFlow (cpp:30-130): (num_vectors, flow [h][w][4] f64, comp [h][w] u8 or None when the
+    reference left comp untouched)."""
+    a, b = _bgr(img1), _bgr(img2)
+    h, w = a.shape[:2]
+    flow = np.zeros((h, w, 4), np.float64)
+    comp = np.zeros((h, w), np.uint8)
+    rows = C.c_int(0)
+    nv = ref_lib("ofc").ref_calculate_optical_flow(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), w, h, pixel_step,
+                                                   C.c_double(min_vector_size), flow.ctypes.data_as(f64p), comp.ctypes.data_as(u8p),
+                                                   C.byref(rows))
+    return nv, flow, (comp if rows.value == h else None)
+
+
+def ref_calculate_trajectories(images, pixel_step=10, min_vector_size=1.0):
+    """OpticalFlowCalculator::calculateOpticalFlowTrajectory (cpp:133-257): (num_vectors, flow [h][w][4], trajectories [T][F][2])."""
+    imgs = np.ascontiguousarray(np.stack([_bgr(i) for i in images]))
+    n, h, w = imgs.shape[:3]
+    P = ((w + pixel_step - 1) // pixel_step) * ((h + pixel_step - 1) // pixel_step)
+    flow = np.zeros((h, w, 4), np.float64)
+    traj = np.zeros((P, n, 2), np.float32)
+    nt = C.c_int(0)
+    nv = ref_lib("ofc").ref_calculate_trajectories(imgs.ctypes.data_as(u8p), n, w, h, pixel_step, C.c_double(min_vector_size),
+                                                   flow.ctypes.data_as(f64p), traj.ctypes.data_as(f32p), P, C.byref(nt))
+    return nv, flow, traj[:nt.value].copy()
+
+
+def ref_calculate_compensated_flow(img1, img2, pixel_step=10):
+    """OpticalFlowCalculator::calculateCompensatedFlow (cpp:264-335): the flow field [h][w][4]."""
+    a, b = _bgr(img1), _bgr(img2)
+    h, w = a.shape[:2]
+    flow = np.zeros((h, w, 4), np.float64)
+    ref_lib("ofc").ref_calculate_compensated_flow(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), w, h, pixel_step, flow.ctypes.data_as(f64p))
+    return flow
+
+
+def ref_write_flow(flow, pixel_step, filename):
+    flow = np.ascontiguousarray(flow, np.float64)
+    h, w = flow.shape[:2]
+    ref_lib("ofc").ref_write_flow(flow.ctypes.data_as(f64p), w, h, pixel_step, filename.encode())
+
+
+def ref_write_trajectories(traj, filename):
+    traj = np.ascontiguousarray(traj, np.float32)
+    ref_lib("ofc").ref_write_trajectories(traj.ctypes.data_as(f32p), traj.shape[0], traj.shape[1], filename.encode())
+
+
+def flow_field_from_filter(pts, status, flow4, w, h):
+    """The Vec4d field calculateOpticalFlow leaves in the node's Mat (cpp:78-117), from the oracle's per-point flow_filter rows."""
+    f = np.zeros((h, w, 4), np.float64)
+    xi = pts[:, 0].astype(np.int64)
+    yi = pts[:, 1].astype(np.int64)
+    f[yi, xi] = flow4
+    return f

@@ -21,5 +21,15 @@ fr = T._vf_pair(160, 120, 9)
 out["vf_U_160x120_l2"], out["vf_V_160x120_l2"] = O.ref_varflow(fr[0], fr[1], max_level=2, n1=1, n2=3)
 out["ce_sizes"], out["ce_members"] = O.ref_cluster_euclidean(T._lattice_points(3), 33.3)
 out["gc_sizes"], out["gc_members"] = O.ref_get_clusters(T._flow_field(2), 10, 50.0, 0.5)
+# the chain composition by the reference's own optical_flow_calculator.cpp (oracle/_ref/libofc_ref.so)
+f0, f1, ps = T._mover_pair()
+nv, flow, comp = O.ref_calculate_optical_flow(f0, f1, ps, 1.0)
+out["ofc_nv"] = np.array([nv])
+out["ofc_flow_grid"] = flow[::ps, ::ps].copy()
+out["ofc_comp_bits"] = np.packbits(comp > 0)
+frames = T.synth.sequence(320, 240, 5, seed=21)[0]
+nv, flow, traj = O.ref_calculate_trajectories(frames, 20, 1.0)
+out["traj_nv"] = np.array([nv])
+out["traj_complete"] = traj
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden_ref.npz"), **out)
 print({k: v.shape for k, v in out.items()})

@@ -120,3 +120,123 @@ def test_oracle_equals_frozen_reference_outputs(oracle):
     lab, ncl = oracle.cluster_vectors(vec, 50.0, 0.5)
     sizes, mem = oracle.clusters_from_labels(vec, lab, ncl)
     assert np.array_equal(sizes, G["gc_sizes"]) and np.array_equal(mem, G["gc_members"])
+
+
+# ---- OpticalFlowCalculator: the reference's own composition (oracle/_ref/libofc_ref.so) ----------------------------------------------
+def _texture(w, h, seed):
+    """high-contrast smooth texture (trackable everywhere)"""
+    import cv2
+    rng = np.random.default_rng(seed)
+    t = cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (0, 0), 2.0)
+    t = (t - t.min()) / (t.max() - t.min())
+    return np.clip((t - 0.5) * 6.0 + 0.5, 0.0, 1.0)
+
+
+def _mover_pair(w=512, h=384, ps=64, seed=11):
+    """A static textured scene in which a few 70 x 70 patches, each centred on ONE grid point of a 64-pixel grid, move by a few
+    pixels: the vectors that survive the min_vector_size filter are those grid points, in different grid columns and not
+    collinear -- so the reference's literal getPerspectiveTransform of the first four kept vectors (cpp:120) is well posed."""
+    base = _texture(w, h, seed)
+    f0 = (base * 255).astype(np.uint8)
+    f1 = f0.copy()
+    movers = [((64, 64), (3, 2)), ((128, 256), (-2, 3)), ((256, 128), (4, -2)), ((320, 320), (2, 2)), ((448, 192), (-3, -3))]
+    for (cx, cy), (dx, dy) in movers:
+        x0, y0 = cx - 35, cy - 35
+        f1[y0 + dy:y0 + dy + 70, x0 + dx:x0 + dx + 70] = f0[y0:y0 + 70, x0:x0 + 70]
+    return f0, f1, ps
+
+
+def test_chain_composition_equals_reference_code(oracle):
+    """OpticalFlowCalculator::calculateOpticalFlow (optical_flow_calculator.cpp:30-130), unmodified: grid order, status /
+    min_vector_size filter, the Vec4d field, getPerspectiveTransform of the first four kept vectors, warpPerspective, absdiff,
+    threshold 190 -- against the oracle's composition in its literal mode (MODE_FIRST4, no morphology)."""
+    _need(oracle, "ofc")
+    f0, f1, ps = _mover_pair()
+    h, w = f0.shape
+    for mvs in (1.0, 0.2):
+        nv, flow, comp = oracle.ref_calculate_optical_flow(f0, f1, ps, mvs)
+        o = oracle.process_pair(f0, f1, pixel_step=ps, min_vector_size=mvs, mode=oracle.MODE_FIRST4, morph=False)
+        assert nv == o["num_vectors"] and nv >= 4
+        assert np.array_equal(flow, oracle.flow_field_from_filter(o["pts"], o["status"], o["flow4"], w, h))
+        assert o["inliers"] == 4, "the first four kept vectors must be in general position for this test"
+        assert comp is not None and np.array_equal(comp, o["mask"])
+        if mvs == 1.0:
+            assert 0 < int((comp > 0).sum()) < comp.size // 4      # the comparison is not vacuous
+
+
+def test_chain_without_vectors_leaves_comp_untouched_like_the_reference(oracle):
+    """num_vectors == 0 (static scene): the reference skips the warp and leaves comp as it was (cpp:118); the field holds the grid
+    points with zero vectors"""
+    _need(oracle, "ofc")
+    f0 = (_texture(256, 192, 3) * 255).astype(np.uint8)
+    nv, flow, comp = oracle.ref_calculate_optical_flow(f0, f0, 32, 1.0)
+    o = oracle.process_pair(f0, f0, pixel_step=32, min_vector_size=1.0, mode=oracle.MODE_FIRST4, morph=False)
+    assert nv == 0 == o["num_vectors"] and comp is None and int(o["mask"].sum()) == 0
+    assert np.array_equal(flow, oracle.flow_field_from_filter(o["pts"], o["status"], o["flow4"], 256, 192))
+
+
+def test_trajectory_bookkeeping_equals_reference_code(oracle):
+    """calculateOpticalFlowTrajectory (cpp:133-257), unmodified: per-pair LK from the tracked positions, the 10-pixel border rule,
+    complete trajectories in grid order, the Vec4d field of the LAST pair."""
+    _need(oracle, "ofc")
+    frames, _ = synth.sequence(320, 240, 5, seed=21)
+    for ps, mvs in ((20, 1.0), (16, 0.2)):
+        nv, flow, traj = oracle.ref_calculate_trajectories(frames, ps, mvs)
+        tr, ln, last = oracle.track_trajectories(frames, ps)
+        full = tr[ln == len(frames)]
+        assert traj.shape == full.shape and len(full) > 50 and np.array_equal(traj, full)
+        prev, nxt, st = last
+        nv_o, keep, flow4 = oracle.flow_filter(prev, nxt, st, mvs)
+        assert nv == nv_o
+        # the field is indexed by the START point of the last pair (cpp:187,215): tracked positions, truncated to int
+        exp = np.zeros_like(flow)
+        for p, row in zip(prev, flow4):
+            exp[int(p[1]), int(p[0])] = row
+        assert np.array_equal(flow, exp)
+
+
+def test_compensated_flow_equals_reference_code(oracle):
+    """calculateCompensatedFlow (cpp:264-335), unmodified: image-input LK with MAX_LEVEL 2, fixed 1.0 filter"""
+    _need(oracle, "ofc")
+    frames, _ = synth.sequence(320, 240, 2, seed=5)
+    flow = oracle.ref_calculate_compensated_flow(frames[0], frames[1], 10)
+    pts = oracle.grid_points(320, 240, 10)
+    p2, st = oracle.lk(frames[0], frames[1], pts, max_level=2)
+    _, _, flow4 = oracle.flow_filter(pts, p2, st, 1.0)
+    assert np.array_equal(flow, oracle.flow_field_from_filter(pts, st, flow4, 320, 240))
+    assert (np.abs(flow[..., 2:]) > 0).any()
+
+
+def test_write_flow_and_trajectories_formats_are_the_reference_code(oracle, tmp_path):
+    """writeFlow / writeTrajectories (cpp:509-562), unmodified, on the very inputs adapter/test/node_callsites.cpp feeds the adapter's
+    host implementations (tests/test_adapter_cpu.py expects the same lines from those)."""
+    _need(oracle, "ofc")
+    flow = np.zeros((20, 30, 4))
+    for y in range(0, 20, 10):
+        for x in range(0, 30, 10):
+            flow[y, x, 0], flow[y, x, 1] = x, y
+    flow[0, 10, 2:] = (1.5, -0.25)
+    flow[10, 20, 2:] = (-2.0, 0.333333333)
+    flow[10, 0] = (-1.0, -1.0, 7.0, 7.0)
+    oracle.ref_write_flow(flow, 10, str(tmp_path / "flow"))
+    assert open(tmp_path / "flow_h").read().splitlines() == ["0, 1.5, 0", "0, 0, -2"]
+    assert open(tmp_path / "flow_f").read().splitlines() == ["0, -0.25, 0", "0, 0, 0.333333"]
+    traj = np.array([[[10, 20], [11.25, 19.5], [12.5, 19]]], np.float32)
+    oracle.ref_write_trajectories(traj, str(tmp_path / "traj"))
+    assert open(tmp_path / "traj").read().splitlines() == ["10, 20, 11.25, 19.5, 12.5, 19"]
+
+
+def test_frozen_reference_chain_outputs(oracle):
+    """the same two comparisons against outputs of the reference code frozen in tests/golden/golden_ref.npz (runs where
+    /root/reference does not exist)"""
+    G = np.load(GOLD)
+    f0, f1, ps = _mover_pair()
+    o = oracle.process_pair(f0, f1, pixel_step=ps, min_vector_size=1.0, mode=oracle.MODE_FIRST4, morph=False)
+    h, w = f0.shape
+    assert o["num_vectors"] == int(G["ofc_nv"][0])
+    assert np.array_equal(oracle.flow_field_from_filter(o["pts"], o["status"], o["flow4"], w, h)[::ps, ::ps], G["ofc_flow_grid"])
+    assert np.array_equal(np.packbits(o["mask"] > 0), G["ofc_comp_bits"])
+    frames, _ = synth.sequence(320, 240, 5, seed=21)
+    tr, ln, last = oracle.track_trajectories(frames, 20)
+    assert np.array_equal(tr[ln == len(frames)], G["traj_complete"])
+    assert oracle.flow_filter(last[0], last[1], last[2], 1.0)[0] == int(G["traj_nv"][0])
