@@ -422,8 +422,8 @@ def flow_field_row_major(pts, nxt, status, keep):
 
 
 def ref_lib(name):
-    """'varflow' (common/src/VarFlow.cpp), 'cluster' (flow_clusterer.cpp + vector_cluster.cpp + point_cluster.cpp) or 'ofc'
-    (optical_flow_calculator.cpp); None when oracle/_ref was not built (no /root/reference at build time)."""
+    """'varflow' (common/src/VarFlow.cpp), 'cluster' (flow_clusterer.cpp + vector_cluster.cpp + point_cluster.cpp), 'ofc'
+    (optical_flow_calculator.cpp) or 'od' (outlier_detector.cpp); None when oracle/_ref was not built (no /root/reference at build time)."""
     if name not in _REF:
         so = os.path.join(_HERE, "_ref", "lib%s_ref.so" % name)
         if not os.path.exists(so) and os.path.exists("/root/reference/common/src/VarFlow.cpp"):
@@ -541,3 +541,29 @@ def flow_field_from_filter(pts, status, flow4, w, h):
     yi = pts[:, 1].astype(np.int64)
     f[yi, xi] = flow4
     return f
+
+
+# ---- the reference's own OutlierDetector (oracle/_ref/libod_ref.so: common/src/outlier_detector.cpp unmodified; Eigen is a small
+# stand-in, see oracle/ref_shim_ofc/Eigen/Dense) -------------------------------------------------------------------------------
+def ref_find_outliers(flow, pixel_step, include_zeros=False):
+    """OutlierDetector::findOutliers (outlier_detector.cpp:37-186) on a Vec4d field [h][w][4]: the outlier_probabilities matrix."""
+    flow = np.ascontiguousarray(flow, np.float64)
+    h, w = flow.shape[:2]
+    prob = np.zeros((h, w), np.float64)
+    ref_lib("od").ref_find_outliers(flow.ctypes.data_as(f64p), w, h, pixel_step, 1 if include_zeros else 0, prob.ctypes.data_as(f64p))
+    return prob
+
+
+def ref_fit_subspace(traj, num_motions=2, sigma=0.5, seed=1):
+    """OutlierDetector::fitSubspace (outlier_detector.cpp:236-331) after srand(seed): (indices of the reported outlier trajectories,
+    sampled columns of the winning hypothesis)."""
+    traj = np.ascontiguousarray(traj, np.float32)
+    T, F, _ = traj.shape
+    oi = np.zeros(T, np.int32)
+    cols = np.zeros(4 * num_motions, np.int32)
+    nc = C.c_int(0)
+    n = ref_lib("od").ref_fit_subspace(traj.ctypes.data_as(f32p), T, F, num_motions, C.c_double(sigma), C.c_uint32(seed),
+                                       oi.ctypes.data_as(i32p), cols.ctypes.data_as(i32p), C.byref(nc))
+    if n < 0:
+        raise RuntimeError("could not map the reported outlier points back to trajectories (duplicate points)")
+    return oi[:n].copy(), cols[:nc.value].copy()

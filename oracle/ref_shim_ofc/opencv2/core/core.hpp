@@ -57,6 +57,7 @@ template <typename T, int N> struct Vec {
     const T &operator[](int i) const { return val[i]; }
 };
 typedef Vec<double, 4> Vec4d;
+template <typename T, int N> std::ostream &operator<<(std::ostream &o, const Vec<T, N> &v) { o << "["; for (int i = 0; i < N; i++) o << (i ? ", " : "") << v[i]; return o << "]"; }
 struct Size { int width, height; Size() : width(0), height(0) {} Size(int w, int h) : width(w), height(h) {} };
 struct Scalar { double val[4]; Scalar(const CvScalar &s) { for (int i = 0; i < 4; i++) val[i] = s.val[i]; } };
 struct TermCriteria { int type, maxCount; double epsilon; TermCriteria(int t, int n, double e) : type(t), maxCount(n), epsilon(e) {} };

@@ -31,5 +31,11 @@ frames = T.synth.sequence(320, 240, 5, seed=21)[0]
 nv, flow, traj = O.ref_calculate_trajectories(frames, 20, 1.0)
 out["traj_nv"] = np.array([nv])
 out["traj_complete"] = traj
+# OutlierDetector by the reference's own outlier_detector.cpp (oracle/_ref/libod_ref.so)
+fld = T._mad_field(3, ps=10, zero_frac=0.3)
+out["mad_flags_nozero"] = (O.ref_find_outliers(fld, 10, False)[::10, ::10].reshape(-1) == 1.0).astype(np.uint8)
+out["mad_flags_zero"] = (O.ref_find_outliers(fld, 10, True)[::10, ::10].reshape(-1) == 1.0).astype(np.uint8)
+tr, _ = T._two_motion_trajectories(7)
+out["sub_outliers"], out["sub_cols"] = O.ref_fit_subspace(tr, 2, 0.5, 7)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "golden_ref.npz"), **out)
 print({k: v.shape for k, v in out.items()})

@@ -57,3 +57,21 @@ def test_device_trajectories_equal_reference_code_outputs(capi):
     assert np.array_equal(full[:, 0], ref[:, 0])
     assert np.abs(full - ref).max() < 0.05 and np.abs(full - ref).mean() < 0.002
     ctx.close()
+
+
+def test_device_outlier_detector_equals_reference_code_outputs(capi):
+    """md_find_outliers and md_fit_subspace against the frozen outputs of the reference's own outlier_detector.cpp"""
+    from test_oracle_ref import _mad_field, _two_motion_trajectories
+    G = np.load(GOLD)
+    ctx = capi.Context(width=320, height=240, max_batch=1, pixel_step=10, seed=1)
+    nodes = _mad_field(3, ps=10, zero_frac=0.3)[::10, ::10].reshape(-1, 4)
+    for inc, key in ((False, "mad_flags_nozero"), (True, "mad_flags_zero")):
+        r = ctx.find_outliers(nodes[:, 2:4], include_zeros=inc)
+        flags = r["outlier"] if isinstance(r, dict) else r[0]
+        assert np.array_equal(np.asarray(flags).astype(np.uint8), G[key])
+    traj, _ = _two_motion_trajectories(7)
+    r = ctx.fit_subspace(traj, num_motions=2, sigma=0.5, seed=7)
+    cols = r["best_cols"] if isinstance(r, dict) else r[2]
+    outl = r["outlier"] if isinstance(r, dict) else r[3]
+    assert np.array_equal(np.asarray(cols), G["sub_cols"]) and np.array_equal(np.nonzero(np.asarray(outl))[0], G["sub_outliers"])
+    ctx.close()

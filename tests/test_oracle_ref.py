@@ -240,3 +240,74 @@ def test_frozen_reference_chain_outputs(oracle):
     tr, ln, last = oracle.track_trajectories(frames, 20)
     assert np.array_equal(tr[ln == len(frames)], G["traj_complete"])
     assert oracle.flow_filter(last[0], last[1], last[2], 1.0)[0] == int(G["traj_nv"][0])
+
+
+# ---- OutlierDetector: the reference's own code (oracle/_ref/libod_ref.so) ----------------------------------------------------------
+def _mad_field(seed, w=320, h=240, ps=10, zero_frac=0.3):
+    rng = np.random.default_rng(seed)
+    flow = np.zeros((h, w, 4))
+    for y in range(0, h, ps):
+        for x in range(0, w, ps):
+            if rng.random() < zero_frac:
+                flow[y, x] = (x, y, 0.0, 0.0)
+            else:
+                d = rng.normal((2.0, -1.0), 0.3) if rng.random() > 0.08 else rng.normal((-4.0, 6.0), 1.5)
+                flow[y, x] = (x, y, d[0], d[1])
+    return flow
+
+
+@pytest.mark.parametrize("include_zeros", [False, True])
+def test_find_outliers_restatement_equals_reference_code(oracle, include_zeros):
+    """OutlierDetector::findOutliers / createMask / getMedian (outlier_detector.cpp:37-186), unmodified: the angle stage and the
+    magnitude stage share one mask; even-count medians average the two middle values"""
+    _need(oracle, "od")
+    for seed in range(6):
+        flow = _mad_field(seed, ps=10, zero_frac=0.3 if seed % 2 else 0.0)
+        prob = oracle.ref_find_outliers(flow, 10, include_zeros)
+        nodes = flow[::10, ::10].reshape(-1, 4)
+        out, _ = oracle.find_outliers(nodes[:, 2:4], include_zeros)
+        assert np.array_equal(prob[::10, ::10].reshape(-1) == 1.0, out == 1), (seed, include_zeros)
+        assert 0 < int(out.sum()) < len(out)
+
+
+def _two_motion_trajectories(seed, T=300, F=5, n_out=30):
+    """points of a small region (centroid-relative coordinates of a few tens of pixels: the f32 rounding of the reference's residuals
+    stays far below the threshold) carried by one affine camera motion plus 0.01 px noise; n_out of them jitter by +-3 px per frame"""
+    rng = np.random.default_rng(seed)
+    p0 = np.stack(np.meshgrid(np.arange(100, 160, 3.0), np.arange(80, 125, 3.0)), -1).reshape(-1, 2)[:T]
+    traj = np.zeros((len(p0), F, 2), np.float32)
+    out = rng.choice(len(p0), n_out, replace=False)
+    A = np.array([[1.002, 0.001], [-0.001, 0.999]]); t = np.array([1.5, -0.7])
+    cur = p0.copy()
+    for j in range(F):
+        traj[:, j] = cur + rng.normal(0, 0.01, cur.shape)
+        traj[out, j] += rng.choice([-3.0, 3.0], (n_out, 2))
+        cur = cur @ A.T + t
+    return traj, np.sort(out)
+
+
+def test_fit_subspace_composition_follows_reference_code(oracle):
+    """OutlierDetector::fitSubspace (outlier_detector.cpp:236-331), unmodified, with a small Eigen stand-in under it (f32 matrices in
+    index order, Jacobi SVD): data layout, mean subtraction, rand() % T sampling after srand(seed), projector, residual, inlier count,
+    first-best rule, chi-square threshold, and which point of a trajectory is reported -- on well separated data the winning sample
+    and the reported outliers are those of the oracle (whose sums are f64: not a bit-level comparison)"""
+    _need(oracle, "od")
+    for seed in (1, 7, 23):
+        traj, planted = _two_motion_trajectories(seed)
+        oi, cols = oracle.ref_fit_subspace(traj, 2, 0.5, seed)
+        n, res, ocols, outl, thr = oracle.fit_subspace(traj, 2, 0.5, seed)
+        assert np.array_equal(cols, ocols), seed
+        assert np.array_equal(oi, np.nonzero(outl)[0]), seed
+        # a planted trajectory that was drawn into the winning sample spans the subspace itself: residual 0, not reported
+        assert set(oi.tolist()) <= set(planted.tolist()) and len(oi) >= len(planted) - 8, seed
+
+
+def test_frozen_reference_outlier_detector_outputs(oracle):
+    """findOutliers flags and the fitSubspace winner / outliers of the reference code, frozen in tests/golden/golden_ref.npz"""
+    G = np.load(GOLD)
+    nodes = _mad_field(3, ps=10, zero_frac=0.3)[::10, ::10].reshape(-1, 4)
+    assert np.array_equal(oracle.find_outliers(nodes[:, 2:4], False)[0], G["mad_flags_nozero"])
+    assert np.array_equal(oracle.find_outliers(nodes[:, 2:4], True)[0], G["mad_flags_zero"])
+    traj, _ = _two_motion_trajectories(7)
+    n, res, cols, outl, thr = oracle.fit_subspace(traj, 2, 0.5, 7)
+    assert np.array_equal(cols, G["sub_cols"]) and np.array_equal(np.nonzero(outl)[0], G["sub_outliers"])
