@@ -322,11 +322,22 @@ __global__ void __launch_bounds__(32, 18) k_lk_phase(const LkParams p, const __g
     // the grid point (cpp:56-64: x outer, y inner) and its successor in the CTA, stepped without divisions
     int kx = k0 / p.gy, ky = k0 - kx * p.gy;
     int gxi = p.ps * kx, gyi = p.ps * ky, gxn, gyn;
+    // Which levels of a point passed the minimum-eigenvalue test (Dinv != 0 in its level records, k_window_sums): lane l looks at
+    // level l, one ballot.  Tracking of a point starts at its HIGHEST usable level: the failed levels above it (half of the
+    // coarsest-level windows of the bench sequence fail) cost neither tiles nor a register fill; a failed level further down is
+    // handled like before (found after its fill).  The mask of point k + 1 is fetched while point k is tracked.
+    const LkLevelRec *rec_top = p.wsum + ((size_t)(p.ph_pair0 + b) * p.g.nlev + top) * p.P;      // level `top`, point 0
+    auto load_D = [&](int kk) { return lane <= top ? __ldg(&(rec_top - (size_t)(top - lane) * p.P + kk)->Dinv) : 0.f; };
+    int first_cur = -1, first_next = -1;        // highest usable level of the current / the next point (-1: none)
+    // the window after (k, level) in processing order: the next finer level of k, or the first usable level of k + 1
     auto issue_next_P = [&](int k, int level) {
         if (level > 0) issue_P(gxi, gyi, level - 1);
-        else if (k + 1 < k1) issue_P(gxn, gyn, top);
+        else if (k + 1 < k1 && first_next >= 0) issue_P(gxn, gyn, first_next);
     };
-    if (k0 < k1) issue_P(gxi, gyi, top);
+    if (k0 < k1) {
+        first_next = 31 - __clz(__ballot_sync(0xffffffffu, load_D(k0) != 0.f));
+        if (first_next >= 0) issue_P(gxi, gyi, first_next);
+    }
 
     for (int k = k0; k < k1; k++, gxi = gxn, gyi = gyn) {
         if (++ky == p.gy) { ky = 0; gxn = gxi + p.ps; gyn = 0; }
@@ -334,7 +345,14 @@ __global__ void __launch_bounds__(32, 18) k_lk_phase(const LkParams p, const __g
         const float2 pt = make_float2((float)gxi, (float)gyi);
         float2 nxt = make_float2(0.f, 0.f);
         int st = 1;
-        const LkLevelRec *rec = p.wsum + ((size_t)(p.ph_pair0 + b) * p.g.nlev + top) * p.P + k;      // the level scalars (k_window_sums)
+        const LkLevelRec *rec = rec_top + k;      // the level scalars (k_window_sums), walked down with the levels
+        first_cur = first_next;
+        first_next = -1;
+        const float d_next = k + 1 < k1 ? load_D(k + 1) : 0.f;      // lands long before level 0 looks at it
+        if (first_cur < 0) {                    // no usable level at all: nothing will be requested for this point, keep the chain going
+            first_next = 31 - __clz(__ballot_sync(0xffffffffu, d_next != 0.f));
+            issue_next_P(k, 0);
+        }
 
         for (int level = top; level >= 0; level--, rec -= p.P) {
             const int Lw = p.g.lv[level].w, Lh = p.g.lv[level].h;
@@ -344,6 +362,11 @@ __global__ void __launch_bounds__(32, 18) k_lk_phase(const LkParams p, const __g
             if (level == top) { s.npx = ppx; s.npy = ppy; }
             else { s.npx = nxt.x * 2.f; s.npy = nxt.y * 2.f; }
             nxt = make_float2(s.npx, s.npy);
+            if (level > first_cur) {            // failed level above the first usable one (or no usable level): stepped over
+                if (level == 0) st = 0;
+                continue;
+            }
+            if (level == 0) first_next = 31 - __clz(__ballot_sync(0xffffffffu, d_next != 0.f));
             ppx = __fsub_rn(ppx, half); ppy = __fsub_rn(ppy, half);
             const int ipx = __float2int_rd(ppx), ipy = __float2int_rd(ppy);
             if (ipx < -WIN || ipx >= Lw || ipy < -WIN || ipy >= Lh) {
