@@ -549,8 +549,8 @@ def main():
     except Exception:
         model, ipp_ncu = None, None
     if model and lk_taps and a.pixel_step == 10 and (w, h) == (1920, 1080) and not vf:
-        nlev = getattr(ctx, "levels", 5)
-        ipp = model["per_point"] + model["per_level_visited"] * nlev + model["per_iteration"] * lk_taps["iterations_per_point"]
+        ipp = (model["per_point"] + model["per_level_iterated"] * lk_taps["levels_iterated_per_point"]
+               + model["per_iteration"] * lk_taps["iterations_per_point"])
         sm_mhz = clocks.get("sm_mhz") or 1965.0
         peak_issue = 148 * 4 * sm_mhz * 1e6                       # one warp instruction per scheduler per clock
         ach = ipp * P * B / (stage_ms[1] * 1e-3)
@@ -558,8 +558,8 @@ def main():
                              "unit": "G warp-instr/s", "frac": ach / peak_issue, "warp_instr_per_point": ipp,
                              "warp_instr_per_point_ncu": ipp_ncu,
                              "thread_instr_per_window_tap": 32.0 * ipp / (1600.0 * lk_taps["iterations_per_point"]),
-                             "source": "k_lk_phase only: per-region static SASS counts (profiles/r02_k2_ncu_full.txt) x iterations per point "
-                                       "counted on the device in this run; the time is the whole K2 stage (planes + window sums + LK), "
+                             "source": "k_lk_phase only: per-region static SASS counts (profiles/r02_lk_phase_regions.txt) x levels and iterations per "
+                                       "point counted on the device in this run; the time is the whole K2 stage (planes + window sums + LK), "
                                        "so frac is a lower bound of the LK kernel's own issue utilisation (79 % under ncu)"}
 
     # ---- e2e: C ABI with HOST (pinned) buffers, H2D + D2H inside the timed region
