@@ -491,8 +491,7 @@ cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pair
         cudaError_t e0 = launch_lk_planes(p, pairs, s);
         if (e0 != cudaSuccess) return e0;
     }
-    static int npts_env = -1;
-    if (npts_env < 0) { const char *e = getenv("MD_LK_NPTS"); npts_env = e ? atoi(e) : 0; }
+    static const int npts_env = [] { const char *e = getenv("MD_LK_NPTS"); return e ? atoi(e) : 0; }();      // read once (thread-safe init)
     auto go = [&](auto kern, int NPTS) {
         const size_t smem = (size_t)PhTile::WARP_BYTES + 128;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
