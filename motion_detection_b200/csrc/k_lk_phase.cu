@@ -501,9 +501,12 @@ cudaError_t launch_lk_phase(const LkParams &p, const LkPhaseMaps *maps, int pair
         MD_COUNT_LAUNCH(1);
         return cudaGetLastError();
     };
-    // points per one-warp CTA (MD_LK_NPTS = 1 | 4 | 16 selects the other builds: tuning aid)
+    // points per one-warp CTA (MD_LK_NPTS = 1 | 2 | 8 | 16 selects the other builds: tuning aid).  Measured on the default bench,
+    // value / e2e frames/s: 1: 5 397 / 4 696, 4: 5 480 / 4 773, 8: 5 437 / 4 725, 16: 5 384 (longer CTAs leave a longer tail per launch,
+    // and the host-buffer pipeline launches six LK kernels per batch)
     if (npts_env == 1) return go(k_lk_phase<1>, 1);
-    if (npts_env == 4) return go(k_lk_phase<4>, 4);
+    if (npts_env == 2) return go(k_lk_phase<2>, 2);
+    if (npts_env == 8) return go(k_lk_phase<8>, 8);
     if (npts_env == 16) return go(k_lk_phase<16>, 16);
-    return go(k_lk_phase<8>, 8);
+    return go(k_lk_phase<4>, 4);
 }
