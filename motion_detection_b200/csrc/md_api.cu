@@ -791,7 +791,7 @@ static int run_post(md_ctx *ctx, int prev0, int p0, int p1, float2 *d_next, uint
 //   copy_out: D2H(c)           after K4(c)          (host buffers only)
 // The context's stream joins aux_post at the end, so the call stays stream-ordered for the caller.
 #define MD_PIPE_CHUNKS_DEVICE 2   // device-resident frames: measured 4 193 pairs/s with 2 even chunks, 4 146 with 3, 4 060 with 4, 3 675 with 6
-#define MD_PIPE_CHUNKS 6      // host buffers, 32 pairs: measured e2e 3 297 / 3 750 / 3 906 / 3 953 / 4 003 pairs/s with 3 / 4 / 5 / 6 / 8 chunks; a short first chunk (its K1 / H2D is exposed), even middle chunks, a short last chunk (its K3 / K4 / D2H is)
+#define MD_PIPE_CHUNKS 7      // host buffers, 32 pairs: measured e2e 4 649 / 4 821 / 4 858 / 4 824 frames/s with 5 / 6 / 7 / 8 chunks (round 2; round 1: 3 297 ... 4 003 with 3 ... 8); a short first chunk (its K1 / H2D is exposed), even middle chunks, a short last chunk (its K3 / K4 / D2H is)
 
 // Enqueues one batch (frames in ring slots prev0 ...) on the context's stream and its side streams; no allocation, no host
 // synchronisation, every side stream joined back into the context's stream: the body can run eagerly or under stream capture.
