@@ -202,7 +202,68 @@ __device__ bool affine_3pt(const double *src, const double *dst, double *H)
     return true;
 }
 
-__global__ void __launch_bounds__(64) k_hypotheses(const EgoParams p)
+// perspective_4pt with one matrix ROW per lane: 8 consecutive lanes (a shuffle group of width 8) solve one hypothesis.  Every
+// element sees exactly the operations of solve_lu above, in the same order (the row updates of one elimination step are independent
+// of each other; the pivot is the first row of maximal |a| like the serial search with its strict >), so the result is bit-identical
+// to the serial routine -- but the 8 x 8 system lives in registers instead of a dynamically indexed local array and a step's seven
+// row updates run side by side.  All 32 lanes of a warp must call this together (idle groups pass any finite data).
+__device__ __forceinline__ bool perspective_4pt_rows(double sx, double sy, double X, double Y, int r, double (&x)[8])
+{
+    // lane r holds the source / target point r & 3: rows 0-3 are the x equations, rows 4-7 the y equations of the four points
+    const double T = r < 4 ? X : Y;
+    double a[8], b = T;
+    a[0] = r < 4 ? sx : 0.0; a[1] = r < 4 ? sy : 0.0; a[2] = r < 4 ? 1.0 : 0.0;
+    a[3] = r < 4 ? 0.0 : sx; a[4] = r < 4 ? 0.0 : sy; a[5] = r < 4 ? 0.0 : 1.0;
+    a[6] = __dmul_rn(-sx, T); a[7] = __dmul_rn(-sy, T);
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        // pivot: the first row >= i with the largest |a[i]|
+        double best = r >= i ? fabs(a[i]) : -1.0;
+        int k = r;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o, 8);
+            const int ok_ = __shfl_xor_sync(0xffffffffu, k, o, 8);
+            if (ob > best || (ob == best && ok_ < k)) { best = ob; k = ok_; }
+        }
+        if (best < DBL_EPSILON * 100) ok = false;
+        // swap rows i and k (lane i <-> lane k)
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const double fk = __shfl_sync(0xffffffffu, a[c], k, 8), fi = __shfl_sync(0xffffffffu, a[c], i, 8);
+            if (k != i) { if (r == i) a[c] = fk; else if (r == k) a[c] = fi; }
+        }
+        {
+            const double fk = __shfl_sync(0xffffffffu, b, k, 8), fi = __shfl_sync(0xffffffffu, b, i, 8);
+            if (k != i) { if (r == i) b = fk; else if (r == k) b = fi; }
+        }
+        // eliminate column i below the pivot row
+        const double pii = __shfl_sync(0xffffffffu, a[i], i, 8);
+        const double d = __ddiv_rn(-1.0, pii);
+        const double alpha = __dmul_rn(a[i], d);
+#pragma unroll
+        for (int c = i + 1; c < 8; c++) {
+            const double pc = __shfl_sync(0xffffffffu, a[c], i, 8);
+            if (r > i) a[c] = __dadd_rn(a[c], __dmul_rn(alpha, pc));
+        }
+        const double pb = __shfl_sync(0xffffffffu, b, i, 8);
+        if (r > i) b = __dadd_rn(b, __dmul_rn(alpha, pb));
+    }
+    // back substitution: row i waits for x[i + 1 .. 7]
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+        double sacc = b;
+#pragma unroll
+        for (int c = i + 1; c < 8; c++) sacc = __dsub_rn(sacc, __dmul_rn(a[c], x[c]));
+        const double xi = __ddiv_rn(sacc, a[i]);
+        x[i] = __shfl_sync(0xffffffffu, xi, i, 8);
+    }
+    return ok;
+}
+
+#define HYP_THREADS 512
+__global__ void __launch_bounds__(HYP_THREADS) k_hypotheses(const EgoParams p)
 {
     const int b = blockIdx.x;
     __shared__ int s_idx[MD_MAX_HYP * 4];
@@ -219,22 +280,47 @@ __global__ void __launch_bounds__(64) k_hypotheses(const EgoParams p)
         }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < nh; j += blockDim.x) {
-        double *H = p.hyp + ((size_t)b * p.iters + j) * 9;
-        bool ok = false;
-        if (M >= p.minimal) {
-            double s[8], d[8];
-            for (int k = 0; k < p.minimal; k++) {
-                int c = p.kept_idx[(size_t)b * p.P + s_idx[j * p.minimal + k]];
-                float2 a = src_point(p, b, c), q = p.next[(size_t)b * p.P + c];
-                s[2 * k] = a.x; s[2 * k + 1] = a.y; d[2 * k] = q.x; d[2 * k + 1] = q.y;
+    if (p.mode == MD_EGO_RANSAC_AFFINE) {                    // two 3 x 3 solves per hypothesis: one thread each
+        for (int j = threadIdx.x; j < nh; j += blockDim.x) {
+            double *H = p.hyp + ((size_t)b * p.iters + j) * 9;
+            bool ok = false;
+            if (M >= p.minimal) {
+                double s[8], d[8];
+                for (int k = 0; k < p.minimal; k++) {
+                    int c = p.kept_idx[(size_t)b * p.P + s_idx[j * p.minimal + k]];
+                    float2 a = src_point(p, b, c), q = p.next[(size_t)b * p.P + c];
+                    s[2 * k] = a.x; s[2 * k + 1] = a.y; d[2 * k] = q.x; d[2 * k + 1] = q.y;
+                }
+                double Hk[9];
+                ok = affine_3pt(s, d, Hk);
+                if (ok) for (int i = 0; i < 9; i++) H[i] = Hk[i];
             }
-            double Hk[9];
-            ok = p.mode == MD_EGO_RANSAC_AFFINE ? affine_3pt(s, d, Hk) : perspective_4pt(s, d, Hk);
-            if (ok) for (int i = 0; i < 9; i++) H[i] = Hk[i];
+            if (!ok) for (int i = 0; i < 9; i++) H[i] = 0;
+            p.hyp_valid[b * p.iters + j] = ok ? 1 : 0;
         }
-        if (!ok) for (int i = 0; i < 9; i++) H[i] = 0;
-        p.hyp_valid[b * p.iters + j] = ok ? 1 : 0;
+        return;
+    }
+    // homography: 8 lanes per hypothesis, one matrix row each (whole warps run the solver together)
+    const int r = threadIdx.x & 7;
+    for (int j0 = 0; j0 < nh; j0 += HYP_THREADS / 8) {
+        const int j = j0 + (threadIdx.x >> 3);
+        const bool act = j < nh && M >= p.minimal;
+        double sx = (r & 1) ? 1.0 : 0.0, sy = (r & 2) ? 1.0 : 0.0, X = sx, Y = sy;      // idle groups: a harmless unit square
+        if (act) {
+            const int c = p.kept_idx[(size_t)b * p.P + s_idx[j * 4 + (r & 3)]];
+            const float2 a = src_point(p, b, c), q = p.next[(size_t)b * p.P + c];
+            sx = a.x; sy = a.y; X = q.x; Y = q.y;
+        }
+        double x[8];
+        const bool ok = perspective_4pt_rows(sx, sy, X, Y, r, x) && act;
+        if (j < nh) {
+            double *H = p.hyp + ((size_t)b * p.iters + j) * 9;
+            double hr = 0.0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) if (r == i) hr = x[i];
+            H[r] = ok ? hr : 0.0;
+            if (r == 0) { H[8] = ok ? 1.0 : 0.0; p.hyp_valid[b * p.iters + j] = ok ? 1 : 0; }
+        }
     }
 }
 
@@ -442,7 +528,7 @@ cudaError_t launch_ego(const EgoParams &p, int pairs, cudaStream_t s)
     k_keep_count<<<gs, 256, 0, s>>>(p);
     k_scan<<<pairs, 1024, 0, s>>>(p);
     k_compact<<<gs, 256, 0, s>>>(p);
-    k_hypotheses<<<pairs, 64, 0, s>>>(p);
+    k_hypotheses<<<pairs, HYP_THREADS, 0, s>>>(p);
     if (p.mode != MD_EGO_FIRST4) {
         int nb = (p.P + 255) / 256;
         if (nb > 592) nb = 592;
