@@ -142,6 +142,19 @@ __device__ int glibc_rand(GlibcRand &st)
     return (int)out;
 }
 
+// The same generator with its 31-word state in REGISTERS: 31 consecutive rand() calls from the initial position (f = 3, b = 0) are
+// r[(3 + t) % 31] += r[t] for t = 0 .. 30 and bring f back to 3, so a round unrolls into 31 adds with static indices (the ring in a
+// dynamically indexed local array costs a dependent local-memory round trip per call: ~40 us for the 510 calls of a pair, which
+// was the whole duration of k_hypotheses).  out != nullptr: the round's 31 outputs (r >> 1) are stored.
+__device__ __forceinline__ void glibc_rand_round31(uint32_t (&r)[31], int *out)
+{
+#pragma unroll
+    for (int t = 0; t < 31; t++) {
+        r[(3 + t) % 31] += r[t];
+        if (out) out[t] = (int)(r[(3 + t) % 31] >> 1);
+    }
+}
+
 // Gaussian elimination with partial pivoting, same operation order as the oracle's solve_lu (no FMA contraction)
 __device__ bool solve_lu(double *A, double *b, int n)
 {
@@ -266,19 +279,34 @@ __device__ __forceinline__ bool perspective_4pt_rows(double sx, double sy, doubl
 __global__ void __launch_bounds__(HYP_THREADS) k_hypotheses(const EgoParams p)
 {
     const int b = blockIdx.x;
-    __shared__ int s_idx[MD_MAX_HYP * 4];
+    __shared__ int s_idx[MD_MAX_HYP * 4 + 31];
     const int M = p.M[b];
     const int nh = p.mode == MD_EGO_FIRST4 ? 1 : p.iters;
+    const int ndraw = nh * p.minimal;
     if (threadIdx.x == 0 && M >= p.minimal) {
         if (p.mode == MD_EGO_FIRST4) {
             for (int k = 0; k < 4; k++) s_idx[k] = k;
         } else {
-            GlibcRand st;
-            glibc_srand(st, p.seed0 + (uint32_t)b + (p.pair_ctr ? (uint32_t)*p.pair_ctr : 0u));
-            for (int i = 0; i < 310; i++) (void)glibc_rand(st);
-            for (int i = 0; i < nh * p.minimal; i++) s_idx[i] = glibc_rand(st) % M;
+            // srand(seed), 310 discarded outputs (10 rounds), then the draws, a round of 31 at a time
+            uint32_t seed = p.seed0 + (uint32_t)b + (p.pair_ctr ? (uint32_t)*p.pair_ctr : 0u);
+            if (seed == 0) seed = 1;
+            uint32_t r[31];
+            r[0] = seed;
+#pragma unroll
+            for (int i = 1; i < 31; i++) {
+                const int32_t prev = (int32_t)r[i - 1];
+                const long long hi = prev / 127773, lo = prev % 127773;
+                long long word = 16807 * lo - 2836 * hi;
+                if (word < 0) word += 2147483647;
+                r[i] = (uint32_t)(int32_t)word;
+            }
+            for (int i = 0; i < 10; i++) glibc_rand_round31(r, nullptr);
+            for (int i = 0; i < ndraw; i += 31) glibc_rand_round31(r, s_idx + i);
         }
     }
+    __syncthreads();
+    if (p.mode != MD_EGO_FIRST4 && M >= p.minimal)
+        for (int i = threadIdx.x; i < ndraw; i += blockDim.x) s_idx[i] = s_idx[i] % M;       // rand() % M, all threads
     __syncthreads();
     if (p.mode == MD_EGO_RANSAC_AFFINE) {                    // two 3 x 3 solves per hypothesis: one thread each
         for (int j = threadIdx.x; j < nh; j += blockDim.x) {
