@@ -220,14 +220,8 @@ __device__ bool affine_3pt(const double *src, const double *dst, double *H)
 // of each other; the pivot is the first row of maximal |a| like the serial search with its strict >), so the result is bit-identical
 // to the serial routine -- but the 8 x 8 system lives in registers instead of a dynamically indexed local array and a step's seven
 // row updates run side by side.  All 32 lanes of a warp must call this together (idle groups pass any finite data).
-__device__ __forceinline__ bool perspective_4pt_rows(double sx, double sy, double X, double Y, int r, double (&x)[8])
+__device__ __forceinline__ bool solve8_rows(double (&a)[8], double b, int r, double (&x)[8])
 {
-    // lane r holds the source / target point r & 3: rows 0-3 are the x equations, rows 4-7 the y equations of the four points
-    const double T = r < 4 ? X : Y;
-    double a[8], b = T;
-    a[0] = r < 4 ? sx : 0.0; a[1] = r < 4 ? sy : 0.0; a[2] = r < 4 ? 1.0 : 0.0;
-    a[3] = r < 4 ? 0.0 : sx; a[4] = r < 4 ? 0.0 : sy; a[5] = r < 4 ? 0.0 : 1.0;
-    a[6] = __dmul_rn(-sx, T); a[7] = __dmul_rn(-sy, T);
     bool ok = true;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -273,6 +267,16 @@ __device__ __forceinline__ bool perspective_4pt_rows(double sx, double sy, doubl
         x[i] = __shfl_sync(0xffffffffu, xi, i, 8);
     }
     return ok;
+}
+__device__ __forceinline__ bool perspective_4pt_rows(double sx, double sy, double X, double Y, int r, double (&x)[8])
+{
+    // lane r holds the source / target point r & 3: rows 0-3 are the x equations, rows 4-7 the y equations of the four points
+    const double T = r < 4 ? X : Y;
+    double a[8];
+    a[0] = r < 4 ? sx : 0.0; a[1] = r < 4 ? sy : 0.0; a[2] = r < 4 ? 1.0 : 0.0;
+    a[3] = r < 4 ? 0.0 : sx; a[4] = r < 4 ? 0.0 : sy; a[5] = r < 4 ? 0.0 : 1.0;
+    a[6] = __dmul_rn(-sx, T); a[7] = __dmul_rn(-sy, T);
+    return solve8_rows(a, T, r, x);
 }
 
 #define HYP_THREADS 512
@@ -479,10 +483,44 @@ __global__ void __launch_bounds__(32) k_solve(const EgoParams p)
         S[threadIdx.x] = v;
     }
     __syncwarp();
+    const int M = p.M[b];
+    // the 8 x 8 normal equations of the homography refit, one row per lane (lanes 0-7; the other lanes solve an identity): same
+    // arithmetic as solve_lu on the matrix thread 0 used to assemble
+    double xr[8];
+    bool ok_rows = false;
+    if (p.mode == MD_EGO_RANSAC_HOMOGRAPHY) {                 // warp-uniform
+        const int r = threadIdx.x & 7;
+        double a[8], rhs;
+#pragma unroll
+        for (int c = 0; c < 8; c++) a[c] = r == c ? 1.0 : 0.0;
+        rhs = 0.0;
+        if (threadIdx.x < 8) {
+            const double u[6] = {S[0], S[1], S[2], S[3], S[4], S[5]};
+            const double c6[6] = {-S[6], -S[7], -S[8], -S[12], -S[13], -S[14]};
+            const double c7[6] = {-S[7], -S[9], -S[10], -S[13], -S[15], -S[16]};
+            const double rr[8] = {S[8], S[10], S[11], S[14], S[16], S[17], -S[21], -S[22]};
+            const int sym[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (r != q) continue;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    double v = 0.0;
+                    if (q < 6) {
+                        if (c < 6) v = (q / 3 == c / 3) ? u[sym[q % 3][c % 3]] : 0.0;
+                        else v = c == 6 ? c6[q] : c7[q];
+                    } else if (q == 6) v = c < 6 ? c6[c] : (c == 6 ? S[18] : S[19]);
+                    else v = c < 6 ? c7[c] : (c == 6 ? S[19] : S[20]);
+                    a[c] = v;
+                }
+                rhs = rr[q];
+            }
+        }
+        ok_rows = solve8_rows(a, rhs, r, xr);
+    }
     if (threadIdx.x != 0) return;
     double H[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     int inl = 0, valid = 0;
-    const int M = p.M[b];
     if (p.mode == MD_EGO_FIRST4) {
         if (M >= 4 && p.hyp_valid[b * p.iters]) {
             for (int i = 0; i < 9; i++) H[i] = p.hyp[(size_t)b * p.iters * 9 + i];
@@ -503,24 +541,8 @@ __global__ void __launch_bounds__(32) k_solve(const EgoParams p)
                 Hn[0] = r[0]; Hn[1] = r[1]; Hn[2] = r[2]; Hn[3] = r2[0]; Hn[4] = r2[1]; Hn[5] = r2[2];
                 Hn[6] = 0; Hn[7] = 0; Hn[8] = 1;
             } else {
-                double N[64];
-                for (int i = 0; i < 64; i++) N[i] = 0;
-                const double u[6] = {S[0], S[1], S[2], S[3], S[4], S[5]};
-                for (int o = 0; o < 6; o += 3) {
-                    N[(o + 0) * 8 + o + 0] = u[0]; N[(o + 0) * 8 + o + 1] = u[1]; N[(o + 0) * 8 + o + 2] = u[2];
-                    N[(o + 1) * 8 + o + 0] = u[1]; N[(o + 1) * 8 + o + 1] = u[3]; N[(o + 1) * 8 + o + 2] = u[4];
-                    N[(o + 2) * 8 + o + 0] = u[2]; N[(o + 2) * 8 + o + 1] = u[4]; N[(o + 2) * 8 + o + 2] = u[5];
-                }
-                const double c6[6] = {-S[6], -S[7], -S[8], -S[12], -S[13], -S[14]};
-                const double c7[6] = {-S[7], -S[9], -S[10], -S[13], -S[15], -S[16]};
-                for (int i = 0; i < 6; i++) {
-                    N[i * 8 + 6] = N[6 * 8 + i] = c6[i];
-                    N[i * 8 + 7] = N[7 * 8 + i] = c7[i];
-                }
-                N[6 * 8 + 6] = S[18]; N[6 * 8 + 7] = N[7 * 8 + 6] = S[19]; N[7 * 8 + 7] = S[20];
-                double r[8] = {S[8], S[10], S[11], S[14], S[16], S[17], -S[21], -S[22]};
-                ok = solve_lu(N, r, 8);
-                for (int i = 0; i < 8; i++) Hn[i] = r[i];
+                ok = ok_rows;
+                for (int i = 0; i < 8; i++) Hn[i] = xr[i];
                 Hn[8] = 1;
             }
             if (ok) {
