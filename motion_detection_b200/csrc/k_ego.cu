@@ -479,7 +479,16 @@ __global__ void __launch_bounds__(32) k_solve(const EgoParams p)
     __shared__ double S[NSUM];
     if (threadIdx.x < NSUM) {
         double v = 0;
-        for (int k = 0; k < p.nblk_acc; k++) v += p.partial[((size_t)b * p.nblk_acc + k) * NSUM + threadIdx.x];   // fixed order
+        const double *pp = p.partial + (size_t)b * p.nblk_acc * NSUM + threadIdx.x;
+        int k = 0;
+        for (; k + 8 <= p.nblk_acc; k += 8) {                 // eight loads in flight, added in the same fixed order
+            double t[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) t[u] = __ldg(pp + (size_t)(k + u) * NSUM);
+#pragma unroll
+            for (int u = 0; u < 8; u++) v += t[u];
+        }
+        for (; k < p.nblk_acc; k++) v += __ldg(pp + (size_t)k * NSUM);
         S[threadIdx.x] = v;
     }
     __syncwarp();
