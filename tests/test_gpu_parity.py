@@ -401,3 +401,35 @@ def test_varflow_fast_mode_is_within_budget(capi, oracle):
     U, V = ctx.varflow(fr[0], fr[1])
     Uo, Vo = oracle.varflow(fr[0], fr[1])
     assert np.sqrt((U - Uo) ** 2 + (V - Vo) ** 2).mean() < FLOW_EPE_TOL
+
+
+def test_lk_points_per_cta_builds_are_equivalent():
+    """k_lk_phase<NPTS> (points per one-warp CTA; MD_LK_NPTS selects the build, read once per process) must not change a bit:
+    the request chain (next level of this point / first usable level of the next point) differs per build, the arithmetic
+    does not.  Odd sizes: the grid is not a multiple of any NPTS and columns end inside a CTA."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from motion_detection_b200 import capi, synth\n"
+        "h = hashlib.sha256()\n"
+        "for (w, hh, ps) in ((320, 240, 10), (333, 211, 7), (640, 480, 16)):\n"
+        "    fr, _ = synth.sequence(w, hh, 4, seed=5)\n"
+        "    ctx = capi.Context(width=w, height=hh, max_batch=3, pixel_step=ps, min_vector_size=0.2, seed=1)\n"
+        "    r = ctx.process_batch(fr)\n"
+        "    for k in ('next', 'status', 'keep', 'H', 'mask'):\n"
+        "        h.update(np.ascontiguousarray(r[k]).tobytes())\n"
+        "    ctx.close()\n"
+        "print(h.hexdigest())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    digests = {}
+    for n in ("", "1", "2", "8", "16"):
+        env = dict(os.environ)
+        env.pop("MD_LK_NPTS", None)
+        if n:
+            env["MD_LK_NPTS"] = n
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests[n or "default"] = out.stdout.strip().splitlines()[-1]
+    assert len(set(digests.values())) == 1, digests
