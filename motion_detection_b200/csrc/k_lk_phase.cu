@@ -213,6 +213,204 @@ __global__ void __launch_bounds__(256) k_window_sums(const PhParams q, int level
     }
 }
 
+// ---- single-pass window sums (and, FUSED, the Ix / Iy phase planes themselves) ------------------------------------------------
+// For lattice steps that divide the window (40 % step == 0, step >= 5: every level of pixel_step 5, 10, 20, 40) each plane row is
+// visited ONCE: a thread walks down two adjacent plane columns with a running prefix of the five products (uint32, wrap-around: a
+// difference of two prefixes 40 rows apart is the exact window column sum, which fits 31 bits), parks the prefix of every lattice row
+// boundary in a thread-private ring of R = 40 / step entries in shared memory, and at boundary k emits prefix(k) - prefix(k - R) =
+// the column sums of the window of lattice row k - R.  No row is subtracted again (k_window_sums reads every row 1.7 - 2.4 times).
+// The horizontal phase adds the column sums of a lattice row in two levels -- sums of `step` adjacent columns (int64), then R of
+// those per point -- instead of 40 columns per point.
+// FUSED: the window samples are not loaded from the phase planes but evaluated on the way down from the padded pyramid level
+// (image + Scharr planes, exactly k_phase_planes' expressions); the Ix / Iy samples are stored for k_lk_phase, the I samples
+// (a third of the plane bytes, read by nobody else) are never materialised, and k_phase_planes is not launched for the level.
+// Only plane pixels inside some grid point's window are written: k_lk_phase uses nothing else of a plane.
+#define WR_NT 128
+#define WR_COLS (2 * WR_NT)
+#define WR_GRP 2
+#define WR_NG (WR_COLS / 5 + 3)
+__device__ __forceinline__ void wr_accumulate(unsigned (&acc)[2][5], int i0, int i1, int x0, int x1, int y0, int y1)
+{
+    acc[0][0] += (unsigned)(x0 * x0); acc[0][1] += (unsigned)(x0 * y0); acc[0][2] += (unsigned)(y0 * y0);
+    acc[0][3] += (unsigned)(i0 * x0); acc[0][4] += (unsigned)(i0 * y0);
+    acc[1][0] += (unsigned)(x1 * x1); acc[1][1] += (unsigned)(x1 * y1); acc[1][2] += (unsigned)(y1 * y1);
+    acc[1][3] += (unsigned)(i1 * x1); acc[1][4] += (unsigned)(i1 * y1);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(WR_NT) k_window_sums_ring(const PhParams q, int level, int cp, int nchunk_x, int seg)
+{
+    extern __shared__ __align__(16) int wr_smem[];
+    const PhaseLevel PL = q.pg.lv[level];
+    const int ncx = PL.ncx, cls = blockIdx.y, cx = cls % ncx, cy = cls / ncx, b = blockIdx.z;
+    const int chunk = blockIdx.x % nchunk_x, sg = blockIdx.x / nchunk_x;
+    const int msk = (1 << level) - 1;
+    const int step = q.ps >> PL.shift;
+    const int R = 40 / step;
+    const float scale = lk_level_scale(level);
+    int kx0 = -1, ky0 = -1;
+    for (int t = 0; t < ncx; t++) {
+        if (kx0 < 0 && t < q.gx && (((q.ps * t) & msk) >> PL.shift) == cx) kx0 = t;
+        if (ky0 < 0 && t < q.gy && (((q.ps * t) & msk) >> PL.shift) == cy) ky0 = t;
+    }
+    if (kx0 < 0 || ky0 < 0) return;
+    const int nx = (q.gx - kx0 + ncx - 1) / ncx, ny = (q.gy - ky0 + ncx - 1) / ncx;
+    const int i0 = chunk * cp, i1 = min(nx, i0 + cp);
+    const int j0 = sg * seg, j1 = min(ny, j0 + seg);
+    if (i0 >= i1 || j0 >= j1) return;
+    const int per_row = i1 - i0, nlat = j1 - j0;
+    const int ox0 = __float2int_rd(__fsub_rn((float)(q.ps * (kx0 + i0 * ncx)) * scale, q.half)) + MD_PH_MARGIN;
+    const int oy0 = __float2int_rd(__fsub_rn((float)(q.ps * (ky0 + j0 * ncx)) * scale, q.half)) + MD_PH_MARGIN;
+    const int c_lo = ox0 & ~1, off = ox0 - c_lo;
+    const int ncols = off + (per_row - 1) * step + 40;             // <= WR_COLS by the choice of cp
+    const int tid = threadIdx.x;
+    const bool col_on = 2 * tid < ncols;
+    const size_t plane = (size_t)PL.pitch * PL.h;
+    int16_t *pbase = q.ph + (size_t)(q.pair0 + b) * q.pg.pair_elems + PL.off + (size_t)cls * 3 * plane + (size_t)oy0 * PL.pitch + c_lo + 2 * tid;
+    const int wp = PL.pitch >> 1;
+
+    int *ring = wr_smem;                                             // [R][5][WR_COLS], thread private columns
+    int *col = ring + R * 5 * WR_COLS;                               // [WR_GRP][5][WR_COLS + 8] window column sums of a group of lattice rows
+    long long *grp = reinterpret_cast<long long *>(col + WR_GRP * 5 * (WR_COLS + 8));     // [WR_GRP][5][WR_NG] sums of `step` columns
+
+    // row sources
+    const uint32_t *pI = reinterpret_cast<const uint32_t *>(pbase), *pX = pI + (plane >> 1), *pY = pX + (plane >> 1);   // !FUSED
+    uint32_t *oX = reinterpret_cast<uint32_t *>(pbase) + (plane >> 1), *oY = oX + (plane >> 1);                      // FUSED
+    const uint8_t *ip = nullptr;
+    const short2 *dp = nullptr;
+    int spitch = 0;
+    int w00 = 0, w01 = 0, w10 = 0, w11 = 0;
+    int ti[2] = {0, 0}, tx[2] = {0, 0}, ty[2] = {0, 0};            // top halves of the current plane row (FUSED)
+    if (FUSED) {
+        const LevelGeom L = q.g.lv[level];
+        const float ppx = __fsub_rn((float)(cx << PL.shift) * scale, q.half), ppy = __fsub_rn((float)(cy << PL.shift) * scale, q.half);
+        lk_weights(__fsub_rn(ppx, floorf(ppx)), __fsub_rn(ppy, floorf(ppy)), w00, w01, w10, w11);
+        const int slot = (q.prev_slot0 + b) % q.g.nslots;
+        spitch = L.pitch;
+        const size_t src0 = (size_t)(q.g.pady - MD_PH_MARGIN + oy0) * L.pitch + (q.g.padx - MD_PH_MARGIN + c_lo + 2 * tid);
+        ip = q.img + (size_t)slot * q.g.slot_img_bytes + L.img_off + src0;
+        dp = q.der + (size_t)slot * q.g.slot_der_elems + L.der_off + src0;
+        if (col_on) {
+            const uint32_t pw = *reinterpret_cast<const uint16_t *>(ip), p2 = ip[2];
+            const uint2 dw = *reinterpret_cast<const uint2 *>(dp);
+            const uint32_t d2 = *reinterpret_cast<const uint32_t *>(dp + 2);
+            const int a0 = (int)(pw & 0xffu), a1 = (int)(pw >> 8), a2 = (int)p2;
+            const int x0 = (int)(short)(dw.x & 0xffffu), x1 = (int)(short)(dw.y & 0xffffu), x2 = (int)(short)(d2 & 0xffffu);
+            const int y0 = (int)dw.x >> 16, y1 = (int)dw.y >> 16, y2 = (int)d2 >> 16;
+            ti[0] = w00 * a0 + w01 * a1; ti[1] = w00 * a1 + w01 * a2;
+            tx[0] = w00 * x0 + w01 * x1; tx[1] = w00 * x1 + w01 * x2;
+            ty[0] = w00 * y0 + w01 * y1; ty[1] = w00 * y1 + w01 * y2;
+        }
+        ip += spitch; dp += spitch;                                  // plane row Y takes its bottom half from source row Y + 1
+    }
+
+    unsigned acc[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    const int K = nlat + R;                                          // lattice row boundaries met on the way down
+    int slot_r = 0, g = 0, jg = j0;
+    for (int k = 0; k < K; k++) {
+        if (col_on) {
+            int *rg = ring + slot_r * 5 * WR_COLS + 2 * tid;
+            if (k >= R) {
+                int *cg = col + g * 5 * (WR_COLS + 8) + 2 * tid;
+#pragma unroll
+                for (int t = 0; t < 5; t++) {
+                    const int2 old = *reinterpret_cast<const int2 *>(rg + t * WR_COLS);
+                    *reinterpret_cast<int2 *>(cg + t * (WR_COLS + 8)) = make_int2((int)(acc[0][t] - (unsigned)old.x), (int)(acc[1][t] - (unsigned)old.y));
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 5; t++) *reinterpret_cast<int2 *>(rg + t * WR_COLS) = make_int2((int)acc[0][t], (int)acc[1][t]);
+        }
+        if (++slot_r == R) slot_r = 0;
+        if (k >= R && (++g == WR_GRP || k == K - 1)) {
+            // the points of g lattice rows (first: jg): sums of `step` adjacent column sums, then R of those per point and the level
+            // scalars k_lk_phase needs (f32 matrix entries, minimum-eigenvalue / determinant test, 1 / det), once per point
+            const int NG = per_row - 1 + R;
+            __syncthreads();
+            for (int e = tid; e < g * 5 * NG; e += WR_NT) {
+                const int row = e / NG, gi = e - row * NG;           // row = (lattice row of the group) * 5 + quantity
+                const int *v = col + row * (WR_COLS + 8) + off + gi * step;
+                long long s = 0;
+                for (int c = 0; c < step; c++) s += v[c];
+                grp[row * WR_NG + gi] = s;
+            }
+            __syncthreads();
+            for (int e = tid; e < g * per_row; e += WR_NT) {
+                const int gg = e / per_row, pi = e - gg * per_row;
+                long long sum[5];
+#pragma unroll
+                for (int t = 0; t < 5; t++) {
+                    const long long *v = grp + (gg * 5 + t) * WR_NG + pi;
+                    long long s = 0;
+                    for (int c = 0; c < R; c++) s += v[c];
+                    sum[t] = s;
+                }
+                const float FLT_SCALE = 1.f / (1 << 20);
+                const float A11 = (float)sum[0] * FLT_SCALE, A12 = (float)sum[1] * FLT_SCALE, A22 = (float)sum[2] * FLT_SCALE;
+                float D;
+                const float Dinv = lk_min_eig_ok(A11, A12, A22, 40, q.min_eig, D) ? D : 0.f;
+                const int kx = kx0 + (i0 + pi) * ncx, ky = ky0 + (jg + gg) * ncx;
+                LkLevelRec *o = q.wsum + (((size_t)(q.pair0 + b) * q.g.nlev + level) * q.P) + (size_t)kx * q.gy + ky;
+                *reinterpret_cast<float4 *>(o) = make_float4(A11, A12, A22, Dinv);
+                *reinterpret_cast<longlong2 *>(&o->C1) = make_longlong2(sum[3], sum[4]);
+            }
+            jg += g; g = 0;
+        }
+        if (k == K - 1 || !col_on) continue;
+        // the `step` rows down to the next boundary, five at a time: all loads of a batch are issued before its arithmetic
+        for (int r0 = 0; r0 < step; r0 += 5) {
+            const int nr = min(5, step - r0);
+            if (FUSED) {
+                uint32_t pw[5], p2[5], d2[5];
+                uint2 dw[5];
+#pragma unroll
+                for (int u = 0; u < 5; u++) {
+                    if (u < nr) {
+                        pw[u] = __ldg(reinterpret_cast<const uint16_t *>(ip + (size_t)u * spitch)); p2[u] = __ldg(ip + (size_t)u * spitch + 2);
+                        dw[u] = __ldg(reinterpret_cast<const uint2 *>(dp + (size_t)u * spitch));
+                        d2[u] = __ldg(reinterpret_cast<const uint32_t *>(dp + (size_t)u * spitch + 2));
+                    }
+                }
+                ip += (size_t)nr * spitch; dp += (size_t)nr * spitch;
+#pragma unroll
+                for (int u = 0; u < 5; u++) {
+                    if (u < nr) {
+                        const int a0 = (int)(pw[u] & 0xffu), a1 = (int)(pw[u] >> 8), a2 = (int)p2[u];
+                        const int x0 = (int)(short)(dw[u].x & 0xffffu), x1 = (int)(short)(dw[u].y & 0xffffu), x2 = (int)(short)(d2[u] & 0xffffu);
+                        const int y0 = (int)dw[u].x >> 16, y1 = (int)dw[u].y >> 16, y2 = (int)d2[u] >> 16;
+                        const int iv0 = (ti[0] + w10 * a0 + w11 * a1 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                        const int iv1 = (ti[1] + w10 * a1 + w11 * a2 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
+                        const int xv0 = (tx[0] + w10 * x0 + w11 * x1 + (1 << (W_BITS - 1))) >> W_BITS;
+                        const int xv1 = (tx[1] + w10 * x1 + w11 * x2 + (1 << (W_BITS - 1))) >> W_BITS;
+                        const int yv0 = (ty[0] + w10 * y0 + w11 * y1 + (1 << (W_BITS - 1))) >> W_BITS;
+                        const int yv1 = (ty[1] + w10 * y1 + w11 * y2 + (1 << (W_BITS - 1))) >> W_BITS;
+                        ti[0] = w00 * a0 + w01 * a1; ti[1] = w00 * a1 + w01 * a2;
+                        tx[0] = w00 * x0 + w01 * x1; tx[1] = w00 * x1 + w01 * x2;
+                        ty[0] = w00 * y0 + w01 * y1; ty[1] = w00 * y1 + w01 * y2;
+                        oX[u * wp] = ((uint32_t)xv0 & 0xffffu) | ((uint32_t)xv1 << 16);
+                        oY[u * wp] = ((uint32_t)yv0 & 0xffffu) | ((uint32_t)yv1 << 16);
+                        wr_accumulate(acc, iv0, iv1, xv0, xv1, yv0, yv1);
+                    }
+                }
+                oX += nr * wp; oY += nr * wp;
+            } else {
+                uint32_t wi[5], wx[5], wy[5];
+#pragma unroll
+                for (int u = 0; u < 5; u++) {
+                    if (u < nr) { wi[u] = __ldg(pI + u * wp); wx[u] = __ldg(pX + u * wp); wy[u] = __ldg(pY + u * wp); }
+                }
+                pI += nr * wp; pX += nr * wp; pY += nr * wp;
+#pragma unroll
+                for (int u = 0; u < 5; u++) {
+                    if (u < nr)
+                        wr_accumulate(acc, (int)(wi[u] & 0xffffu), (int)(wi[u] >> 16), (int)(short)wx[u], (int)wx[u] >> 16, (int)(short)wy[u],
+                                      (int)wy[u] >> 16);
+                }
+            }
+        }
+    }
+}
+
 // ---- LK on phase planes ------------------------------------------------------------------------------------------------
 struct PhTile {
     static constexpr int WIN = 40, LXN = 4, LYN = 8;
@@ -471,14 +669,39 @@ cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1
         const PhaseLevel &PL = p.pg.lv[l];
         const int step = p.ps >> PL.shift;
         if (step > WS_COLS - 42) return cudaErrorInvalidConfiguration;          // one point per chunk must fit (pixel_step <= 470)
-        const int threads = (PL.pitch / 8) * ((PL.h + 3) / 4);
-        dim3 grid((threads + 255) / 256, PL.ncx * PL.ncx, pairs);
-        k_phase_planes<<<grid, 256, 0, s>>>(q, l);
-        const int cp = (WS_COLS - 42) / step + 1;                                // lattice columns per CTA
         const int nx = (q.gx + PL.ncx - 1) / PL.ncx, ny = (q.gy + PL.ncx - 1) / PL.ncx;   // upper bounds per class
+        // MD_WS_MODE: 2 (default) = planes and sums in one pass (k_window_sums_ring<true>), 1 = k_phase_planes + single-pass sums,
+        // 0 = k_phase_planes + sliding sums; lattice steps the ring kernel does not take (40 % step != 0 or step < 5) always get 0
+        static const int ws_mode = [] { const char *e = getenv("MD_WS_MODE"); return e ? atoi(e) : 2; }();
+        static const int ws_rows = [] { const char *e = getenv("MD_WS_ROWS"); return e && atoi(e) > 0 ? atoi(e) : 160; }();
+        const bool ring = ws_mode > 0 && step >= 5 && step <= 40 && 40 % step == 0;
+        if (!ring || ws_mode == 1) {
+            const int threads = (PL.pitch / 8) * ((PL.h + 3) / 4);
+            dim3 grid((threads + 255) / 256, PL.ncx * PL.ncx, pairs);
+            k_phase_planes<<<grid, 256, 0, s>>>(q, l);
+            MD_COUNT_LAUNCH(1);
+        }
+        if (ring) {
+            const int R = 40 / step, seg = max(2, ws_rows / step);
+            const int cpr = (WR_COLS - 41) / step + 1;                              // lattice columns per CTA
+            const int ncx_r = (nx + cpr - 1) / cpr, nseg_r = (ny + seg - 1) / seg;
+            const size_t smem = ((size_t)R * 5 * WR_COLS + (size_t)WR_GRP * 5 * (WR_COLS + 8)) * sizeof(int) + (size_t)WR_GRP * 5 * WR_NG * sizeof(long long);
+            static const cudaError_t attr = [] {
+                const int most = (8 * 5 * WR_COLS + WR_GRP * 5 * (WR_COLS + 8)) * (int)sizeof(int) + WR_GRP * 5 * WR_NG * (int)sizeof(long long);
+                cudaError_t e = cudaFuncSetAttribute(k_window_sums_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+                return e != cudaSuccess ? e : cudaFuncSetAttribute(k_window_sums_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+            }();
+            if (attr != cudaSuccess) return attr;
+            const dim3 grid(ncx_r * nseg_r, PL.ncx * PL.ncx, pairs);
+            if (ws_mode == 1) k_window_sums_ring<false><<<grid, WR_NT, smem, s>>>(q, l, cpr, ncx_r, seg);
+            else k_window_sums_ring<true><<<grid, WR_NT, smem, s>>>(q, l, cpr, ncx_r, seg);
+            MD_COUNT_LAUNCH(1);
+            continue;
+        }
+        const int cp = (WS_COLS - 42) / step + 1;                                // lattice columns per CTA
         const int nchunk_x = (nx + cp - 1) / cp, nseg = (ny + WS_SEG - 1) / WS_SEG;
         k_window_sums<<<dim3(nchunk_x * nseg, PL.ncx * PL.ncx, pairs), 256, 0, s>>>(q, l, cp, nchunk_x);
-        MD_COUNT_LAUNCH(2);
+        MD_COUNT_LAUNCH(1);
     }
     return cudaGetLastError();
 }

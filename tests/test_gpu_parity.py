@@ -433,3 +433,37 @@ def test_lk_points_per_cta_builds_are_equivalent():
         assert out.returncode == 0, out.stderr[-2000:]
         digests[n or "default"] = out.stdout.strip().splitlines()[-1]
     assert len(set(digests.values())) == 1, digests
+
+
+def test_window_sum_kernels_are_equivalent():
+    """The three ways the level records (and the Ix / Iy phase planes) of grid-mode LK are produced -- MD_WS_MODE 2 (default):
+    k_window_sums_ring<true>, planes and window sums in one pass down the pyramid level; 1: k_phase_planes + the single-pass sums on
+    the stored planes; 0: k_phase_planes + the sliding sums of k_window_sums -- are the same integers: whole batches must not change
+    a bit.  pixel_step 5 / 8 / 10 / 20 / 40 cover every lattice step the ring kernel takes (5, 8, 10, 20, 40) and, at the levels where
+    it does not (step 1, 2, 4), the mix of both kernels in one pyramid; odd sizes end lattice rows and columns inside a CTA."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import sys, hashlib, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from motion_detection_b200 import capi, synth\n"
+        "h = hashlib.sha256()\n"
+        "for (w, hh, ps) in ((320, 240, 10), (333, 211, 5), (640, 480, 20), (641, 479, 8), (1920, 1080, 10), (800, 600, 40)):\n"
+        "    fr, _ = synth.sequence(w, hh, 3, seed=11)\n"
+        "    ctx = capi.Context(width=w, height=hh, max_batch=2, pixel_step=ps, min_vector_size=0.2, seed=1)\n"
+        "    r = ctx.process_batch(fr)\n"
+        "    for k in ('next', 'status', 'keep', 'H', 'mask'):\n"
+        "        h.update(np.ascontiguousarray(r[k]).tobytes())\n"
+        "    ctx.close()\n"
+        "print(h.hexdigest())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    digests = {}
+    for m in ("", "1", "0"):
+        env = dict(os.environ)
+        env.pop("MD_WS_MODE", None)
+        if m:
+            env["MD_WS_MODE"] = m
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        digests[m or "default"] = out.stdout.strip().splitlines()[-1]
+    assert len(set(digests.values())) == 1, digests
