@@ -611,10 +611,71 @@ def main():
         ctx2.close()
         return res
 
+    # ---- e2e through streams.BatchPipeline: the same sequence, batches alternating over two contexts of this GPU as asynchronous
+    # host-buffer calls (MD_MEM_HOST_ASYNC; unchained, one overlap frame per batch -> B + 1 uploads per step), results identical to
+    # the chained single context (tests/test_gpu_stream.py).  Every step's H2D and D2H are inside the timed region; the host waits
+    # for (and reads) batch k - 1 after submitting batch k.
+    def measure_e2e_pipeline(lanes=2):
+        pipe = streams.BatchPipeline(lanes=lanes, width=w, height=h, max_batch=B, pixel_step=a.pixel_step, min_vector_size=0.2, seed=1,
+                                     device=local, flow_engine=engine)
+        clips = [torch.empty((B + 1, h, w), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        clips[0].copy_(host)                                     # f0 .. fB
+        clips[1].copy_(torch.flip(host, dims=[0]))               # fB .. f0: played alternately, every pair is a real consecutive pair
+        pins, houts = [], []
+        for _ in range(lanes):
+            pin = dict(mask=torch.empty((B, h, w), dtype=torch.uint8).pin_memory(),
+                       nxt=torch.empty((B, P, 2), dtype=torch.float32).pin_memory(),
+                       st=torch.empty((B, P), dtype=torch.uint8).pin_memory(),
+                       keep=torch.empty((B, P), dtype=torch.uint8).pin_memory(),
+                       H=torch.empty((B, 9), dtype=torch.float64).pin_memory(),
+                       nv=torch.empty((B,), dtype=torch.int32).pin_memory(),
+                       inl=torch.empty((B,), dtype=torch.int32).pin_memory())
+            pins.append(pin)
+            houts.append(capi.MdOutputs(pin["nxt"].data_ptr(), pin["st"].data_ptr(), pin["keep"].data_ptr(), pin["H"].data_ptr(),
+                                        pin["nv"].data_ptr(), pin["inl"].data_ptr(), pin["mask"].data_ptr(), w, w * h))
+        low = [1 << 30]
+
+        def run(nsteps):
+            last = None
+            for i in range(nsteps):
+                t = pipe.submit(clips[pipe.batches % 2].data_ptr(), 1, w, frame_bytes, B + 1, houts[pipe.batches % lanes])
+                if last is not None:
+                    pipe.wait(last)
+                    low[0] = min(low[0], int(pins[pipe.lane_of(last)]["inl"].min()))      # the host reads the finished batch
+                last = t
+            pipe.wait(last)
+            low[0] = min(low[0], int(pins[pipe.lane_of(last)]["inl"].min()))
+
+        run(2 * lanes * 2 + 2 * lanes)                            # every lane sees both clips eager, captured and replayed
+        torch.cuda.synchronize()
+        barrier()
+        nst = a.steps + (a.steps % 2)
+        t0 = time.perf_counter()
+        run(nst)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert low[0] > 0
+        res = {"value": world * B * nst / float(t.item()), "unit": UNIT, "h2d_bytes_per_step": (B + 1) * frame_bytes,
+               "d2h_bytes_per_step": B * (w * h + P * 8 + P + P + 72 + 4 + 4), "steps": nst,
+               "api": "streams.BatchPipeline, %d contexts fed alternately with MD_MEM_HOST_ASYNC batches of one sequence" % lanes,
+               "graph_replays": pipe.stats()["graph_replays"]}
+        pipe.close()
+        return res
+
     e2e = None
     e2e_packed = None
+    e2e_one = None
     if not a.no_e2e:
         e2e = measure_e2e(False)
+        e2e["api"] = "md_process_batch(MD_MEM_HOST), one context, chained"
+        if not vf:
+            e2e_one = e2e
+            e2e_pipe = measure_e2e_pipeline(2)
+            if e2e_pipe["value"] > e2e_one["value"]:
+                e2e = e2e_pipe
         if not a.lean and not vf:
             # the same with md_config.mask_packed (1 bit per mask pixel on the way back: the u8 mask is 91 % of the D2H bytes)
             e2e_packed = measure_e2e(True)
@@ -731,7 +792,7 @@ def main():
             "mpx_per_s": value * N / 1e6,
             "roofline": roofline, "lk_work": lk_taps, "stages": stages, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "stream_stats": gathered, "two_streams_per_gpu": multi, "host_pinning": pinned, "host_link": host_link,
-            "e2e_packed_mask": e2e_packed, "graph_replays": st["graph_replays"],
+            "e2e_packed_mask": e2e_packed, "e2e_one_context": e2e_one, "graph_replays": st["graph_replays"],
             "ms_per_step_by_rank": [m / a.steps for m in ms_ranks], "priming_steps": priming,
         }
         assert line["config"]["grid_points"] == P

@@ -37,7 +37,13 @@ typedef enum md_status {
     MD_ERR_STATE = -5        /* call order (e.g. chained batch without a cached frame) */
 } md_status;
 
-typedef enum md_mem { MD_MEM_HOST = 0, MD_MEM_DEVICE = 1 } md_mem;
+/* MD_MEM_HOST_ASYNC (md_process_batch only): host pointers like MD_MEM_HOST, but the call returns as soon as the batch -- copies
+ * in, kernels, copies out -- is queued on the context's streams; md_sync() waits for it.  The frames and the outputs must stay valid
+ * (and should be pinned: a pageable copy blocks the call) until then.  With two contexts fed alternately this keeps a batch queued
+ * on the GPU while the host consumes the previous one: the head (first upload, first pyramids) and the tail (last egomotion fit,
+ * last mask, last download) of a batch run beside the other context's flow kernels instead of on an idle GPU
+ * (motion_detection_b200/streams.py: BatchPipeline). */
+typedef enum md_mem { MD_MEM_HOST = 0, MD_MEM_DEVICE = 1, MD_MEM_HOST_ASYNC = 2 } md_mem;
 
 /* Egomotion model fitted to the kept flow vectors.
  *  FIRST4: literal cv::getPerspectiveTransform(&src[0], &dst[0]) on the first four kept vectors
@@ -275,6 +281,10 @@ int md_varflow(md_ctx *ctx, const uint8_t *A, const uint8_t *B, int32_t pitch, f
 /* ---- per-stream statistics (what NCCL gathers at report time) --------------------------------------------------- */
 int md_stats_get(md_ctx *ctx, md_stats *out);
 int md_stats_reset(md_ctx *ctx);
+/* The context's count of pairs processed so far, which numbers the RANSAC seeds (pair i draws after srand(seed + i),
+ * outlier_detector.cpp:223-234 pattern).  Setting it (stream ordered) lets several contexts share one camera sequence -- batch k on
+ * context k % n -- and draw exactly the hypotheses a single context would. */
+int md_set_pair_index(md_ctx *ctx, uint64_t index);
 
 /* ---- measurement hook: CUDA events around the four stages of md_process_batch ---------------------------------- */
 /* enable != 0: the next md_process_batch calls record events on the context's stream around

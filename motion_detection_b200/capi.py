@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmotion_b200.so")
 
 MD_OK = 0
-MD_MEM_HOST, MD_MEM_DEVICE = 0, 1
+MD_MEM_HOST, MD_MEM_DEVICE, MD_MEM_HOST_ASYNC = 0, 1, 2
 MD_EGO_FIRST4, MD_EGO_RANSAC_HOMOGRAPHY, MD_EGO_RANSAC_AFFINE = 0, 1, 2
 MD_FLOW_LK, MD_FLOW_VARFLOW = 0, 1
 STATUS_NAMES = {0: "MD_OK", -1: "MD_ERR_INVALID", -2: "MD_ERR_CUDA", -3: "MD_ERR_NOMEM", -4: "MD_ERR_UNSUPPORTED",
@@ -25,7 +25,7 @@ SYMBOLS = [
     "md_pyramid_read", "md_pyramid_read_deriv", "md_lk_flow", "md_fit_egomotion", "md_motion_mask",
     "md_process_batch", "md_process_pair", "md_track_trajectories", "md_fit_subspace", "md_varflow", "md_stats_get",
     "md_stats_reset", "md_profile", "md_profile_read", "md_live_params_default", "md_window_reset", "md_window_push",
-    "md_window_detect", "md_cluster_points", "md_find_outliers", "md_cluster_vectors", "md_draw_flow",
+    "md_window_detect", "md_cluster_points", "md_find_outliers", "md_cluster_vectors", "md_draw_flow", "md_set_pair_index",
 ]
 
 
@@ -254,6 +254,10 @@ class Context:
         """Thin call for device (or pinned host) pointers. `outputs` is an MdOutputs."""
         fr = MdFrames(C.c_void_p(frames_ptr), channels, pitch, frame_stride, count, 1 if chain else 0)
         self._ck(lib().md_process_batch(self._h, C.byref(fr), C.byref(outputs), mem))
+
+    def set_pair_index(self, index):
+        """Number of the next pair (numbers the RANSAC seeds): lets several contexts share one sequence (streams.BatchPipeline)."""
+        self._ck(lib().md_set_pair_index(self._h, C.c_uint64(index)))
 
     def track_trajectories(self, frames):
         frames = np.ascontiguousarray(frames, np.uint8)

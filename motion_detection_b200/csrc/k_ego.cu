@@ -643,6 +643,13 @@ cudaError_t launch_traj_step(float2 *pts_cur, const float2 *next, const uint8_t 
 
 // the context's pair counter lives on the device: bumped at the end of every batch (inside the captured graph as well)
 __global__ void k_advance_pairs(unsigned long long *ctr, int pairs) { *ctr += (unsigned long long)pairs; }
+__global__ void k_set_pairs(unsigned long long *ctr, unsigned long long v) { *ctr = v; }
+cudaError_t launch_set_pairs(unsigned long long *ctr, unsigned long long v, cudaStream_t s)
+{
+    k_set_pairs<<<1, 1, 0, s>>>(ctr, v);
+    MD_COUNT_LAUNCH(1);
+    return cudaGetLastError();
+}
 cudaError_t launch_advance_pairs(unsigned long long *ctr, int pairs, cudaStream_t s)
 {
     k_advance_pairs<<<1, 1, 0, s>>>(ctr, pairs);

@@ -1032,6 +1032,7 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
         FAIL(MD_ERR_INVALID, "md_process_batch: bad frame descriptor");
     const int pairs = fr->chain ? fr->count : fr->count - 1;
     if (pairs < 1 || pairs > ctx->cfg.max_batch) FAIL(MD_ERR_INVALID, "md_process_batch: pairs must be in [1, max_batch]");
+    if (mem != MD_MEM_HOST && mem != MD_MEM_DEVICE && mem != MD_MEM_HOST_ASYNC) FAIL(MD_ERR_INVALID, "md_process_batch: bad mem");
     if (fr->chain && !ctx->have_cached) FAIL(MD_ERR_STATE, "md_process_batch: chain=1 without a cached previous frame");
     if (out->mask && out->mask_pitch < (ctx->cfg.mask_packed ? (ctx->cfg.width + 7) / 8 : ctx->cfg.width))
         FAIL(MD_ERR_INVALID, "md_process_batch: mask_pitch too small");
@@ -1121,7 +1122,7 @@ extern "C" int md_process_batch(md_ctx *ctx, const md_frames *fr, const md_outpu
         r = batch_enqueue(ctx, fr, out, mem, prev0, serial);
         if (r != MD_OK) return r;
     }
-    if (host) CK(cudaStreamSynchronize(s));
+    if (host && mem != MD_MEM_HOST_ASYNC) CK(cudaStreamSynchronize(s));       // MD_MEM_HOST_ASYNC: the caller waits with md_sync()
     ctx->slot_base = (prev0 + pairs) % ns;
     ctx->have_cached = 1;
     ctx->win_fill = 0;               // the ring now belongs to the batch API
@@ -1493,6 +1494,15 @@ extern "C" int md_stats_reset(md_ctx *ctx)
     int dev = ctx->stats.device;
     memset(&ctx->stats, 0, sizeof ctx->stats);
     ctx->stats.device = dev;
+    return MD_OK;
+}
+
+extern "C" int md_set_pair_index(md_ctx *ctx, uint64_t index)
+{
+    if (!ctx) return MD_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_set_pairs(ctx->d_pair_ctr, (unsigned long long)index, ctx->stream));
+    ctx->pair_counter = index;
     return MD_OK;
 }
 

@@ -264,6 +264,7 @@ cudaError_t launch_draw_flow(const uint8_t *src, int channels, int spitch, uint8
                              const uint8_t *colour, void *segs, void *abox, int *drawn, cudaStream_t s);
 size_t draw_segs_bytes(int n);
 cudaError_t launch_advance_pairs(unsigned long long *ctr, int pairs, cudaStream_t s);
+cudaError_t launch_set_pairs(unsigned long long *ctr, unsigned long long v, cudaStream_t s);
 cudaError_t launch_mask(const MaskParams &p, int pairs, const MaskTmaMaps *maps, cudaStream_t s);
 bool mask_encode_maps(MaskTmaMaps *m, const uint8_t *prev, const uint8_t *cur, int w, int h, int pitch, long long stride, int nframes);
 cudaError_t launch_compact_trajectories(const float2 *traj, const int32_t *len, int P, int F, int *blockcnt, int *idx, int *total,

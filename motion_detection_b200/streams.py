@@ -47,3 +47,67 @@ def max_over_ranks(value):
     t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+class BatchPipeline:
+    """One camera sequence over `lanes` contexts of ONE GPU, fed alternately with MD_MEM_HOST_ASYNC batches (include/motion_b200.h).
+
+    A host-buffer md_process_batch call has a head (first upload, first pyramids, planes and window sums) and a tail (last egomotion
+    fit, last mask, last download, the host's wait) during which the flow kernels -- 70 % of the work -- have nothing to run.  With
+    two contexts the head and tail of batch k run beside the flow kernels of batch k +- 1.  Every batch is handed in UNCHAINED: `count`
+    frames, the first being the last frame of the previous batch (a pair needs only its two frames, optical_flow_calculator.cpp:30;
+    one extra upload and pyramid per batch), and the lane's pair counter is set to the sequence's pair index first, so the results --
+    RANSAC draws included -- are those of a single chained context (tests/test_gpu_stream.py).
+
+    submit() returns a ticket; wait(ticket) returns when that batch's outputs are in the caller's (pinned) buffers.  A lane's buffers
+    (frames and outputs of its batch in flight) must stay untouched until its ticket has been waited for; submit() itself waits for
+    the lane's previous batch."""
+
+    def __init__(self, lanes=2, device=0, **ctx_kw):
+        from . import capi
+        self._capi = capi
+        self.ctxs = [capi.Context(device=device, **ctx_kw) for _ in range(lanes)]
+        self.batches = 0                       # batches submitted
+        self.pairs = 0                         # pairs submitted = index of the next pair of the sequence
+        self._pending = [None] * lanes         # ticket in flight per lane
+
+    def lane_of(self, ticket):
+        return ticket % len(self.ctxs)
+
+    def submit(self, frames_ptr, channels, pitch, frame_stride, count, outputs):
+        """count frames (count - 1 pairs) at frames_ptr, `outputs` an MdOutputs of host pointers; returns the ticket."""
+        ticket = self.batches
+        lane = self.lane_of(ticket)
+        if self._pending[lane] is not None:
+            self.wait(self._pending[lane])
+        ctx = self.ctxs[lane]
+        ctx.set_pair_index(self.pairs)
+        ctx.raw_process_batch(frames_ptr, channels, pitch, frame_stride, count, False, outputs, self._capi.MD_MEM_HOST_ASYNC)
+        self._pending[lane] = ticket
+        self.batches += 1
+        self.pairs += count - 1
+        return ticket
+
+    def wait(self, ticket):
+        lane = self.lane_of(ticket)
+        if self._pending[lane] == ticket:
+            self.ctxs[lane].sync()
+            self._pending[lane] = None
+
+    def drain(self):
+        for t in sorted(p for p in self._pending if p is not None):
+            self.wait(t)
+
+    def stats(self):
+        """Counters summed over the lanes."""
+        out = {}
+        for c in self.ctxs:
+            st = c.stats()
+            for k in ("pairs", "mask_pixels", "tracked", "inliers", "kernel_launches", "lk_iterations", "lk_levels", "graph_replays"):
+                out[k] = out.get(k, 0) + int(st[k])
+        return out
+
+    def close(self):
+        self.drain()
+        for c in self.ctxs:
+            c.close()

@@ -71,3 +71,46 @@ def test_two_contexts_interleaved_on_one_gpu(capi):
     for got, ref in ((x1, a1), (x2, a2), (y1, b1), (y2, b2)):
         for k in ("next", "status", "keep", "H", "num_vectors", "inliers", "mask"):
             assert np.array_equal(got[k], ref[k]), k
+
+
+@pytest.mark.parametrize("lanes", [2, 3])
+def test_batch_pipeline_equals_one_chained_context(capi, lanes):
+    """streams.BatchPipeline: batches of one sequence alternate over `lanes` contexts as asynchronous host-buffer calls
+    (MD_MEM_HOST_ASYNC, unchained with a one-frame overlap, md_set_pair_index before each).  Every output of every pair -- the RANSAC
+    draws included -- must equal a single context's chained calls bit for bit."""
+    from motion_detection_b200 import streams
+    w, h, B, nb = 320, 240, 4, 7
+    frames, _ = synth.sequence(w, h, B * nb + 1, seed=31, blobs=2)
+    kw = dict(width=w, height=h, max_batch=B, pixel_step=10, min_vector_size=0.2, seed=9)
+    ctx = capi.Context(**kw)
+    ref = [ctx.process_batch(frames[:B + 1])]
+    for k in range(1, nb):
+        ref.append(ctx.process_batch(frames[1 + k * B:1 + (k + 1) * B], chain=True))
+    pipe = streams.BatchPipeline(lanes=lanes, **kw)
+    P = pipe.ctxs[0].P
+    bufs = [dict(next=np.zeros((B, P, 2), np.float32), status=np.zeros((B, P), np.uint8), keep=np.zeros((B, P), np.uint8),
+                 H=np.zeros((B, 3, 3), np.float64), num_vectors=np.zeros(B, np.int32), inliers=np.zeros(B, np.int32),
+                 mask=np.zeros((B, h, w), np.uint8)) for _ in range(lanes)]
+    outs = [capi.MdOutputs(capi._ptr(b["next"]), capi._ptr(b["status"]), capi._ptr(b["keep"]), capi._ptr(b["H"]), capi._ptr(b["num_vectors"]),
+                           capi._ptr(b["inliers"]), capi._ptr(b["mask"]), w, w * h) for b in bufs]
+    got = []
+
+    def collect(ticket):
+        pipe.wait(ticket)
+        got.append({k: v.copy() for k, v in bufs[pipe.lane_of(ticket)].items()})
+
+    for k in range(nb):
+        if k >= lanes:
+            collect(k - lanes)                                   # the lane's buffers are free again
+        fr = frames[k * B:k * B + B + 1]
+        assert fr.flags["C_CONTIGUOUS"]
+        assert pipe.submit(fr.ctypes.data, 1, w, w * h, B + 1, outs[k % lanes]) == k
+    for k in range(max(0, nb - lanes), nb):
+        collect(k)
+    assert len(got) == nb
+    for k in range(nb):
+        for key in ("next", "status", "keep", "H", "num_vectors", "inliers", "mask"):
+            assert np.array_equal(got[k][key], ref[k][key]), (k, key)
+    assert pipe.stats()["pairs"] == B * nb
+    pipe.close()
+    ctx.close()
