@@ -222,13 +222,16 @@ __global__ void __launch_bounds__(256) k_window_sums(const PhParams q, int level
 // The horizontal phase adds the column sums of a lattice row in two levels -- sums of `step` adjacent columns (int64), then R of
 // those per point -- instead of 40 columns per point.
 // FUSED: the window samples are not loaded from the phase planes but evaluated on the way down from the padded pyramid level
-// (image + Scharr planes, exactly k_phase_planes' expressions); the Ix / Iy samples are stored for k_lk_phase, the I samples
-// (a third of the plane bytes, read by nobody else) are never materialised, and k_phase_planes is not launched for the level.
-// Only plane pixels inside some grid point's window are written: k_lk_phase uses nothing else of a plane.
-#define WR_NT 128
-#define WR_COLS (2 * WR_NT)
+// (image + Scharr planes, exactly k_phase_planes' expressions; the I sample by dp2a on the packed pixel bytes, the rounding constants
+// riding in the carried top halves); the Ix / Iy samples are stored for k_lk_phase, the I samples (a third of the plane bytes, read
+// by nobody else) are never materialised, and k_phase_planes is not launched for the level.  Only plane pixels inside some grid
+// point's window are written: k_lk_phase uses nothing else of a plane.  The rows of the next lattice step are requested before the
+// boundary work (ring, horizontal phase, barriers) of the current one.
+// NT threads = 2 NT plane columns per CTA; the launcher picks NT per level (wide levels: 256, i.e. less overlap between
+// neighbouring CTAs, whose windows share 40 - step columns; narrow class planes: 128 / 96 / 64).
 #define WR_GRP 2
-#define WR_NG (WR_COLS / 5 + 3)
+#define WR_NG(NT) (2 * (NT) / 5 + 3)
+#define WR_BATCH 5
 __device__ __forceinline__ void wr_accumulate(unsigned (&acc)[2][5], int i0, int i1, int x0, int x1, int y0, int y1)
 {
     acc[0][0] += (unsigned)(x0 * x0); acc[0][1] += (unsigned)(x0 * y0); acc[0][2] += (unsigned)(y0 * y0);
@@ -236,10 +239,15 @@ __device__ __forceinline__ void wr_accumulate(unsigned (&acc)[2][5], int i0, int
     acc[1][0] += (unsigned)(x1 * x1); acc[1][1] += (unsigned)(x1 * y1); acc[1][2] += (unsigned)(y1 * y1);
     acc[1][3] += (unsigned)(i1 * x1); acc[1][4] += (unsigned)(i1 * y1);
 }
-
-template <bool FUSED>
-__global__ void __launch_bounds__(WR_NT) k_window_sums_ring(const PhParams q, int level, int cp, int nchunk_x, int seg)
+static inline size_t wr_smem_bytes(int NT, int R)
 {
+    return ((size_t)R * 5 * 2 * NT + (size_t)WR_GRP * 5 * (2 * NT + 8)) * sizeof(int) + (size_t)WR_GRP * 5 * WR_NG(NT) * sizeof(long long);
+}
+
+template <bool FUSED, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT) k_window_sums_ring(const PhParams q, int level, int cp, int nchunk_x, int seg)
+{
+    constexpr int COLS = 2 * NT, CPITCH = COLS + 8, NGP = WR_NG(NT);
     extern __shared__ __align__(16) int wr_smem[];
     const PhaseLevel PL = q.pg.lv[level];
     const int ncx = PL.ncx, cls = blockIdx.y, cx = cls % ncx, cy = cls / ncx, b = blockIdx.z;
@@ -262,16 +270,16 @@ __global__ void __launch_bounds__(WR_NT) k_window_sums_ring(const PhParams q, in
     const int ox0 = __float2int_rd(__fsub_rn((float)(q.ps * (kx0 + i0 * ncx)) * scale, q.half)) + MD_PH_MARGIN;
     const int oy0 = __float2int_rd(__fsub_rn((float)(q.ps * (ky0 + j0 * ncx)) * scale, q.half)) + MD_PH_MARGIN;
     const int c_lo = ox0 & ~1, off = ox0 - c_lo;
-    const int ncols = off + (per_row - 1) * step + 40;             // <= WR_COLS by the choice of cp
+    const int ncols = off + (per_row - 1) * step + 40;             // <= COLS by the choice of cp
     const int tid = threadIdx.x;
     const bool col_on = 2 * tid < ncols;
     const size_t plane = (size_t)PL.pitch * PL.h;
     int16_t *pbase = q.ph + (size_t)(q.pair0 + b) * q.pg.pair_elems + PL.off + (size_t)cls * 3 * plane + (size_t)oy0 * PL.pitch + c_lo + 2 * tid;
     const int wp = PL.pitch >> 1;
 
-    int *ring = wr_smem;                                             // [R][5][WR_COLS], thread private columns
-    int *col = ring + R * 5 * WR_COLS;                               // [WR_GRP][5][WR_COLS + 8] window column sums of a group of lattice rows
-    long long *grp = reinterpret_cast<long long *>(col + WR_GRP * 5 * (WR_COLS + 8));     // [WR_GRP][5][WR_NG] sums of `step` columns
+    int *ring = wr_smem;                                             // [R][5][COLS], thread private columns
+    int *col = ring + R * 5 * COLS;                                  // [WR_GRP][5][CPITCH] window column sums of a group of lattice rows
+    long long *grp = reinterpret_cast<long long *>(col + WR_GRP * 5 * CPITCH);            // [WR_GRP][5][NGP] sums of `step` columns
 
     // row sources
     const uint32_t *pI = reinterpret_cast<const uint32_t *>(pbase), *pX = pI + (plane >> 1), *pY = pX + (plane >> 1);   // !FUSED
@@ -279,12 +287,15 @@ __global__ void __launch_bounds__(WR_NT) k_window_sums_ring(const PhParams q, in
     const uint8_t *ip = nullptr;
     const short2 *dp = nullptr;
     int spitch = 0;
-    int w00 = 0, w01 = 0, w10 = 0, w11 = 0;
-    int ti[2] = {0, 0}, tx[2] = {0, 0}, ty[2] = {0, 0};            // top halves of the current plane row (FUSED)
+    int w00 = 0, w01 = 0, w10 = 0, w11 = 0, wtop = 0, wbot = 0;
+    // top halves of the current plane row (FUSED), the rounding constants of the final shifts included
+    constexpr int RND_I = 1 << (W_BITS - 5 - 1), RND_D = 1 << (W_BITS - 1);
+    int ti[2] = {0, 0}, tx[2] = {0, 0}, ty[2] = {0, 0};
     if (FUSED) {
         const LevelGeom L = q.g.lv[level];
         const float ppx = __fsub_rn((float)(cx << PL.shift) * scale, q.half), ppy = __fsub_rn((float)(cy << PL.shift) * scale, q.half);
         lk_weights(__fsub_rn(ppx, floorf(ppx)), __fsub_rn(ppy, floorf(ppy)), w00, w01, w10, w11);
+        wtop = w00 | (w01 << 16); wbot = w10 | (w11 << 16);       // 14-bit weights as the 16-bit halves dp2a multiplies with two pixel bytes
         const int slot = (q.prev_slot0 + b) % q.g.nslots;
         spitch = L.pitch;
         const size_t src0 = (size_t)(q.g.pady - MD_PH_MARGIN + oy0) * L.pitch + (q.g.padx - MD_PH_MARGIN + c_lo + 2 * tid);
@@ -294,32 +305,79 @@ __global__ void __launch_bounds__(WR_NT) k_window_sums_ring(const PhParams q, in
             const uint32_t pw = *reinterpret_cast<const uint16_t *>(ip), p2 = ip[2];
             const uint2 dw = *reinterpret_cast<const uint2 *>(dp);
             const uint32_t d2 = *reinterpret_cast<const uint32_t *>(dp + 2);
-            const int a0 = (int)(pw & 0xffu), a1 = (int)(pw >> 8), a2 = (int)p2;
+            const uint32_t pa = pw | (p2 << 16);
             const int x0 = (int)(short)(dw.x & 0xffffu), x1 = (int)(short)(dw.y & 0xffffu), x2 = (int)(short)(d2 & 0xffffu);
             const int y0 = (int)dw.x >> 16, y1 = (int)dw.y >> 16, y2 = (int)d2 >> 16;
-            ti[0] = w00 * a0 + w01 * a1; ti[1] = w00 * a1 + w01 * a2;
-            tx[0] = w00 * x0 + w01 * x1; tx[1] = w00 * x1 + w01 * x2;
-            ty[0] = w00 * y0 + w01 * y1; ty[1] = w00 * y1 + w01 * y2;
+            ti[0] = dp2a_lo(wtop, pa, RND_I); ti[1] = dp2a_lo(wtop, pa >> 8, RND_I);
+            tx[0] = w00 * x0 + (w01 * x1 + RND_D); tx[1] = w00 * x1 + (w01 * x2 + RND_D);
+            ty[0] = w00 * y0 + (w01 * y1 + RND_D); ty[1] = w00 * y1 + (w01 * y2 + RND_D);
         }
         ip += spitch; dp += spitch;                                  // plane row Y takes its bottom half from source row Y + 1
     }
 
+    // one batch of rows in registers: FUSED pw / p2 = pixels (X, X + 1) / (X + 2), dw / d2 = their Scharr pairs; else wi, wx, wy words
+    uint32_t ba[WR_BATCH], bb[WR_BATCH], bc[WR_BATCH];
+    uint2 bd[WR_BATCH];
+    auto load_batch = [&](int nr) {
+#pragma unroll
+        for (int u = 0; u < WR_BATCH; u++) {
+            if (u < nr) {
+                if (FUSED) {
+                    ba[u] = __ldg(reinterpret_cast<const uint16_t *>(ip + (size_t)u * spitch)); bb[u] = __ldg(ip + (size_t)u * spitch + 2);
+                    bd[u] = __ldg(reinterpret_cast<const uint2 *>(dp + (size_t)u * spitch));
+                    bc[u] = __ldg(reinterpret_cast<const uint32_t *>(dp + (size_t)u * spitch + 2));
+                } else {
+                    ba[u] = __ldg(pI + u * wp); bb[u] = __ldg(pX + u * wp); bc[u] = __ldg(pY + u * wp);
+                }
+            }
+        }
+        if (FUSED) { ip += (size_t)nr * spitch; dp += (size_t)nr * spitch; }
+        else { pI += nr * wp; pX += nr * wp; pY += nr * wp; }
+    };
     unsigned acc[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};
+    auto compute_batch = [&](int nr) {
+#pragma unroll
+        for (int u = 0; u < WR_BATCH; u++) {
+            if (u < nr) {
+                if (FUSED) {
+                    const uint32_t pa = ba[u] | (bb[u] << 16), pb = pa >> 8;      // bytes (a0, a1, a2) and (a1, a2)
+                    const int x0 = (int)(short)(bd[u].x & 0xffffu), x1 = (int)(short)(bd[u].y & 0xffffu), x2 = (int)(short)(bc[u] & 0xffffu);
+                    const int y0 = (int)bd[u].x >> 16, y1 = (int)bd[u].y >> 16, y2 = (int)bc[u] >> 16;
+                    const int iv0 = dp2a_lo(wbot, pa, ti[0]) >> (W_BITS - 5), iv1 = dp2a_lo(wbot, pb, ti[1]) >> (W_BITS - 5);
+                    const int xv0 = (tx[0] + w10 * x0 + w11 * x1) >> W_BITS, xv1 = (tx[1] + w10 * x1 + w11 * x2) >> W_BITS;
+                    const int yv0 = (ty[0] + w10 * y0 + w11 * y1) >> W_BITS, yv1 = (ty[1] + w10 * y1 + w11 * y2) >> W_BITS;
+                    ti[0] = dp2a_lo(wtop, pa, RND_I); ti[1] = dp2a_lo(wtop, pb, RND_I);
+                    tx[0] = w00 * x0 + (w01 * x1 + RND_D); tx[1] = w00 * x1 + (w01 * x2 + RND_D);
+                    ty[0] = w00 * y0 + (w01 * y1 + RND_D); ty[1] = w00 * y1 + (w01 * y2 + RND_D);
+                    oX[u * wp] = ((uint32_t)xv0 & 0xffffu) | ((uint32_t)xv1 << 16);
+                    oY[u * wp] = ((uint32_t)yv0 & 0xffffu) | ((uint32_t)yv1 << 16);
+                    wr_accumulate(acc, iv0, iv1, xv0, xv1, yv0, yv1);
+                } else {
+                    wr_accumulate(acc, (int)(ba[u] & 0xffffu), (int)(ba[u] >> 16), (int)(short)bb[u], (int)bb[u] >> 16, (int)(short)bc[u],
+                                  (int)bc[u] >> 16);
+                }
+            }
+        }
+        if (FUSED) { oX += nr * wp; oY += nr * wp; }
+    };
+
     const int K = nlat + R;                                          // lattice row boundaries met on the way down
+    const int nr0 = min(WR_BATCH, step);
+    if (col_on) load_batch(nr0);
     int slot_r = 0, g = 0, jg = j0;
     for (int k = 0; k < K; k++) {
         if (col_on) {
-            int *rg = ring + slot_r * 5 * WR_COLS + 2 * tid;
+            int *rg = ring + slot_r * 5 * COLS + 2 * tid;
             if (k >= R) {
-                int *cg = col + g * 5 * (WR_COLS + 8) + 2 * tid;
+                int *cg = col + g * 5 * CPITCH + 2 * tid;
 #pragma unroll
                 for (int t = 0; t < 5; t++) {
-                    const int2 old = *reinterpret_cast<const int2 *>(rg + t * WR_COLS);
-                    *reinterpret_cast<int2 *>(cg + t * (WR_COLS + 8)) = make_int2((int)(acc[0][t] - (unsigned)old.x), (int)(acc[1][t] - (unsigned)old.y));
+                    const int2 old = *reinterpret_cast<const int2 *>(rg + t * COLS);
+                    *reinterpret_cast<int2 *>(cg + t * CPITCH) = make_int2((int)(acc[0][t] - (unsigned)old.x), (int)(acc[1][t] - (unsigned)old.y));
                 }
             }
 #pragma unroll
-            for (int t = 0; t < 5; t++) *reinterpret_cast<int2 *>(rg + t * WR_COLS) = make_int2((int)acc[0][t], (int)acc[1][t]);
+            for (int t = 0; t < 5; t++) *reinterpret_cast<int2 *>(rg + t * COLS) = make_int2((int)acc[0][t], (int)acc[1][t]);
         }
         if (++slot_r == R) slot_r = 0;
         if (k >= R && (++g == WR_GRP || k == K - 1)) {
@@ -327,22 +385,35 @@ __global__ void __launch_bounds__(WR_NT) k_window_sums_ring(const PhParams q, in
             // scalars k_lk_phase needs (f32 matrix entries, minimum-eigenvalue / determinant test, 1 / det), once per point
             const int NG = per_row - 1 + R;
             __syncthreads();
-            for (int e = tid; e < g * 5 * NG; e += WR_NT) {
+            for (int e = tid; e < g * 5 * NG; e += NT) {
                 const int row = e / NG, gi = e - row * NG;           // row = (lattice row of the group) * 5 + quantity
-                const int *v = col + row * (WR_COLS + 8) + off + gi * step;
+                const int *v = col + row * CPITCH + off + gi * step;
                 long long s = 0;
-                for (int c = 0; c < step; c++) s += v[c];
-                grp[row * WR_NG + gi] = s;
+                for (int c0 = 0; c0 < step; c0 += 8) {
+                    int t8[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) t8[u] = c0 + u < step ? v[c0 + u] : 0;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) s += t8[u];
+                }
+                grp[row * NGP + gi] = s;
             }
             __syncthreads();
-            for (int e = tid; e < g * per_row; e += WR_NT) {
+            for (int e = tid; e < g * per_row; e += NT) {
                 const int gg = e / per_row, pi = e - gg * per_row;
+                long long part[5][8];
+#pragma unroll
+                for (int t = 0; t < 5; t++) {
+                    const long long *v = grp + (gg * 5 + t) * NGP + pi;
+#pragma unroll
+                    for (int c = 0; c < 8; c++) part[t][c] = c < R ? v[c] : 0;
+                }
                 long long sum[5];
 #pragma unroll
                 for (int t = 0; t < 5; t++) {
-                    const long long *v = grp + (gg * 5 + t) * WR_NG + pi;
                     long long s = 0;
-                    for (int c = 0; c < R; c++) s += v[c];
+#pragma unroll
+                    for (int c = 0; c < 8; c++) s += part[t][c];
                     sum[t] = s;
                 }
                 const float FLT_SCALE = 1.f / (1 << 20);
@@ -357,56 +428,12 @@ __global__ void __launch_bounds__(WR_NT) k_window_sums_ring(const PhParams q, in
             jg += g; g = 0;
         }
         if (k == K - 1 || !col_on) continue;
-        // the `step` rows down to the next boundary, five at a time: all loads of a batch are issued before its arithmetic
-        for (int r0 = 0; r0 < step; r0 += 5) {
-            const int nr = min(5, step - r0);
-            if (FUSED) {
-                uint32_t pw[5], p2[5], d2[5];
-                uint2 dw[5];
-#pragma unroll
-                for (int u = 0; u < 5; u++) {
-                    if (u < nr) {
-                        pw[u] = __ldg(reinterpret_cast<const uint16_t *>(ip + (size_t)u * spitch)); p2[u] = __ldg(ip + (size_t)u * spitch + 2);
-                        dw[u] = __ldg(reinterpret_cast<const uint2 *>(dp + (size_t)u * spitch));
-                        d2[u] = __ldg(reinterpret_cast<const uint32_t *>(dp + (size_t)u * spitch + 2));
-                    }
-                }
-                ip += (size_t)nr * spitch; dp += (size_t)nr * spitch;
-#pragma unroll
-                for (int u = 0; u < 5; u++) {
-                    if (u < nr) {
-                        const int a0 = (int)(pw[u] & 0xffu), a1 = (int)(pw[u] >> 8), a2 = (int)p2[u];
-                        const int x0 = (int)(short)(dw[u].x & 0xffffu), x1 = (int)(short)(dw[u].y & 0xffffu), x2 = (int)(short)(d2[u] & 0xffffu);
-                        const int y0 = (int)dw[u].x >> 16, y1 = (int)dw[u].y >> 16, y2 = (int)d2[u] >> 16;
-                        const int iv0 = (ti[0] + w10 * a0 + w11 * a1 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                        const int iv1 = (ti[1] + w10 * a1 + w11 * a2 + (1 << (W_BITS - 5 - 1))) >> (W_BITS - 5);
-                        const int xv0 = (tx[0] + w10 * x0 + w11 * x1 + (1 << (W_BITS - 1))) >> W_BITS;
-                        const int xv1 = (tx[1] + w10 * x1 + w11 * x2 + (1 << (W_BITS - 1))) >> W_BITS;
-                        const int yv0 = (ty[0] + w10 * y0 + w11 * y1 + (1 << (W_BITS - 1))) >> W_BITS;
-                        const int yv1 = (ty[1] + w10 * y1 + w11 * y2 + (1 << (W_BITS - 1))) >> W_BITS;
-                        ti[0] = w00 * a0 + w01 * a1; ti[1] = w00 * a1 + w01 * a2;
-                        tx[0] = w00 * x0 + w01 * x1; tx[1] = w00 * x1 + w01 * x2;
-                        ty[0] = w00 * y0 + w01 * y1; ty[1] = w00 * y1 + w01 * y2;
-                        oX[u * wp] = ((uint32_t)xv0 & 0xffffu) | ((uint32_t)xv1 << 16);
-                        oY[u * wp] = ((uint32_t)yv0 & 0xffffu) | ((uint32_t)yv1 << 16);
-                        wr_accumulate(acc, iv0, iv1, xv0, xv1, yv0, yv1);
-                    }
-                }
-                oX += nr * wp; oY += nr * wp;
-            } else {
-                uint32_t wi[5], wx[5], wy[5];
-#pragma unroll
-                for (int u = 0; u < 5; u++) {
-                    if (u < nr) { wi[u] = __ldg(pI + u * wp); wx[u] = __ldg(pX + u * wp); wy[u] = __ldg(pY + u * wp); }
-                }
-                pI += nr * wp; pX += nr * wp; pY += nr * wp;
-#pragma unroll
-                for (int u = 0; u < 5; u++) {
-                    if (u < nr)
-                        wr_accumulate(acc, (int)(wi[u] & 0xffffu), (int)(wi[u] >> 16), (int)(short)wx[u], (int)wx[u] >> 16, (int)(short)wy[u],
-                                      (int)wy[u] >> 16);
-                }
-            }
+        // the `step` rows down to the next boundary, WR_BATCH at a time; the batch in registers was requested before the boundary work
+        for (int r0 = 0; r0 < step; r0 += WR_BATCH) {
+            compute_batch(min(WR_BATCH, step - r0));
+            const int left = step - r0 - WR_BATCH;
+            if (left > 0) load_batch(min(WR_BATCH, left));
+            else if (k + 1 < K - 1) load_batch(nr0);
         }
     }
 }
@@ -674,6 +701,7 @@ cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1
         // 0 = k_phase_planes + sliding sums; lattice steps the ring kernel does not take (40 % step != 0 or step < 5) always get 0
         static const int ws_mode = [] { const char *e = getenv("MD_WS_MODE"); return e ? atoi(e) : 2; }();
         static const int ws_rows = [] { const char *e = getenv("MD_WS_ROWS"); return e && atoi(e) > 0 ? atoi(e) : 160; }();
+        static const int ws_nt = [] { const char *e = getenv("MD_WS_NT"); const int v = e ? atoi(e) : 0; return v == 256 || v == 128 || v == 96 || v == 64 ? v : 0; }();
         const bool ring = ws_mode > 0 && step >= 5 && step <= 40 && 40 % step == 0;
         if (!ring || ws_mode == 1) {
             const int threads = (PL.pitch / 8) * ((PL.h + 3) / 4);
@@ -683,18 +711,37 @@ cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1
         }
         if (ring) {
             const int R = 40 / step, seg = max(2, ws_rows / step);
-            const int cpr = (WR_COLS - 41) / step + 1;                              // lattice columns per CTA
-            const int ncx_r = (nx + cpr - 1) / cpr, nseg_r = (ny + seg - 1) / seg;
-            const size_t smem = ((size_t)R * 5 * WR_COLS + (size_t)WR_GRP * 5 * (WR_COLS + 8)) * sizeof(int) + (size_t)WR_GRP * 5 * WR_NG * sizeof(long long);
+            // threads per CTA (2 columns each): the fewest thread slots over the chunks of a lattice row, the wider CTA on a tie
+            int NT = 128, cpr = 0, ncx_r = 0;
+            {
+                const int cand[4] = {256, 128, 96, 64};
+                long best = -1;
+                for (int c = 0; c < 4; c++) {
+                    if (ws_mode == 1 && cand[c] != 128) continue;
+                    const int cpmax = (2 * cand[c] - 41) / step + 1;
+                    if (cpmax < 1) continue;
+                    const int nch = (nx + cpmax - 1) / cpmax, cpe = (nx + nch - 1) / nch;
+                    const long cost = (long)nch * cand[c];
+                    if (best < 0 || cost < best) { best = cost; NT = cand[c]; cpr = cpe; ncx_r = nch; }
+                }
+                if (ws_nt > 0 && ws_mode != 1) { NT = ws_nt; const int cpmax = (2 * NT - 41) / step + 1; ncx_r = (nx + cpmax - 1) / cpmax; cpr = (nx + ncx_r - 1) / ncx_r; }
+            }
+            const int nseg_r = (ny + seg - 1) / seg;
+            const size_t smem = wr_smem_bytes(NT, R);
             static const cudaError_t attr = [] {
-                const int most = (8 * 5 * WR_COLS + WR_GRP * 5 * (WR_COLS + 8)) * (int)sizeof(int) + WR_GRP * 5 * WR_NG * (int)sizeof(long long);
-                cudaError_t e = cudaFuncSetAttribute(k_window_sums_ring<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
-                return e != cudaSuccess ? e : cudaFuncSetAttribute(k_window_sums_ring<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+                cudaError_t e = cudaFuncSetAttribute(k_window_sums_ring<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(256, 8));
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(128, 8));
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(96, 8));
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(128, 8));
+                return e;
             }();
             if (attr != cudaSuccess) return attr;
             const dim3 grid(ncx_r * nseg_r, PL.ncx * PL.ncx, pairs);
-            if (ws_mode == 1) k_window_sums_ring<false><<<grid, WR_NT, smem, s>>>(q, l, cpr, ncx_r, seg);
-            else k_window_sums_ring<true><<<grid, WR_NT, smem, s>>>(q, l, cpr, ncx_r, seg);
+            if (ws_mode == 1) k_window_sums_ring<false, 128><<<grid, 128, smem, s>>>(q, l, cpr, ncx_r, seg);
+            else if (NT == 256) k_window_sums_ring<true, 256><<<grid, 256, smem, s>>>(q, l, cpr, ncx_r, seg);
+            else if (NT == 128) k_window_sums_ring<true, 128><<<grid, 128, smem, s>>>(q, l, cpr, ncx_r, seg);
+            else if (NT == 96) k_window_sums_ring<true, 96><<<grid, 96, smem, s>>>(q, l, cpr, ncx_r, seg);
+            else k_window_sums_ring<true, 64><<<grid, 64, smem, s>>>(q, l, cpr, ncx_r, seg);
             MD_COUNT_LAUNCH(1);
             continue;
         }
