@@ -245,7 +245,7 @@ static inline size_t wr_smem_bytes(int NT, int R)
 }
 
 template <bool FUSED, int NT>
-__global__ void __launch_bounds__(NT, 512 / NT) k_window_sums_ring(const PhParams q, int level, int cp, int nchunk_x, int seg)
+__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) k_window_sums_ring(const PhParams q, int level, int cp, int nchunk_x, int seg)
 {
     constexpr int COLS = 2 * NT, CPITCH = COLS + 8, NGP = WR_NG(NT);
     extern __shared__ __align__(16) int wr_smem[];
@@ -401,20 +401,14 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_window_sums_ring(const PhParam
             __syncthreads();
             for (int e = tid; e < g * per_row; e += NT) {
                 const int gg = e / per_row, pi = e - gg * per_row;
-                long long part[5][8];
-#pragma unroll
-                for (int t = 0; t < 5; t++) {
-                    const long long *v = grp + (gg * 5 + t) * NGP + pi;
-#pragma unroll
-                    for (int c = 0; c < 8; c++) part[t][c] = c < R ? v[c] : 0;
-                }
                 long long sum[5];
 #pragma unroll
                 for (int t = 0; t < 5; t++) {
-                    long long s = 0;
+                    const long long *v = grp + (gg * 5 + t) * NGP + pi;
+                    long long part[8];
 #pragma unroll
-                    for (int c = 0; c < 8; c++) s += part[t][c];
-                    sum[t] = s;
+                    for (int c = 0; c < 8; c++) part[c] = c < R ? v[c] : 0;
+                    sum[t] = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
                 }
                 const float FLT_SCALE = 1.f / (1 << 20);
                 const float A11 = (float)sum[0] * FLT_SCALE, A12 = (float)sum[1] * FLT_SCALE, A22 = (float)sum[2] * FLT_SCALE;
