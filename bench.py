@@ -506,7 +506,7 @@ def main():
     stage_bytes = [1.3333 * N * (B + 1), (10.0 * N if vf else 2.6667 * N + 9 * P) * B, 9.0 * P * B, 3.0 * N * B]
     names = ["K1 pyramid+scharr (k_level0/k_pyrdown/k_scharr)",
              "K2 dense variational flow VarFlow::CalcFlow (k_vf_*: presmooth, derivatives, Gauss-Seidel wavefront V-cycles)" if vf else
-             "K2 pyramidal LK on the tracked grid (k_phase_planes + k_window_sums + k_lk_phase)",
+             "K2 pyramidal LK on the tracked grid (k_window_sums_ring = phase planes + window sums, k_lk_phase)",
              "K3 egomotion (k_keep_count/k_scan/k_compact/k_hypotheses/k_score/k_accum/k_solve)",
              "K4 fused warp+diff+threshold+erode+dilate (k_mask, TMA-staged tiles)"]
     peak, peak_src = peaks()
