@@ -62,3 +62,52 @@ def test_stats_gather_gloo_world2(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
                        env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_batch_pipeline_bookkeeping(monkeypatch):
+    """streams.BatchPipeline without a GPU: batches alternate over the lanes, every lane's pair counter is set to the sequence's pair
+    index before its batch, a lane is waited for before it is fed again, every call is an unchained MD_MEM_HOST_ASYNC batch."""
+    from motion_detection_b200 import capi
+    log = []
+
+    class FakeCtx:
+        n = 0
+
+        def __init__(self, device=0, **kw):
+            self.id = FakeCtx.n
+            FakeCtx.n += 1
+            self.kw = kw
+
+        def set_pair_index(self, i):
+            log.append(("idx", self.id, i))
+
+        def raw_process_batch(self, ptr, ch, pitch, stride, count, chain, outputs, mem):
+            assert not chain and mem == capi.MD_MEM_HOST_ASYNC
+            log.append(("run", self.id, ptr, count))
+
+        def sync(self):
+            log.append(("sync", self.id))
+
+        def stats(self):
+            return dict(pairs=3, mask_pixels=1, tracked=2, inliers=1, kernel_launches=4, lk_iterations=5, lk_levels=6, graph_replays=7,
+                        last_H=None, device=0)
+
+        def close(self):
+            log.append(("close", self.id))
+
+    monkeypatch.setattr(capi, "Context", FakeCtx)
+    pipe = streams.BatchPipeline(lanes=2, width=64, height=48)
+    assert [c.kw for c in pipe.ctxs] == [dict(width=64, height=48)] * 2
+    t = [pipe.submit(1000 + k, 1, 64, 64 * 48, 5, None) for k in range(3)]      # 4 pairs per batch
+    assert t == [0, 1, 2] and pipe.pairs == 12 and [pipe.lane_of(x) for x in t] == [0, 1, 0]
+    assert log == [("idx", 0, 0), ("run", 0, 1000, 5), ("idx", 1, 4), ("run", 1, 1001, 5),
+                   ("sync", 0), ("idx", 0, 8), ("run", 0, 1002, 5)]              # lane 0 is waited for before batch 2
+    pipe.wait(0)                                                                # already retired: nothing happens
+    assert log[-1][0] == "run"
+    pipe.wait(1)
+    assert log[-1] == ("sync", 1)
+    pipe.drain()
+    assert log[-1] == ("sync", 0)
+    assert pipe.stats()["pairs"] == 6 and pipe.stats()["graph_replays"] == 14
+    pipe.close()
+    assert log[-2:] == [("close", 0), ("close", 1)]
