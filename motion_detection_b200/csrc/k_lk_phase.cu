@@ -385,22 +385,32 @@ __global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) k_window_sums_ri
             // scalars k_lk_phase needs (f32 matrix entries, minimum-eigenvalue / determinant test, 1 / det), once per point
             const int NG = per_row - 1 + R;
             __syncthreads();
-            for (int e = tid; e < g * 5 * NG; e += NT) {
-                const int row = e / NG, gi = e - row * NG;           // row = (lattice row of the group) * 5 + quantity
-                const int *v = col + row * CPITCH + off + gi * step;
-                long long s = 0;
-                for (int c0 = 0; c0 < step; c0 += 8) {
-                    int t8[8];
+            // a warp takes a (lattice row, quantity) line of column sums, a lane a group of `step` columns
+            for (int row = tid >> 5; row < g * 5; row += NT / 32) {
+                for (int gi = tid & 31; gi < NG; gi += 32) {
+                    const int *v = col + row * CPITCH + off + gi * step;
+                    long long s;
+                    if (step == 5) s = ((long long)v[0] + v[1]) + ((long long)v[2] + v[3]) + v[4];
+                    else if (step == 10)
+                        s = (((long long)v[0] + v[1]) + ((long long)v[2] + v[3])) + (((long long)v[4] + v[5]) + ((long long)v[6] + v[7])) +
+                            ((long long)v[8] + v[9]);
+                    else {
+                        s = 0;
+                        for (int c0 = 0; c0 < step; c0 += 8) {
+                            int t8[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) t8[u] = c0 + u < step ? v[c0 + u] : 0;
+                            for (int u = 0; u < 8; u++) t8[u] = c0 + u < step ? v[c0 + u] : 0;
 #pragma unroll
-                    for (int u = 0; u < 8; u++) s += t8[u];
+                            for (int u = 0; u < 8; u++) s += t8[u];
+                        }
+                    }
+                    grp[row * NGP + gi] = s;
                 }
-                grp[row * NGP + gi] = s;
             }
             __syncthreads();
             for (int e = tid; e < g * per_row; e += NT) {
-                const int gg = e / per_row, pi = e - gg * per_row;
+                static_assert(WR_GRP == 2, "a group holds at most two lattice rows");
+                const int gg = e >= per_row ? 1 : 0, pi = e - gg * per_row;
                 long long sum[5];
 #pragma unroll
                 for (int t = 0; t < 5; t++) {
