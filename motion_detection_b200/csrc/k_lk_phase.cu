@@ -244,8 +244,8 @@ static inline size_t wr_smem_bytes(int NT, int R)
     return ((size_t)R * 5 * 2 * NT + (size_t)WR_GRP * 5 * (2 * NT + 8)) * sizeof(int) + (size_t)WR_GRP * 5 * WR_NG(NT) * sizeof(long long);
 }
 
-template <bool FUSED, int NT>
-__global__ void __launch_bounds__(NT, NT == 256 ? 3 : 512 / NT) k_window_sums_ring(const PhParams q, int level, int cp, int nchunk_x, int seg)
+template <bool FUSED, int NT, int MINB = 512 / NT>
+__global__ void __launch_bounds__(NT, MINB) k_window_sums_ring(const PhParams q, int level, int cp, int nchunk_x, int seg)
 {
     constexpr int COLS = 2 * NT, CPITCH = COLS + 8, NGP = WR_NG(NT);
     extern __shared__ __align__(16) int wr_smem[];
@@ -705,6 +705,9 @@ cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1
         // 0 = k_phase_planes + sliding sums; lattice steps the ring kernel does not take (40 % step != 0 or step < 5) always get 0
         static const int ws_mode = [] { const char *e = getenv("MD_WS_MODE"); return e ? atoi(e) : 2; }();
         static const int ws_rows = [] { const char *e = getenv("MD_WS_ROWS"); return e && atoi(e) > 0 ? atoi(e) : 160; }();
+        // CTAs per SM the 256-thread build is compiled for: 2 (default, 128 registers) or 3 (80 registers: 134 instead of ~100 instructions per
+        // row visit, measured 5 839 against 5 867 frames/s)
+        static const int ws_minb = [] { const char *e = getenv("MD_WS_MINB"); return e ? atoi(e) : 2; }();
         static const int ws_nt = [] { const char *e = getenv("MD_WS_NT"); const int v = e ? atoi(e) : 0; return v == 256 || v == 128 || v == 96 || v == 64 ? v : 0; }();
         const bool ring = ws_mode > 0 && step >= 5 && step <= 40 && 40 % step == 0;
         if (!ring || ws_mode == 1) {
@@ -734,6 +737,7 @@ cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1
             const size_t smem = wr_smem_bytes(NT, R);
             static const cudaError_t attr = [] {
                 cudaError_t e = cudaFuncSetAttribute(k_window_sums_ring<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(256, 8));
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<true, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(256, 8));
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(128, 8));
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(96, 8));
                 if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(128, 8));
@@ -742,6 +746,7 @@ cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1
             if (attr != cudaSuccess) return attr;
             const dim3 grid(ncx_r * nseg_r, PL.ncx * PL.ncx, pairs);
             if (ws_mode == 1) k_window_sums_ring<false, 128><<<grid, 128, smem, s>>>(q, l, cpr, ncx_r, seg);
+            else if (NT == 256 && ws_minb == 3) k_window_sums_ring<true, 256, 3><<<grid, 256, smem, s>>>(q, l, cpr, ncx_r, seg);
             else if (NT == 256) k_window_sums_ring<true, 256><<<grid, 256, smem, s>>>(q, l, cpr, ncx_r, seg);
             else if (NT == 128) k_window_sums_ring<true, 128><<<grid, 128, smem, s>>>(q, l, cpr, ncx_r, seg);
             else if (NT == 96) k_window_sums_ring<true, 96><<<grid, 96, smem, s>>>(q, l, cpr, ncx_r, seg);
