@@ -735,22 +735,23 @@ cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1
             }
             const int nseg_r = (ny + seg - 1) / seg;
             const size_t smem = wr_smem_bytes(NT, R);
-            static const cudaError_t attr = [] {
-                cudaError_t e = cudaFuncSetAttribute(k_window_sums_ring<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(256, 8));
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<true, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(256, 8));
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<true, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(128, 8));
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<true, 96>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(96, 8));
-                if (e == cudaSuccess) e = cudaFuncSetAttribute(k_window_sums_ring<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wr_smem_bytes(128, 8));
-                return e;
-            }();
-            if (attr != cudaSuccess) return attr;
             const dim3 grid(ncx_r * nseg_r, PL.ncx * PL.ncx, pairs);
-            if (ws_mode == 1) k_window_sums_ring<false, 128><<<grid, 128, smem, s>>>(q, l, cpr, ncx_r, seg);
-            else if (NT == 256 && ws_minb == 3) k_window_sums_ring<true, 256, 3><<<grid, 256, smem, s>>>(q, l, cpr, ncx_r, seg);
-            else if (NT == 256) k_window_sums_ring<true, 256><<<grid, 256, smem, s>>>(q, l, cpr, ncx_r, seg);
-            else if (NT == 128) k_window_sums_ring<true, 128><<<grid, 128, smem, s>>>(q, l, cpr, ncx_r, seg);
-            else if (NT == 96) k_window_sums_ring<true, 96><<<grid, 96, smem, s>>>(q, l, cpr, ncx_r, seg);
-            else k_window_sums_ring<true, 64><<<grid, 64, smem, s>>>(q, l, cpr, ncx_r, seg);
+            // (the attribute is per device: set at every launch, like launch_lk_phase does, so that a process with contexts on several
+            // GPUs never launches with the 48 KB default)
+            auto go = [&](auto kern, int nt) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e != cudaSuccess) return e;
+                kern<<<grid, nt, smem, s>>>(q, l, cpr, ncx_r, seg);
+                return cudaSuccess;
+            };
+            cudaError_t e;
+            if (ws_mode == 1) e = go(k_window_sums_ring<false, 128>, 128);
+            else if (NT == 256 && ws_minb == 3) e = go(k_window_sums_ring<true, 256, 3>, 256);
+            else if (NT == 256) e = go(k_window_sums_ring<true, 256>, 256);
+            else if (NT == 128) e = go(k_window_sums_ring<true, 128>, 128);
+            else if (NT == 96) e = go(k_window_sums_ring<true, 96>, 96);
+            else e = go(k_window_sums_ring<true, 64>, 64);
+            if (e != cudaSuccess) return e;
             MD_COUNT_LAUNCH(1);
             continue;
         }
