@@ -36,7 +36,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="frame pairs per step (16: 4 202 pairs/s, 32: 4 440, 64: 4 551)")
+    ap.add_argument("--batch", type=int, default=64, help="frame pairs per step (round 2, value / e2e frames/s: 32: 5 866 / 5 770, 48: 5 928 / 5 868, "
+                                                          "64: 5 964 / 5 908; the head and tail of a batch are paid once per step)")
     ap.add_argument("--pixel-step", type=int, default=10, help="grid step (launch-file default 10; 1 = dense)")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
