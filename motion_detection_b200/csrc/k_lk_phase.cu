@@ -14,6 +14,9 @@
 //  * The five integer window sums A11, A12, A22, sum I*Ix, sum I*Iy of a point are box sums over its class planes; points
 //    of one grid row and class share their 40 window rows, so k_window_sums forms the column sums once per (row, class)
 //    and every point adds up 40 of them: 28 M pixel visits per 1080p pair instead of 166 M per-point taps, exact int64.
+//    Where the lattice step of a level divides the window (every level of pixel_step 5 / 10 / 20 / 40) k_window_sums_ring does both
+//    jobs in one pass down the level: the samples are evaluated on the way, Ix / Iy stored, the I plane never materialised, no row
+//    visited twice (running prefix + ring of lattice-boundary snapshots in shared memory).
 //  * The iteration loop (J tile staged by TMA, dp2a bilinear samples, dp2a mismatch accumulation on packed tap pairs,
 //    REDUX reductions) is the one of k_lk_tma.cu.
 #include <stdlib.h>
