@@ -707,7 +707,11 @@ cudaError_t launch_lk_planes_levels(const LkParams &p, int pairs, int l0, int l1
         // MD_WS_MODE: 2 (default) = planes and sums in one pass (k_window_sums_ring<true>), 1 = k_phase_planes + single-pass sums,
         // 0 = k_phase_planes + sliding sums; lattice steps the ring kernel does not take (40 % step != 0 or step < 5) always get 0
         static const int ws_mode = [] { const char *e = getenv("MD_WS_MODE"); return e ? atoi(e) : 2; }();
-        static const int ws_rows = [] { const char *e = getenv("MD_WS_ROWS"); return e && atoi(e) > 0 ? atoi(e) : 160; }();
+        // plane rows per CTA segment: neighbouring segments recompute the 40 - step rows their windows share, shorter segments fill the
+        // GPU better.  Measured (frames/s): 16 pairs per launch 80 / 120 / 160 / 240 / 320 rows: 5 724 / 5 754 / 5 780 / 5 740 / 5 718;
+        // 32 pairs per launch 160 / 240 / 320: 5 966 / 5 969 / 5 993
+        static const int ws_rows_env = [] { const char *e = getenv("MD_WS_ROWS"); return e && atoi(e) > 0 ? atoi(e) : 0; }();
+        const int ws_rows = ws_rows_env > 0 ? ws_rows_env : (pairs >= 24 ? 320 : 160);
         // CTAs per SM the 256-thread build is compiled for: 2 (default, 128 registers) or 3 (80 registers: 134 instead of ~100 instructions per
         // row visit, measured 5 839 against 5 867 frames/s)
         static const int ws_minb = [] { const char *e = getenv("MD_WS_MINB"); return e ? atoi(e) : 2; }();

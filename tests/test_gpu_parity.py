@@ -458,10 +458,13 @@ def test_window_sum_kernels_are_equivalent():
         "    ctx.close()\n"
         "print(h.hexdigest())\n" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     digests = {}
-    for m in ("", "1", "0"):
+    for m in ("", "1", "0", "rows320", "rows60"):
         env = dict(os.environ)
         env.pop("MD_WS_MODE", None)
-        if m:
+        env.pop("MD_WS_ROWS", None)
+        if m.startswith("rows"):
+            env["MD_WS_ROWS"] = m[4:]            # plane rows per CTA segment of the single-pass kernel (launch geometry only)
+        elif m:
             env["MD_WS_MODE"] = m
         out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
