@@ -286,6 +286,11 @@ int md_stats_reset(md_ctx *ctx);
  * context k % n -- and draw exactly the hypotheses a single context would. */
 int md_set_pair_index(md_ctx *ctx, uint64_t index);
 
+/* ---- host utility: a mask_packed = 1 mask (1 bit per pixel, LSB first) expanded to the reference's cv::Mat form, 0 / 255 bytes ----- */
+/* Pure host code (no context, no GPU): `rows` rows of `width` pixels; bits_pitch >= (width + 7) / 8, mask_pitch >= width.  For users who
+ * take the packed mask over a saturated host link and still need `comp` as optical_flow_calculator.cpp:127 leaves it. */
+int md_unpack_mask_host(const uint8_t *bits, int32_t bits_pitch, int32_t width, int32_t rows, uint8_t *mask, int32_t mask_pitch);
+
 /* ---- measurement hook: CUDA events around the four stages of md_process_batch ---------------------------------- */
 /* enable != 0: the next md_process_batch calls record events on the context's stream around
  * K1 (pyramid), K2 (LK), K3 (egomotion), K4 (mask).  md_profile_read waits for the last batch and returns the

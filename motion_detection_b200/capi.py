@@ -26,6 +26,7 @@ SYMBOLS = [
     "md_process_batch", "md_process_pair", "md_track_trajectories", "md_fit_subspace", "md_varflow", "md_stats_get",
     "md_stats_reset", "md_profile", "md_profile_read", "md_live_params_default", "md_window_reset", "md_window_push",
     "md_window_detect", "md_cluster_points", "md_find_outliers", "md_cluster_vectors", "md_draw_flow", "md_set_pair_index",
+    "md_unpack_mask_host",
 ]
 
 
@@ -116,6 +117,17 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return C.c_void_p(a.ctypes.data)
     return C.c_void_p(a.data_ptr())     # torch tensor
+
+
+def unpack_mask(bits, width):
+    """Host utility md_unpack_mask_host: [..., rows, pitch] packed mask bits (LSB first) -> [..., rows, width] bytes 0 / 255."""
+    bits = np.ascontiguousarray(bits, np.uint8)
+    rows = int(np.prod(bits.shape[:-1]))
+    out = np.empty(bits.shape[:-1] + (width,), np.uint8)
+    rc = lib().md_unpack_mask_host(_ptr(bits), bits.shape[-1], width, rows, _ptr(out), width)
+    if rc != MD_OK:
+        raise MotionB200Error(rc, "md_unpack_mask_host")
+    return out
 
 
 class Context:

@@ -1506,6 +1506,31 @@ extern "C" int md_set_pair_index(md_ctx *ctx, uint64_t index)
     return MD_OK;
 }
 
+// Host utility (no context, no GPU): one table look-up turns a byte of 8 mask bits into 8 bytes of 0 / 255.
+extern "C" int md_unpack_mask_host(const uint8_t *bits, int32_t bits_pitch, int32_t width, int32_t rows, uint8_t *mask, int32_t mask_pitch)
+{
+    if (!bits || !mask || width < 1 || rows < 0 || bits_pitch < (width + 7) / 8 || mask_pitch < width) return MD_ERR_INVALID;
+    static const struct Lut {
+        uint64_t v[256];
+        Lut()
+        {
+            for (int b = 0; b < 256; b++) {
+                uint64_t x = 0;
+                for (int k = 0; k < 8; k++) if (b >> k & 1) x |= 0xffull << (8 * k);      // bit k -> byte k (little endian: pixel 8 i + k)
+                v[b] = x;
+            }
+        }
+    } lut;
+    const int full = width >> 3, rest = width & 7;
+    for (int y = 0; y < rows; y++) {
+        const uint8_t *src = bits + (size_t)y * bits_pitch;
+        uint8_t *dst = mask + (size_t)y * mask_pitch;
+        for (int i = 0; i < full; i++) memcpy(dst + 8 * i, &lut.v[src[i]], 8);
+        if (rest) memcpy(dst + 8 * full, &lut.v[src[full]], rest);
+    }
+    return MD_OK;
+}
+
 // ---- measurement hook ----------------------------------------------------------------------------------------------------
 extern "C" int md_profile(md_ctx *ctx, int enable)
 {

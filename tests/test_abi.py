@@ -91,3 +91,19 @@ def test_product_never_imports_oracle():
     # and the shared library has no dependency on it
     out = subprocess.run(["ldd", os.path.join(pkg, "lib", "libmotion_b200.so")], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_unpack_mask_host_matches_numpy():
+    """md_unpack_mask_host is pure host code (runs without a GPU): packed mask bits, LSB first, -> bytes 0 / 255."""
+    import numpy as np
+    from motion_detection_b200 import capi
+    rng = np.random.default_rng(3)
+    for w in (1, 7, 8, 9, 64, 333, 1920):
+        pitch = (w + 7) // 8 + 2
+        bits = rng.integers(0, 256, (2, 5, pitch), dtype=np.uint8)
+        ref = np.unpackbits(bits, axis=-1, bitorder="little")[..., :w] * np.uint8(255)
+        assert np.array_equal(capi.unpack_mask(bits, w), ref), w
+    one = np.zeros((1, 1), np.uint8)
+    out = np.zeros((1, 16), np.uint8)
+    assert capi.lib().md_unpack_mask_host(capi._ptr(one), 1, 16, 1, capi._ptr(out), 16) == -1      # bits_pitch too small: MD_ERR_INVALID
+    assert capi.lib().md_unpack_mask_host(None, 1, 8, 1, capi._ptr(out), 16) == -1
