@@ -107,3 +107,22 @@ def test_unpack_mask_host_matches_numpy():
     out = np.zeros((1, 16), np.uint8)
     assert capi.lib().md_unpack_mask_host(capi._ptr(one), 1, 16, 1, capi._ptr(out), 16) == -1      # bits_pitch too small: MD_ERR_INVALID
     assert capi.lib().md_unpack_mask_host(None, 1, 8, 1, capi._ptr(out), 16) == -1
+
+
+def test_pipeline_snippet_of_integration_md_compiles_as_c99(tmp_path):
+    """The two-contexts loop INTEGRATION.md shows (MD_MEM_HOST_ASYNC + md_set_pair_index) is valid C against the header."""
+    import re
+    import subprocess
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"```c\n(md_ctx \*lane\[2\];.*?)```", text, re.S)
+    assert m, "pipeline snippet not found in INTEGRATION.md"
+    body = m.group(1).replace("md_ctx *lane[2];", "", 1)
+    src = tmp_path / "snip.c"
+    src.write_text(
+        "#include <stddef.h>\n#include \"motion_b200.h\"\n"
+        "static void consume(md_outputs o) { (void)o; }\n"
+        "int run(md_ctx *lane[2], const uint8_t *clip, int B, int pitch, long long frame_bytes, md_outputs out[2], int nbatches)\n{\n"
+        + body + "    return 0;\n}\n")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
